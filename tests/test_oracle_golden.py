@@ -1,0 +1,170 @@
+"""The oracles (oracle/sem_oracle.py, oracle/sem_oracle.c) against the golden vectors produced by the
+unmodified reference (tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names, mt_doubles
+from oracle import sem_oracle as so
+
+MODEL_OF = {"sir": 0, "seir": 1, "subgroups": 2}
+
+
+# ---------------------------------------------------------------- SSA (gillespie_algo.py)
+@pytest.mark.parametrize("name", golden_names("ssa_"))
+def test_ssa_python_oracle_bit_exact(name):
+    g = golden(name)
+    model = str(g["model"])
+    st = so.MTStream(g["mt_key"], g["mt_pos"])
+    tmax = float(g["max_time"])
+    if model == "sir":
+        _, _, t, s = so.ssa_sir(g["population"], g["theta"], tmax, st, True)
+    elif model == "seir":
+        _, _, t, s = so.ssa_seir(g["population"], g["theta"], tmax, st, True)
+    else:
+        G = g["population"].shape[0]
+        th = g["theta"]
+        _, _, t, s = so.ssa_subgroups(g["population"], th[:G * G].reshape(G, G), th[-1], tmax, st, True)
+    assert np.array_equal(t, g["times"])
+    assert np.array_equal(s.reshape(g["states"].shape), g["states"])
+
+
+@pytest.mark.parametrize("name", golden_names("ssa_"))
+def test_ssa_c_oracle_bit_exact(name, c_oracle):
+    g = golden(name)
+    model = MODEL_OF[str(g["model"])]
+    pop = g["population"]
+    G = pop.shape[0] if model == 2 else 1
+    n_ev = g["times"].size - 1
+    u = mt_doubles(g["mt_key"], g["mt_pos"], 2 * (n_ev + 2))
+    out = c_oracle.ssa(model, G, pop, g["theta"], float(g["max_time"]), arith=0, u=u, max_rec=n_ev + 8)
+    assert out["n_rec"] == n_ev + 1
+    assert np.array_equal(out["times"], g["times"])          # same libm log => bit-equal times
+    assert np.array_equal(out["states"], g["states"])
+    # FAST arithmetic: same integer path, times to a few ulp
+    out2 = c_oracle.ssa(model, G, pop, g["theta"], float(g["max_time"]), arith=1, u=u, max_rec=n_ev + 8)
+    assert np.array_equal(out2["states"], g["states"])
+    np.testing.assert_allclose(out2["times"], g["times"], rtol=1e-13, atol=0)
+
+
+# ---------------------------------------------------------------- particle filter (pmcmc.py:123-233)
+PF_CASES = [n for n in golden_names("pf_") if n != "pf_sir_collapse"]
+
+
+@pytest.mark.parametrize("name", PF_CASES)
+def test_pf_python_oracle_bit_exact(name):
+    g = golden(name)
+    if int(g["n_particles"]) > 200:
+        pytest.skip("python oracle is slow; covered by the C oracle")
+    st = so.MTStream(g["mt_key"], g["mt_pos"])
+    out = so.particle_filter(g["Y"], so.MODEL_IDS[str(g["model"])], g["theta"], bool(g["observations"]),
+                             float(g["probs"]), g["hidden_process"][0], st)
+    assert not out["collapsed"]
+    assert np.array_equal(out["hidden_process"], g["hidden_process"])
+    assert np.array_equal(out["ancestry_matrix"], g["ancestry_matrix"])
+    assert np.array_equal(out["zetas"], g["zetas"])
+
+
+def run_c_pf_flat(c_oracle, g, arith=0):
+    model = so.MODEL_IDS[str(g["model"])]
+    N = int(g["n_particles"])
+    G = g["mu"].size if model >= 2 else 1
+    T = g["Y"].shape[0]
+    n = 4096
+    while True:
+        flat = mt_doubles(g["mt_key"], g["mt_pos"], n)
+        try:
+            out = c_oracle.pf_run(model, g["Y"], g["theta"], bool(g["observations"]), float(g["probs"]), N, G=G,
+                                  arith=arith, X0=g["hidden_process"][0], flat_u=flat, want_logw=True)
+            return out, flat
+        except RuntimeError:
+            n *= 4
+
+
+@pytest.mark.parametrize("name", PF_CASES)
+def test_pf_c_oracle_vs_reference(name, c_oracle):
+    g = golden(name)
+    out, flat = run_c_pf_flat(c_oracle, g)
+    assert out["collapsed"] == 0
+    assert np.array_equal(out["X_hist"], g["hidden_process"].astype(np.int32))       # trajectories bit-exact
+    assert np.array_equal(out["ancestry"], g["ancestry_matrix"].astype(np.int32))    # resampling indices bit-exact
+    np.testing.assert_allclose(out["log_zetas"], np.log(g["zetas"]), rtol=1e-9, atol=1e-12)
+    # per-particle CSR replay reproduces the flat replay
+    ssa_u, off = c_oracle.flat_to_csr(flat, out["ssa_start"], out["ssa_end"])
+    model = so.MODEL_IDS[str(g["model"])]
+    G = g["mu"].size if model >= 2 else 1
+    out2 = c_oracle.pf_run(model, g["Y"], g["theta"], bool(g["observations"]), float(g["probs"]),
+                           int(g["n_particles"]), G=G, X0=g["hidden_process"][0], res_u=out["res_u"], ssa_u=ssa_u,
+                           ssa_off=off)
+    assert np.array_equal(out2["X_hist"], out["X_hist"]) and np.array_equal(out2["ancestry"], out["ancestry"])
+    assert np.array_equal(out2["log_zetas"], out["log_zetas"])
+
+
+def test_pf_collapse(c_oracle):
+    g = golden("pf_sir_collapse")
+    N = int(g["n_particles"])
+    np.random.seed(int(g["seed"]))
+    I0 = np.random.poisson(g["mu"][0], N)                 # pmcmc.py:157
+    X0 = np.stack([int(g["n_population"][0]) - I0, I0, 0 * I0], 1)
+    flat = mt_doubles(g["mt_key"], g["mt_pos"], 4096)
+    out = c_oracle.pf_run(0, g["Y"], g["theta"], False, float(g["probs"]), N, X0=X0, flat_u=flat)
+    assert out["collapsed"] == 1                          # reference returns (None,None,None), pmcmc.py:191-192
+    st = so.MTStream(g["mt_key"], g["mt_pos"])
+    assert so.particle_filter(g["Y"], 0, g["theta"], False, float(g["probs"]), X0, st)["collapsed"]
+
+
+@pytest.mark.parametrize("name", golden_names("path_"))
+def test_path_sampler(name, c_oracle):
+    g = golden(name)
+    src = golden(str(g["source"]))
+    tr = so.particle_path_sampler(src["hidden_process"], src["ancestry_matrix"], int(g["chosen"]))
+    assert np.array_equal(tr, g["trajectory"])
+    tr_c = c_oracle.path_sample(src["hidden_process"].astype(np.int32), src["ancestry_matrix"].astype(np.int32),
+                                int(g["chosen"]))
+    assert np.array_equal(tr_c, g["trajectory"].astype(np.int32))
+
+
+# ---------------------------------------------------------------- observation weights (pmcmc.py:178-181)
+def test_weights_known_answers(c_oracle):
+    g = golden("weights_known_answers")
+    lp = c_oracle.binom_logpmf(g["binom_k"], g["binom_n"], g["binom_p"])
+    ref = g["binom_pmf"]
+    zero = ref == 0
+    assert np.all(np.isneginf(lp[zero & (g["binom_k"] != np.floor(g["binom_k"]))]))
+    assert np.all(np.exp(lp[zero]) == 0)                                   # support / underflow agree
+    np.testing.assert_allclose(np.exp(lp[~zero]), ref[~zero], rtol=2e-12)   # vs scipy/Boost
+    big = ref > 1e-300
+    np.testing.assert_allclose(lp[big], np.log(ref[big]), rtol=1e-11, atol=1e-11)
+    ln = c_oracle.norm_logpdf(g["norm_y"], g["norm_x"], g["norm_probs"])
+    ok = g["norm_pdf"] > 1e-300
+    np.testing.assert_allclose(ln[ok], np.log(g["norm_pdf"][ok]), rtol=1e-12, atol=1e-12)
+
+
+# ---------------------------------------------------------------- ABC (abc_algo.py)
+def test_abc_python_and_c(c_oracle):
+    g = golden("abc_sir_small")
+    obs = g["observed"]
+    n = g["distance"].size
+    streams, offs = [], [0]
+    for i in range(n):
+        st = so.MTStream(g["mt_key"][i], g["mt_pos"][i])
+        tr, d = so.abc_trial(obs, g["theta"][i, 0], g["theta"][i, 1], g["n_start"][i], st)
+        assert d == g["distance"][i]
+        assert np.array_equal(tr[:, 2], g["I_sim"][i]) and np.array_equal(tr[:, 3], g["R_sim"][i])
+        streams.append(np.array(st.log)); offs.append(offs[-1] + len(st.log))
+    out = c_oracle.abc_trials(obs, n, float(g["threshold"]), theta=g["theta"], n_start=g["n_start"],
+                              ssa_u=np.concatenate(streams), ssa_off=np.array(offs))
+    np.testing.assert_allclose(out["distance"], g["distance"], rtol=1e-13)
+    assert np.array_equal(out["traj"][:, :, 1], g["I_sim"].astype(np.int32))
+    assert np.array_equal(out["traj"][:, :, 2], g["R_sim"].astype(np.int32))
+    acc = out["distance"] <= float(g["threshold"])
+    assert np.array_equal(out["theta"][acc, 0], g["post_beta"]) and np.array_equal(out["theta"][acc, 1], g["post_gamma"])
+    assert np.array_equal(out["traj"][acc], g["trajectories"][:, :, 1:].astype(np.int32))
+    assert np.array_equal(g["trajectories"][0, :, 0], np.arange(obs.shape[0]))
+
+
+# ---------------------------------------------------------------- Philox known answers (Random123 kat_vectors)
+def test_philox_known_answers(c_oracle):
+    assert c_oracle.philox4x32([0, 0, 0, 0], [0, 0]) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert c_oracle.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert c_oracle.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
