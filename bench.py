@@ -1,0 +1,286 @@
+#!/usr/bin/env python
+"""Benchmark of the particle-filter hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one pass of the bootstrap particle filter (X_0 init, then T-1 x [weigh, accumulate likelihood,
+resample, gather, Gillespie-SSA propagate]) = one PMCMC likelihood evaluation, on the BASELINE.json metric
+workload: SIR, population 1e4, 1e5 particles, 100 observation intervals (workloads.HEADLINE).
+Metric: particle-steps/s (one particle advanced across one observation interval, including its share of
+weighting + resampling).  Prints ONE JSON line (rank 0).
+
+N > 1 (torchrun): every rank runs its own independent filter (independent PMCMC chains shard trivially,
+SURVEY 8(e)(2)); no data-path collective; weak scaling; value = all ranks' particle-steps / max-over-ranks time.
+
+--impl reference: the reference's CPU algorithm for the same path, timed on this box's host cores.  The reference
+itself is pure Python and cannot travel to the GPU box, so this arm runs its C restatement (oracle/sem_oracle.c,
+pinned bit-exact to the reference's outputs by tests/golden) with all host threads on a bounded sample of the
+same workload.  BASELINE.md holds the Python reference's own measured rate (~220 particle-steps/s/core).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import workloads  # noqa: E402
+
+I_ALG = 128            # declared thread-instructions per SSA event, SIR fp64; see DESIGN.md
+B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
+LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), float(p.get("sm_max_mhz", 1965.0)), "measured"
+    except Exception:
+        return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.samples, self.reasons, self.max_mhz = index, False, [], set(), None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {getattr(nv, k): k.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+                     for k in dir(nv) if k.startswith("nvmlClocksThrottleReason") and k not in
+                     ("nvmlClocksThrottleReasonNone", "nvmlClocksThrottleReasonAll")}
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                    for bit, nm in names.items():
+                        if bit and (r & bit):
+                            self.reasons.add(nm)
+                except Exception:
+                    pass
+                time.sleep(0.02)
+        except Exception as e:      # NVML unavailable: report it rather than inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "samples": len(s),
+                "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(Y, w, n_particles, threads, seed=1):
+    """C restatement of the reference (oracle/sem_oracle.c) on the host cores: bounded sample of the workload."""
+    from oracle import c_oracle as co
+    co.build()
+    t0 = time.perf_counter()
+    o = co.pf_run(0, Y, list(w["theta"]), w["observations"], w["probs"], n_particles, resampler=1, arith=0, seed=seed,
+                  mu=[w["mu"]], npop=[w["n_population"]], n_threads=threads)
+    dt = time.perf_counter() - t0
+    T = Y.shape[0]
+    used = threads if threads > 0 else co.lib().so_num_threads()
+    return dict(value=n_particles * (T - 1) / dt, unit="particle-steps/s", cores=used, kind="port",
+                sample=f"{n_particles} particles x {T - 1} steps of the same workload, reference fp64 operation order, "
+                       f"{o['n_events']} SSA events in {dt:.2f} s",
+                events_per_s=o["n_events"] / dt, seconds=dt)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = workloads.HEADLINE
+    Y = workloads.headline_Y()
+    n_sample = 10_000
+    T = Y.shape[0]
+    for i in range(args.warmup):
+        cpu_baseline(Y, w, 1000, 0, seed=100 + i)
+    t_tot, last = 0.0, None
+    for i in range(args.steps):
+        last = cpu_baseline(Y, w, n_sample, 0, seed=i)
+        t_tot += last["seconds"]
+    value = args.steps * n_sample * (T - 1) / t_tot
+    cb = dict(value=value, unit="particle-steps/s", cores=last["cores"], kind="port",
+              sample=f"each step = {n_sample} particles x {T - 1} observation intervals of the {w['name']} workload "
+                     "(C restatement of the Python reference, all host threads)")
+    print(json.dumps({
+        "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": w["name"], "sample_particles": n_sample, "n_obs": T, "population": w["n_population"]},
+        "cpu_baseline": cb,
+        "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference is pure Python (cannot run on the GPU box); its measured rate in the build container is "
+                "~220 particle-steps/s/core (BASELINE.md); this arm is its C port, ~500x faster per core",
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--particles", type=int, default=None, help="override n_particles (not the headline then)")
+    ap.add_argument("--resampler", default="systematic")
+    ap.add_argument("--arith", default="fast")
+    ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    import sem_b200
+    from sem_b200 import engine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = dict(workloads.HEADLINE)
+    if args.particles:
+        w["n_particles"] = args.particles
+    Y = workloads.headline_Y()
+    T, N = Y.shape[0], w["n_particles"]
+    theta = np.array(w["theta"], dtype=np.float64)
+    K, W = args.steps, max(args.warmup, 3)
+
+    # ---------------------------------------------------------------- device-resident timing ("value")
+    cfg = engine.make_pf_config(0, N, T, probs=w["probs"], observations=w["observations"], resampler=args.resampler,
+                                arith=args.arith, seed=1234, filter_id0=rank * 4096, mu=[w["mu"]],
+                                n_population=[w["n_population"]], block_particles=args.block)
+    out = engine.alloc_pf_outputs(cfg, dev)
+    Yd = torch.from_numpy(Y).to(dev)
+    thd = torch.from_numpy(theta).to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def one_pass(i):
+        cfg.filter_id0 = (rank * 4096 + i) & 0xFFFFFF
+        return engine.run_pf(cfg, Yd, thd, out=out)
+
+    for i in range(W):
+        res = one_pass(i)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    events_total = 0
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()                                                    # L2 flush between timed iterations (untimed)
+        evs[i][0].record(stream)
+        res = one_pass(W + i)
+        evs[i][1].record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    dev_ms = sum(a.elapsed_time(b) for a, b in evs)
+    events_last = int(res.n_events.cpu()[0])
+    status = int(res.status.cpu()[0])
+    logz = float(res.log_zetas[0, -1].cpu())
+    assert status == 0, f"filter collapsed at step {status}"
+    t_max = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t_max.cpu()[0])
+    value = world * K * N * (T - 1) / (dev_ms_max / 1e3)
+
+    # ---------------------------------------------------------------- end-to-end through the public API
+    e2e = None
+    if not args.no_e2e:
+        np.random.seed(rank)
+        st = {}
+        n_it = max(4, min(K, 12))
+        sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=3, probs=w["probs"], n_particles=N,
+                               n_population=w["n_population"], mu=w["mu"], seed=77 + rank)          # warm-up
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=n_it, probs=w["probs"],
+                               n_particles=N, n_population=w["n_population"], mu=w["mu"], seed=99 + rank, stats=st,
+                               resampler=args.resampler, arith=args.arith)
+        torch.cuda.synchronize()
+        te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.cpu()[0])
+        runs = st["filter_runs"]
+        e2e = {"value": world * runs * N * (T - 1) / e2e_s, "unit": "particle-steps/s",
+               "h2d_bytes_per_step": int(theta.nbytes + Y.nbytes / runs), "d2h_bytes_per_step": int(8 + 4 + T * 3 * 4),
+               "api": "sem_b200.particle_mcmc (drop-in for pmcmc.py:251): host numpy in, host numpy out, one filter pass + "
+                      "path sample per MH iteration", "iterations": runs, "pmcmc_iters_per_s": world * runs / e2e_s}
+        # the other public call: particle_filter returning the reference's full (T,N,C)+(T,N) float64 history on the host
+        t0 = time.perf_counter()
+        z, H, A = sem_b200.particle_filter(Y, sem_b200.ModelType.SIR, theta, w["observations"], w["probs"], N,
+                                           w["n_population"], w["mu"], seed=5, resampler=args.resampler, arith=args.arith)
+        th = time.perf_counter() - t0
+        e2e["full_history"] = {"value": N * (T - 1) / th, "unit": "particle-steps/s", "d2h_bytes_per_step": int(H.nbytes + A.nbytes + z.nbytes),
+                               "api": "sem_b200.particle_filter (pmcmc.py:123) returning float64 numpy history", "per_gpu": True}
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    clocks = sampler.result()
+
+    if rank == 0:
+        hbm_peak, sm_max, how = measured_peaks()
+        f_sm = (clocks["sm_mhz"] or sm_max) * 1e6
+        per_gpu_ms = dev_ms / K
+        events_per_s = events_last / (per_gpu_ms / 1e3)
+        issue_peak = LANES * f_sm
+        roofline = {"bound": "issue", "kernel": "pf_step<SirModel>", "achieved": events_per_s * I_ALG / 1e9,
+                    "peak": issue_peak / 1e9, "unit": "Gthread-inst/s", "frac": events_per_s * I_ALG / issue_peak,
+                    "traffic": None, "events_per_s": events_per_s, "events_per_particle_step": events_last / (N * (T - 1)),
+                    "I_alg": I_ALG, "sm_mhz_used": f_sm / 1e6, "avg_launch_us": 1e3 * per_gpu_ms / T,
+                    "note": "SSA propagate is bound by SM instruction issue, not HBM (SURVEY 8(d)); peak = 148 SMs x 4 "
+                            "schedulers x 32 lanes x SM clock sampled during the run"}
+        hbm_ach = N * B_ALG / (per_gpu_ms / 1e3 / T) / 1e9
+        roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
+                        "traffic": None, "peak_source": how, "bytes_per_launch": N * B_ALG}
+        line = {
+            "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K,
+            "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": w["name"], "model": "SIR", "n_particles": N, "n_obs": T, "population": w["n_population"],
+                       "theta": list(theta), "obs_model": "binomial p=0.1", "resampler": args.resampler, "arith": args.arith,
+                       "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"{world} independent filters"},
+            "pmcmc_iters_per_s": world * K / (dev_ms_max / 1e3), "events_per_s": events_per_s * world,
+            "log_likelihood": logz, "gpu_launches": K * res.launches, "clocks": clocks,
+            "roofline": roofline, "roofline_hbm": roofline_hbm, "e2e": e2e, "wall_s_timed_region": t_wall,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(Y, w, 5000, 1)
+            cb.pop("seconds")
+            cb["python_reference_measured_in_build_container"] = "~220 particle-steps/s/core (BASELINE.md section 2)"
+            line["cpu_baseline"] = cb
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,186 @@
+/*
+ * sem_b200.h -- C ABI of the B200 (sm_100a) particle-filter / SSA / ABC engine.
+ *
+ * This is the drop-in boundary for the hot path of GeorgeEfstathiadis/Stochastic-Epidemic-Modelling.
+ * The reference is pure Python and has no FFI of its own; each entry point below replaces the body of
+ * one reference function (file:line given), and INTEGRATION.md shows the ctypes stub a maintainer
+ * would add to the reference to bind it.
+ *
+ * Conventions
+ *   - plain C types only; no torch / CUDA types in signatures (stream is an opaque void* = cudaStream_t).
+ *   - every pointer documented "device" is a CUDA device pointer owned by the caller; the library
+ *     allocates nothing persistent.  `workspace` is caller-allocated scratch of sem_pf_workspace_bytes().
+ *   - every call enqueues on `stream` and returns without synchronising, except the *_host variants,
+ *     which take host buffers, do their own staging and synchronise before returning.
+ *   - return value: 0 = ok, negative = error (sem_last_error() gives the text).  A collapsed filter is
+ *     NOT an error: it is reported through `status` (reference: pmcmc.py:191-192 returns (None,None,None)).
+ *   - thread-safe per stream; no global mutable state besides the thread-local error string.
+ *
+ * State layout in HBM (structure of arrays, int32):
+ *   X_hist   [n_filters][T][C][N]   compartment counts of every particle at every observation time
+ *   ancestry [n_filters][T][N]      parent index at the previous time (row 0 = 0), as pmcmc.py:193
+ *   log_zetas[n_filters][T]         log of the reference's running likelihood zetas[p] (pmcmc.py:183)
+ */
+#ifndef SEM_B200_H
+#define SEM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEM_ABI_VERSION 1
+#define SEM_MAX_GROUPS 4
+
+/* pmcmc.py:116-120 ModelType */
+enum { SEM_MODEL_SIR = 0, SEM_MODEL_SEIR = 1, SEM_MODEL_SIR_SUBGROUPS = 2, SEM_MODEL_SIR_SUBGROUPS2 = 3 };
+/* pmcmc.py:178-181: observations=False -> binomial pmf, observations=True -> normal pdf */
+enum { SEM_OBS_BINOMIAL = 0, SEM_OBS_NORMAL = 1 };
+/* pmcmc.py:188-190 is multinomial; systematic is the production resampler (one uniform per step) */
+enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
+/* fp64 operation order of one SSA event: the reference's own (gillespie_algo.py:38-39,62-63) or an
+ * algebraically equal form with a single division */
+enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1 };
+
+enum {
+    SEM_OK = 0,
+    SEM_ERR_INVALID = -1,   /* bad argument */
+    SEM_ERR_CUDA = -2,      /* CUDA runtime error */
+    SEM_ERR_REPLAY = -3,    /* replay buffer exhausted */
+    SEM_ERR_NO_DEVICE = -4  /* no sm_100 device */
+};
+
+int sem_abi_version(void);
+const char *sem_last_error(void);
+/* number of SMs / compute capability of the current device, <0 on error */
+int sem_device_info(int *sm_count, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Particle filter: replaces the body of particle_filter (pmcmc.py:123-233): X_0 initialisation,
+ * and for p = 1..T-1: weight X[p-1] against Y[p-1] (min over columns), accumulate the likelihood,
+ * resample, propagate every particle one observation interval with exact Gillespie SSA
+ * (gillespie_algo.py:10-233).  The whole time loop runs on the device, one launch per step.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sem_pf_config {
+    int32_t model;          /* SEM_MODEL_* */
+    int32_t obs_kind;       /* SEM_OBS_* */
+    int32_t resampler;      /* SEM_RESAMPLE_* */
+    int32_t arith;          /* SEM_ARITH_* */
+    int32_t n_particles;    /* N */
+    int32_t n_obs;          /* T = rows of Y */
+    int32_t n_groups;       /* G (1 for SIR/SEIR) */
+    int32_t n_obs_cols;     /* columns of Y: 3, 4, 3G or (SUBGROUPS2) 3 */
+    int32_t n_filters;      /* independent filters (chains / thetas) run side by side, >= 1 */
+    int32_t block_particles;/* particles per CTA, 0 = choose from N and the SM count */
+    int32_t store_history;  /* 1: write all T rows of X_hist/ancestry; 0: keep only two rows (ping-pong) */
+    int32_t reserved;
+    double probs;           /* p_obs (binomial) or noise ratio (normal), pmcmc.py:128 */
+    double dt;              /* observation interval, the reference uses 1 (pmcmc.py:205) */
+    uint64_t seed;          /* Philox key */
+    uint32_t filter_id0;    /* stream id of filter 0; filter f uses filter_id0 + f */
+    uint32_t reserved2;
+    double mu[SEM_MAX_GROUPS];           /* Poisson mean of I_0 per group (pmcmc.py:157,161,167) */
+    double n_population[SEM_MAX_GROUPS]; /* population per group (pmcmc.py:158,162,168) */
+} sem_pf_config;
+
+typedef struct sem_pf_buffers {
+    const double *Y;            /* device [T][n_obs_cols] */
+    const double *theta;        /* device [n_filters][P]; P = 2 (SIR: beta,gamma), 3 (SEIR: beta,alpha,gamma),
+                                   G*G+1 (subgroups: betas row-major [infector][susceptible], gamma) */
+    const int32_t *X0;          /* device [C][N] initial state shared by all filters, or NULL = draw
+                                   I_0 ~ Poisson(mu) on the device */
+    /* replay mode (all three NULL = Philox).  Uniforms in the reference's consumption order:        */
+    const double *replay_resample_u; /* device [T-1][N]: the N doubles np.random.choice draws at step p */
+    const double *replay_ssa_u;      /* device: per (step,particle) the (u1,u2) pairs of its SSA events */
+    const int64_t *replay_ssa_off;   /* device [(T-1)*N+1]: CSR offsets (in doubles) into replay_ssa_u */
+    int32_t *X_hist;            /* device, see layout above (T rows, or 2 if !store_history) */
+    int32_t *ancestry;          /* device */
+    double *log_zetas;          /* device [n_filters][T] */
+    int32_t *status;            /* device [n_filters]: 0 ok, p>0 collapsed at step p, -3 replay exhausted */
+    uint64_t *n_events;         /* device [n_filters] total SSA events drawn (incl. discarded overshoots) or NULL */
+    void *workspace;            /* device, sem_pf_workspace_bytes() */
+} sem_pf_buffers;
+
+size_t sem_pf_workspace_bytes(const sem_pf_config *cfg);
+/* number of int32 in X_hist / ancestry and doubles in log_zetas the caller must provide */
+size_t sem_pf_hist_elems(const sem_pf_config *cfg);
+size_t sem_pf_ancestry_elems(const sem_pf_config *cfg);
+/* launches made by one sem_pf_run (for launch accounting) */
+int sem_pf_launch_count(const sem_pf_config *cfg);
+int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream);
+
+/* Host-buffer variant (end-to-end call): Y, theta, X0 (may be NULL) and all outputs are HOST pointers;
+ * outputs may be NULL when not wanted.  X_hist_out is (T,N,C) float64 and ancestry_out (T,N) float64 exactly
+ * as pmcmc.py:151-152,233 returns them; zetas_out = exp(log_zetas).  Returns 0, >0 = collapsed at that step. */
+int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *theta, const int32_t *X0,
+                    double *log_zetas_out, double *zetas_out, double *hidden_process_out, double *ancestry_out,
+                    uint64_t *n_events_out);
+
+/* particle_path_sampler (pmcmc.py:236-248).  chosen < 0: pick uniformly with Philox(seed); exact = 0 keeps
+ * the reference's off-by-one ancestry indexing, 1 follows the true genealogy.  traj: device [T][C] int32. */
+int sem_path_sample(const int32_t *X_hist, const int32_t *ancestry, int32_t T, int32_t N, int32_t C,
+                    int32_t chosen, int32_t exact, uint64_t seed, uint32_t filter_id, int32_t *traj, void *stream);
+
+/* (T,C,N) int32 SoA history -> (T,N,C) float64 as the reference returns it (pmcmc.py:151); device pointers */
+int sem_hist_to_f64(const int32_t *X_hist, int32_t T, int32_t N, int32_t C, double *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Independent SSA runs: replaces sir_simulate / seir_simulate / sir_subgroups_simulate
+ * (gillespie_algo.py:10-75, 78-146, 148-233) for a batch of n_sims simulations.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sem_sim_config {
+    int32_t model, n_groups, arith, n_sims;
+    int32_t shared_theta;   /* 1: theta is [P] for all sims, 0: [n_sims][P] */
+    int32_t shared_x0;      /* 1: x0 is [C], 0: [n_sims][C] */
+    int64_t record_capacity;/* rows per sim in times/states (0 = last values only) */
+    double max_time;
+    uint64_t seed;
+    uint32_t sim_index0;    /* Philox item id of sim 0 */
+    uint32_t reserved;
+} sem_sim_config;
+
+/* x0 device int32; theta device; replay_u/replay_off device or NULL (Philox); x_out device [n_sims][C] int32;
+ * n_rows device [n_sims] int64 (events+1); times device [n_sims][cap] double, states [n_sims][cap][C] int32. */
+int sem_ssa_simulate(const sem_sim_config *cfg, const int32_t *x0, const double *theta, const double *replay_u,
+                     const int64_t *replay_off, int32_t *x_out, int64_t *n_rows, double *times, int32_t *states,
+                     void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * ABC rejection trials: replaces the trial loop body of abc_algo (abc_algo.py:33-99) for SIR:
+ * prior draw, Poisson-perturbed start, SSA, daily discretisation, L1 distance (abc_algo.py:10-13).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sem_abc_config {
+    int32_t n_days;         /* T = rows of observed_data */
+    int32_t arith;
+    int32_t early_reject;   /* stop a trial once its partial distance already exceeds threshold */
+    int32_t reserved;
+    int64_t n_trials;
+    uint64_t trial0;        /* id of the first trial (shards: rank r starts at r*n_trials) */
+    double threshold;
+    double prior[4];        /* beta lo,hi ; gamma lo,hi (abc_algo.py:36-37) */
+    uint64_t seed;
+} sem_abc_config;
+
+/* obs device [T][3] (S,I,R).  trial_ids device [n_trials] uint64 or NULL (= trial0 + i): lets accepted trials be
+ * re-simulated to emit their trajectories.  Replay (tests): theta_in [n][2], n_start_in [n][3] int64,
+ * replay_u / replay_off CSR; all NULL = Philox.  Outputs: theta_out device [n][2], distance device [n] (inf when
+ * rejected early), traj device [n][T][3] int32 or NULL, n_events device [1] or NULL, work_counter device [1] uint64
+ * scratch (zeroed by the call). */
+int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *trial_ids, const double *theta_in,
+                const int64_t *n_start_in, const double *replay_u, const int64_t *replay_off, double *theta_out,
+                double *distance, int32_t *traj, uint64_t *n_events, uint64_t *work_counter, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small exported pieces used by the parity tests (device-side evaluation of host arrays of length n).
+ * ---------------------------------------------------------------------------------------------- */
+int sem_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+int sem_test_binom_logpmf(const double *k, const double *n, const double *p, double *out, int64_t count);
+int sem_test_norm_logpdf(const double *y, const double *x, const double *probs, double *out, int64_t count);
+int sem_test_poisson(double mu, uint64_t seed, uint32_t domain, uint32_t c2, double *out, int64_t count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEM_B200_H */

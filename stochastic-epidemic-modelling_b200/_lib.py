@@ -1,0 +1,115 @@
+"""ctypes binding of libsem_b200.so (the C ABI declared in include/sem_b200.h).
+
+There is NO CPU fallback: if the CUDA library is missing or fails to load, every entry point raises.
+"""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsem_b200.so")
+
+SEM_MAX_GROUPS = 4
+MODEL_SIR, MODEL_SEIR, MODEL_SIR_SUBGROUPS, MODEL_SIR_SUBGROUPS2 = 0, 1, 2, 3
+OBS_BINOMIAL, OBS_NORMAL = 0, 1
+RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
+ARITH_REFERENCE, ARITH_FAST = 0, 1
+ERR_REPLAY = -3
+
+EXPORTS = [
+    "sem_abi_version", "sem_last_error", "sem_device_info",
+    "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
+    "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
+    "sem_ssa_simulate", "sem_abc_run",
+    "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson",
+]
+
+
+class PfConfig(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("obs_kind", C.c_int32), ("resampler", C.c_int32), ("arith", C.c_int32),
+        ("n_particles", C.c_int32), ("n_obs", C.c_int32), ("n_groups", C.c_int32), ("n_obs_cols", C.c_int32),
+        ("n_filters", C.c_int32), ("block_particles", C.c_int32), ("store_history", C.c_int32), ("reserved", C.c_int32),
+        ("probs", C.c_double), ("dt", C.c_double), ("seed", C.c_uint64), ("filter_id0", C.c_uint32),
+        ("reserved2", C.c_uint32), ("mu", C.c_double * SEM_MAX_GROUPS), ("n_population", C.c_double * SEM_MAX_GROUPS),
+    ]
+
+
+class PfBuffers(C.Structure):
+    _fields_ = [
+        ("Y", C.c_void_p), ("theta", C.c_void_p), ("X0", C.c_void_p),
+        ("replay_resample_u", C.c_void_p), ("replay_ssa_u", C.c_void_p), ("replay_ssa_off", C.c_void_p),
+        ("X_hist", C.c_void_p), ("ancestry", C.c_void_p), ("log_zetas", C.c_void_p), ("status", C.c_void_p),
+        ("n_events", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
+class SimConfig(C.Structure):
+    _fields_ = [
+        ("model", C.c_int32), ("n_groups", C.c_int32), ("arith", C.c_int32), ("n_sims", C.c_int32),
+        ("shared_theta", C.c_int32), ("shared_x0", C.c_int32), ("record_capacity", C.c_int64),
+        ("max_time", C.c_double), ("seed", C.c_uint64), ("sim_index0", C.c_uint32), ("reserved", C.c_uint32),
+    ]
+
+
+class AbcConfig(C.Structure):
+    _fields_ = [
+        ("n_days", C.c_int32), ("arith", C.c_int32), ("early_reject", C.c_int32), ("reserved", C.c_int32),
+        ("n_trials", C.c_int64), ("trial0", C.c_uint64), ("threshold", C.c_double), ("prior", C.c_double * 4),
+        ("seed", C.c_uint64),
+    ]
+
+
+class SemError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the CUDA library; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SemError(
+            f"{LIB_PATH} not found: build it with `python stochastic-epidemic-modelling_b200/build.py` "
+            "(nvcc, sm_100a). There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    L.sem_last_error.restype = C.c_char_p
+    L.sem_abi_version.restype = C.c_int
+    for name in ("sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems"):
+        getattr(L, name).restype = C.c_size_t
+        getattr(L, name).argtypes = [C.POINTER(PfConfig)]
+    L.sem_pf_launch_count.restype = C.c_int
+    L.sem_pf_launch_count.argtypes = [C.POINTER(PfConfig)]
+    L.sem_pf_run.restype = C.c_int
+    L.sem_pf_run.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p]
+    L.sem_pf_run_host.restype = C.c_int
+    L.sem_pf_run_host.argtypes = [C.POINTER(PfConfig)] + [C.c_void_p] * 8
+    L.sem_path_sample.restype = C.c_int
+    L.sem_path_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                  C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]
+    L.sem_hist_to_f64.restype = C.c_int
+    L.sem_hist_to_f64.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    L.sem_ssa_simulate.restype = C.c_int
+    L.sem_ssa_simulate.argtypes = [C.POINTER(SimConfig)] + [C.c_void_p] * 9
+    L.sem_abc_run.restype = C.c_int
+    L.sem_abc_run.argtypes = [C.POINTER(AbcConfig)] + [C.c_void_p] * 12
+    L.sem_device_info.restype = C.c_int
+    L.sem_device_info.argtypes = [C.POINTER(C.c_int)] * 3
+    L.sem_test_philox.restype = C.c_int
+    L.sem_test_binom_logpmf.restype = C.c_int
+    L.sem_test_norm_logpdf.restype = C.c_int
+    L.sem_test_poisson.restype = C.c_int
+    L.sem_test_poisson.argtypes = [C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64]
+    if L.sem_abi_version() != 1:
+        raise SemError("libsem_b200.so ABI version mismatch")
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc < 0:
+        raise SemError(f"{what} failed ({rc}): {load().sem_last_error().decode()}")
+    return rc

@@ -1,0 +1,333 @@
+// sem_common.cuh -- device-side building blocks shared by the particle-filter, ABC and simulate kernels.
+//   * Philox4x32-10 counter RNG and the stream layout (DESIGN.md "RNG streams")
+//   * uniform sources (Philox / replay buffer)
+//   * Poisson sampler for X_0 and the ABC start (pmcmc.py:157-169, abc_algo.py:39-40)
+//   * observation log-weights: binomial (Loader saddle point) and normal (pmcmc.py:178-181)
+//   * epidemic models: reaction tables of gillespie_algo.py in the reference's reaction order
+//   * the Gillespie direct-method loop (gillespie_algo.py:48-70)
+// sm_100a only.  All arithmetic that decides an integer outcome uses explicit round-to-nearest intrinsics so
+// that FMA contraction can never change a trajectory relative to the CPU oracle.
+#pragma once
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/sem_b200.h"
+
+namespace sem {
+
+enum : uint32_t { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7 };
+
+// ------------------------------------------------------------------------------------------ Philox4x32-10
+struct PhiloxKey { uint32_t k0, k1; };
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
+    uint32_t k0 = key.k0, k1 = key.k1;
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;     // IMAD.WIDE.U32
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0; // LOP3
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c0, c1, c2, c3);
+}
+
+// two words -> double in [1,2) carrying 52 random mantissa bits; u = d - 1 in [0,1), and 1 - u = 2 - d exactly
+__device__ __forceinline__ double bits_to_d12(uint32_t lo, uint32_t hi) {
+    return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
+}
+
+__host__ __device__ __forceinline__ uint32_t stream_word(uint32_t domain, uint32_t fid) { return (domain << 24) | (fid & 0xFFFFFFu); }
+
+// A sequential source of (u1,u2) pairs: one Philox call, or two doubles of a replay buffer.
+template <bool REPLAY>
+struct PairSource;
+
+template <>
+struct PairSource<false> {
+    PhiloxKey key; uint32_t k, c1, c2, c3;
+    __device__ __forceinline__ void init(PhiloxKey key_, uint32_t c1_, uint32_t c2_, uint32_t c3_) { key = key_; k = 0; c1 = c1_; c2 = c2_; c3 = c3_; }
+    __device__ __forceinline__ uint4 raw() { return philox4x32_10(k++, c1, c2, c3, key); }
+    __device__ __forceinline__ bool next(double &u1, double &u2) {
+        const uint4 w = raw();
+        u1 = bits_to_d12(w.x, w.y) - 1.0; u2 = bits_to_d12(w.z, w.w) - 1.0;
+        return true;
+    }
+};
+
+template <>
+struct PairSource<true> {
+    const double *u; long long pos, end;
+    __device__ __forceinline__ void init(const double *u_, long long pos_, long long end_) { u = u_; pos = pos_; end = end_; }
+    __device__ __forceinline__ bool next(double &u1, double &u2) {
+        if (pos + 2 > end) { u1 = 0.5; u2 = 0.5; return false; }
+        u1 = u[pos]; u2 = u[pos + 1]; pos += 2;
+        return true;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ log-weights
+static __constant__ double kSfe[16] = {0.0, 0.08106146679532726, 0.04134069595540929, 0.02767792568499834,
+    0.02079067210376509, 0.01664469118982119, 0.01387612882307075, 0.01189670994589177,
+    0.01041126526197209, 0.009255462182712733, 0.008330563433362871, 0.007573675487951841,
+    0.006942840107209530, 0.006408994188004207, 0.005951370112758848, 0.005554733551962801};
+
+__device__ __forceinline__ double stirlerr(double n) {   // log(n!) - log(sqrt(2 pi n)(n/e)^n), Loader (2000)
+    const double S0 = 1.0 / 12, S1 = 1.0 / 360, S2 = 1.0 / 1260, S3 = 1.0 / 1680, S4 = 1.0 / 1188;
+    if (n < 16) return kSfe[(int)n];
+    const double nn = n * n;
+    if (n > 500) return (S0 - S1 / nn) / n;
+    if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
+    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+}
+
+__device__ __forceinline__ double bd0(double x, double np) {   // x log(x/np) + np - x, stable near x = np
+    if (fabs(x - np) < 0.1 * (x + np)) {
+        double v = (x - np) / (x + np), s = (x - np) * v, ej = 2 * x * v;
+        v = v * v;
+        for (int j = 1; j < 1000; j++) {
+            ej *= v;
+            const double s1 = s + ej / (2 * j + 1);
+            if (s1 == s) return s1;
+            s = s1;
+        }
+    }
+    return x * log(x / np) + np - x;
+}
+
+// log binom.pmf(k | n, p) with scipy's support rules (pmcmc.py:179): k<0, k>n, non-integer k -> -inf
+static __device__ __noinline__ double binom_logpmf(double k, double n, double p) {
+    if (!(k >= 0) || k > n || k != floor(k)) return -CUDART_INF;
+    const double q = 1 - p;
+    if (p == 0) return k == 0 ? 0.0 : -CUDART_INF;
+    if (q == 0) return k == n ? 0.0 : -CUDART_INF;
+    if (k == 0) {
+        if (n == 0) return 0.0;
+        return p < 0.1 ? -bd0(n, n * q) - n * p : n * log(q);
+    }
+    if (k == n) return q < 0.1 ? -bd0(n, n * p) - n * q : n * log(p);
+    const double lc = stirlerr(n) - stirlerr(k) - stirlerr(n - k) - bd0(k, n * p) - bd0(n - k, n * q);
+    const double lf = 1.8378770664093453 + log(k) + log1p(-k / n);
+    return lc - 0.5 * lf;
+}
+
+// log norm.pdf(y | loc = x, scale = probs*x + 1e-4)  (pmcmc.py:181)
+__device__ __forceinline__ double norm_logpdf(double y, double x, double probs) {
+    const double sd = probs * x + .0001, z = (y - x) / sd;
+    return -0.5 * z * z - log(sd) - 0.9189385332046727;
+}
+
+__device__ __forceinline__ double log_factorial(double k) {
+    if (k < 2) return 0.0;
+    return k * log(k) - k + 0.5 * log(6.283185307179586 * k) + stirlerr(k);
+}
+
+// Poisson(mu): mu < 10 sequential inversion with one uniform, else Hormann's PTRS transformed rejection.
+template <class Src>
+__device__ __noinline__ double poisson_draw(Src &src, double mu) {
+    double u1, u2;
+    if (!(mu > 0)) return 0.0;
+    if (mu < 10) {
+        src.next(u1, u2);
+        double pk = exp(-mu), F = pk, k = 0;
+        while (u1 > F && k < 1000) { k += 1; pk *= mu / k; F += pk; }
+        return k;
+    }
+    const double slam = sqrt(mu), loglam = log(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double invalpha = 1.1239 + 1.1328 / (b - 3.4), vr = 0.9277 - 3.6224 / (b - 2);
+    for (;;) {
+        src.next(u1, u2);
+        const double U = u1 - 0.5, V = u2, us = 0.5 - fabs(U);
+        const double k = floor((2 * a / us + b) * U + mu + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0 || (us < 0.013 && V > us)) continue;
+        if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -mu + k * loglam - log_factorial(k)) return k;
+    }
+}
+
+// ------------------------------------------------------------------------------------------ models
+// State is kept as fp64 integers in registers (exact up to 2^53); converted to int32 at observation boundaries.
+// rates<ARITH>() fills r[] in the reference's reaction order; REF divides by N per event like
+// gillespie_algo.py:38, FAST multiplies by the hoisted beta/N.
+
+struct SirModel {
+    static constexpr int C = 3, R = 2, NTHETA = 2, G = 1;
+    double beta, gamma, N, bN;
+    __device__ __forceinline__ void setup(const double *th, const double *x) {
+        beta = th[0]; gamma = th[1];
+        N = __dadd_rn(__dadd_rn(x[0], x[1]), x[2]);                      // gillespie_algo.py:35
+        bN = __dmul_rn(beta, __ddiv_rn(1.0, N));
+    }
+    __device__ __forceinline__ bool alive(const double *x) const { return x[1] > 0; }      // :48
+    template <int ARITH>
+    __device__ __forceinline__ void rates(const double *x, double *r) const {
+        if (ARITH == SEM_ARITH_REFERENCE) r[0] = __ddiv_rn(__dmul_rn(__dmul_rn(beta, x[0]), x[1]), N);   // :38
+        else r[0] = __dmul_rn(__dmul_rn(bN, x[0]), x[1]);
+        r[1] = __dmul_rn(gamma, x[1]);                                                                  // :39
+    }
+    __device__ __forceinline__ void apply(double *x, int j) const {                                     // :43-46
+        const bool inf = (j == 0);
+        x[0] = inf ? x[0] - 1.0 : x[0];
+        x[1] = inf ? x[1] + 1.0 : x[1] - 1.0;
+        x[2] = inf ? x[2] : x[2] + 1.0;
+    }
+};
+
+struct SeirModel {
+    static constexpr int C = 4, R = 3, NTHETA = 3, G = 1;
+    double beta, alpha, gamma, N, bN;
+    __device__ __forceinline__ void setup(const double *th, const double *x) {
+        beta = th[0]; alpha = th[1]; gamma = th[2];                                        // :92
+        N = __dadd_rn(__dadd_rn(__dadd_rn(x[0], x[1]), x[2]), x[3]);                       // :104
+        bN = __dmul_rn(beta, __ddiv_rn(1.0, N));
+    }
+    __device__ __forceinline__ bool alive(const double *x) const { return x[1] > 0 || x[2] > 0; }   // :119
+    template <int ARITH>
+    __device__ __forceinline__ void rates(const double *x, double *r) const {
+        if (ARITH == SEM_ARITH_REFERENCE) r[0] = __ddiv_rn(__dmul_rn(__dmul_rn(beta, x[0]), x[2]), N);   // :107
+        else r[0] = __dmul_rn(__dmul_rn(bN, x[0]), x[2]);
+        r[1] = __dmul_rn(alpha, x[1]);                                                                  // :108
+        r[2] = __dmul_rn(gamma, x[2]);                                                                  // :109
+    }
+    __device__ __forceinline__ void apply(double *x, int j) const {                                     // :113-117
+        x[0] = (j == 0) ? x[0] - 1.0 : x[0];
+        x[1] = (j == 0) ? x[1] + 1.0 : ((j == 1) ? x[1] - 1.0 : x[1]);
+        x[2] = (j == 1) ? x[2] + 1.0 : ((j == 2) ? x[2] - 1.0 : x[2]);
+        x[3] = (j == 2) ? x[3] + 1.0 : x[3];
+    }
+};
+
+template <int G_>
+struct SubModel {
+    static constexpr int G = G_, C = 3 * G_, R = G_ * G_ + G_, NTHETA = G_ * G_ + 1;
+    double betas[G_ * G_], bN[G_ * G_], gamma, N;
+    __device__ __forceinline__ void setup(const double *th, const double *x) {
+#pragma unroll
+        for (int i = 0; i < G * G; i++) betas[i] = th[i];                 // betas[a*G+b]: infector a -> susceptible b (:182)
+        gamma = th[G * G];
+        double tot = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; g++) {                                      // :176 per-group builtin sum, then sum(N) (:182)
+            const double ng = __dadd_rn(__dadd_rn(__dadd_rn(0.0, x[3 * g]), x[3 * g + 1]), x[3 * g + 2]);
+            tot = __dadd_rn(tot, ng);
+        }
+        N = tot;
+        const double invN = __ddiv_rn(1.0, N);
+#pragma unroll
+        for (int i = 0; i < G * G; i++) bN[i] = __dmul_rn(betas[i], invN);
+    }
+    __device__ __forceinline__ bool alive(const double *x) const {        // :192-193
+        double inf = 0.0;
+#pragma unroll
+        for (int g = 0; g < G; g++) inf = __dadd_rn(inf, x[3 * g + 1]);
+        return inf > 0;
+    }
+    template <int ARITH>
+    __device__ __forceinline__ void rates(const double *x, double *r) const {
+#pragma unroll
+        for (int a = 0; a < G; a++) {
+#pragma unroll
+            for (int b = 0; b < G; b++) {
+                if (ARITH == SEM_ARITH_REFERENCE)
+                    r[a * (G + 1) + b] = __ddiv_rn(__dmul_rn(__dmul_rn(betas[a * G + b], x[3 * b]), x[3 * a + 1]), N);
+                else
+                    r[a * (G + 1) + b] = __dmul_rn(__dmul_rn(bN[a * G + b], x[3 * b]), x[3 * a + 1]);
+            }
+            r[a * (G + 1) + G] = __dmul_rn(gamma, x[3 * a + 1]);         // :184
+        }
+    }
+    __device__ __forceinline__ void apply(double *x, int j) const {       // :183,185
+        const int a = j / (G + 1), k = j - a * (G + 1);
+#pragma unroll
+        for (int g = 0; g < G; g++) {
+            const bool infect = (k == g);                   // susceptible of group g infected (by group a)
+            const bool recover = (k == G) && (a == g);
+            x[3 * g] = infect ? x[3 * g] - 1.0 : x[3 * g];
+            x[3 * g + 1] = infect ? x[3 * g + 1] + 1.0 : (recover ? x[3 * g + 1] - 1.0 : x[3 * g + 1]);
+            x[3 * g + 2] = recover ? x[3 * g + 2] + 1.0 : x[3 * g + 2];
+        }
+    }
+};
+
+// One Gillespie draw (split so that no uniform is consumed when the total propensity is not positive):
+//   ssa_total : propensities r[] in the reference's reaction order and a0 = builtin sum() = 0 + r0 + r1 ...
+//   ssa_pick  : waiting time tau and reaction index j from (u1,u2).
+// REF reproduces numpy's legacy exponential / choice arithmetic (gillespie_algo.py:62-63):
+//   tau = -log(1-u1) * (1/a0);  p = r/a0; cdf = cumsum(p); cdf /= cdf[-1]; j = #(cdf <= u2)
+// FAST: tau = -log(1-u1)/a0;  j = #(prefix(r) <= u2*a0)
+template <class Model, int ARITH>
+__device__ __forceinline__ double ssa_total(const Model &m, const double *x, double *r) {
+    m.template rates<ARITH>(x, r);
+    double a0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < Model::R; i++) a0 = __dadd_rn(a0, r[i]);
+    return a0;
+}
+
+template <class Model, int ARITH>
+__device__ __forceinline__ void ssa_pick(const double *r, double a0, double u1, double u2, double &tau, int &j) {
+    const double E = -log(__dsub_rn(1.0, u1));
+    j = 0;
+    if (ARITH == SEM_ARITH_REFERENCE) {
+        tau = __dmul_rn(E, __ddiv_rn(1.0, a0));
+        double cdf[Model::R], acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < Model::R; i++) { acc = __dadd_rn(acc, __ddiv_rn(r[i], a0)); cdf[i] = acc; }
+#pragma unroll
+        for (int i = 0; i < Model::R; i++) j += (__ddiv_rn(cdf[i], acc) <= u2) ? 1 : 0;
+        j = min(j, Model::R - 1);
+    } else {
+        tau = __ddiv_rn(E, a0);
+        const double v = __dmul_rn(u2, a0);
+        double acc = 0.0;
+#pragma unroll
+        for (int i = 0; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
+    }
+}
+
+// Direct method from t = 0 to max_time (gillespie_algo.py:48-70).  Both uniforms are drawn before the
+// overshoot test, so the discarded last event consumes a pair too (:62-66).  Returns pairs drawn, or -1 when a
+// replay buffer ran dry.  Rec(t, x) is called after every accepted event.
+template <class Model, int ARITH, bool REPLAY, class Rec>
+__device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src, Rec rec) {
+    double t = 0.0;
+    long long pairs = 0;
+    while (m.alive(x)) {
+        double r[Model::R], u1, u2, tau;
+        int j;
+        const double a0 = ssa_total<Model, ARITH>(m, x, r);
+        if (!(a0 > 0)) break;                                              // (the reference would raise inside choice())
+        if (!src.next(u1, u2)) return -1;
+        pairs++;
+        ssa_pick<Model, ARITH>(r, a0, u1, u2, tau, j);
+        const double tn = __dadd_rn(t, tau);
+        if (tn > max_time) break;                                          // :65
+        t = tn;
+        m.apply(x, j);
+        rec(t, x);
+    }
+    return pairs;
+}
+
+struct NoRec { __device__ __forceinline__ void operator()(double, const double *) const {} };
+
+// ------------------------------------------------------------------------------------------ block primitives
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_xor_d(double v, int d) { return __shfl_xor_sync(0xffffffffu, v, d); }
+
+__device__ __forceinline__ double warp_max_d(double v) {
+#pragma unroll
+    for (int d = 16; d; d >>= 1) v = fmax(v, shfl_xor_d(v, d));
+    return v;
+}
+__device__ __forceinline__ double warp_incl_scan_d(double v, int lane) {
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const double o = shfl_up_d(v, d); if (lane >= d) v += o; }
+    return v;
+}
+
+}  // namespace sem

@@ -1,0 +1,465 @@
+// sem_pf.cu -- bootstrap particle filter on the device (replaces pmcmc.py:123-233).
+//
+// One kernel launch per observation step p (the launch boundary is the resampling barrier):
+//   pf_step(p):  [resample]   ancestor a_j = first i with cdf_{p-1}(i) > u_j * total      (pmcmc.py:187-193)
+//                [gather]     x = X[p-1][:, a_j]   (fused into the load, no separate gather pass, :195-199)
+//                [propagate]  exact Gillespie SSA over one observation interval            (gillespie_algo.py)
+//                [store]      X[p][:, j] = x, coalesced SoA int32                          (pmcmc.py:222-231)
+//                [weigh]      logw_j = min_c log pmf/pdf(Y[p][c] | x_c)                    (pmcmc.py:178-181, used at p+1)
+//                [scan]       CTA-local max m_b and inclusive scan L of exp(logw - m_b) (warp shuffles + smem)
+//                [finalize]   the last CTA to finish combines the per-CTA (m_b, s_b) partials: global max M,
+//                             CTA prefixes, total, and log_zetas[p+1] = log_zetas[p] + M + log(total) - log(N)
+//                             (pmcmc.py:183 in the log domain); flags collapse (pmcmc.py:191-192).
+//   cdf_p(i) for i in CTA b  =  pfx[b] + scale[b] * L[i],  scale[b] = exp(m_b - M): no second pass over the weights.
+// pf_step(0) initialises X_0 (given, or I_0 ~ Poisson(mu) per pmcmc.py:156-169) and weighs it against Y[0].
+// Timing convention of the reference is kept: step p weighs X[p-1] against Y[p-1]; the last state is
+// never weighed.
+#include <stdio.h>
+
+#include "sem_common.cuh"
+#include "sem_host.h"
+
+namespace sem {
+
+struct PfDev {
+    int N, T, Cobs, obs_kind, resampler, nb, ppb, hist_rows, model, n_filters, ntheta, init_poisson;
+    double probs, dt;
+    PhiloxKey key;
+    uint32_t filter_id0;
+    double mu[SEM_MAX_GROUPS], npop[SEM_MAX_GROUPS];
+    const double *Y, *theta;
+    const int32_t *X0;
+    const double *res_u, *ssa_u;
+    const long long *ssa_off;
+    int32_t *X_hist, *ancestry, *status;
+    double *log_zetas;
+    unsigned long long *n_events;
+    // workspace (double-buffered by step parity)
+    double *L[2];        // [F][N]   CTA-local inclusive scan of exp(logw - m_b)
+    double *pfx[2];      // [F][nb]  exclusive prefix of scale_b * s_b
+    double *scale[2];    // [F][nb]
+    double *total[2];    // [F]
+    double2 *part;       // [F][nb]  (m_b, s_b)
+    unsigned int *counter;  // [F]
+};
+
+constexpr int kMaxThreads = 768;
+
+__device__ __forceinline__ double block_max(double v, double *sm, int tid, int nwarps) {
+    v = warp_max_d(v);
+    __syncthreads();
+    if ((tid & 31) == 0) sm[tid >> 5] = v;
+    __syncthreads();
+    double r = sm[0];
+    for (int w = 1; w < nwarps; w++) r = fmax(r, sm[w]);
+    return r;
+}
+
+// inclusive scan over the CTA; returns this thread's inclusive value, *total = CTA sum
+__device__ __forceinline__ double block_incl_scan(double v, double *sm, int tid, int nwarps, double *total) {
+    const int lane = tid & 31, w = tid >> 5;
+    v = warp_incl_scan_d(v, lane);
+    __syncthreads();
+    if (lane == 31) sm[w] = v;
+    __syncthreads();
+    double off = 0.0, tot = 0.0;
+    for (int i = 0; i < nwarps; i++) { const double s = sm[i]; if (i < w) off += s; tot += s; }
+    *total = tot;
+    return v + off;
+}
+
+template <class Model>
+__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow) {
+    double lw = CUDART_INF;
+#pragma unroll
+    for (int c = 0; c < Model::C; c++) {
+        if (c < P.Cobs) {
+            double xc = x[c];
+            if (P.model == SEM_MODEL_SIR_SUBGROUPS2) {      // observes the group sum of each compartment (pmcmc.py:172-173)
+                xc = 0.0;
+#pragma unroll
+                for (int g = 0; g < Model::G; g++) xc += x[3 * g + (c % 3)];
+            }
+            const double y = Yrow[c];
+            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf(y, xc, P.probs) : norm_logpdf(y, xc, P.probs);
+            lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
+        }
+    }
+    return lw;
+}
+
+template <class Model, int ARITH, bool REPLAY>
+__global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int p) {
+    __shared__ double sm[32];
+    __shared__ bool is_last;
+    const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+    if (P.status[f] != 0) return;                            // collapsed (or replay exhausted) earlier
+    const int N = P.N, j = b * P.ppb + tid;
+    const bool active = tid < P.ppb && j < N;
+    const int par = p & 1;
+    const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
+    int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
+    int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
+    const uint32_t fid = P.filter_id0 + f;
+    double x[Model::C];
+    long long pairs = 0;
+    bool replay_dry = false;
+
+    if (active) {
+        if (p == 0) {
+            // ---------------------------------------------------------------- X_0 (pmcmc.py:156-170)
+            if (!P.init_poisson) {
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) x[c] = (double)P.X0[(size_t)c * N + j];
+            } else {
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) x[c] = 0.0;
+#pragma unroll
+                for (int g = 0; g < Model::G; g++) {
+                    PairSource<false> src; src.init(P.key, (uint32_t)j, (uint32_t)g, stream_word(DOM_INIT, fid));
+                    const double i0 = poisson_draw(src, P.mu[g]);
+                    constexpr bool seir = (Model::C == 4);
+                    x[seir ? 2 : 3 * g + 1] = i0;
+                    x[seir ? 0 : 3 * g] = P.npop[g] - i0;
+                }
+            }
+            Af[(size_t)row * N + j] = 0;
+        } else {
+            // ---------------------------------------------------------------- resample (pmcmc.py:187-193)
+            const double total = P.total[par ^ 1][f];
+            double u;
+            if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
+            else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
+                const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+                const double u0 = bits_to_d12(w.x, w.y) - 1.0;
+                u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
+            } else {
+                const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+                u = bits_to_d12(w.x, w.y) - 1.0;
+            }
+            const double v = __dmul_rn(u, total);
+            const double *pfx = P.pfx[par ^ 1] + (size_t)f * P.nb;
+            int lo = 0, hi = P.nb;                          // last CTA index with pfx[b] <= v  (pfx[0] = 0)
+            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= v) lo = mid; else hi = mid; }
+            const int base = lo * P.ppb, len = min(P.ppb, N - base);
+            const double sc = P.scale[par ^ 1][(size_t)f * P.nb + lo], pf = pfx[lo];
+            const double *L = P.L[par ^ 1] + (size_t)f * N + base;
+            int a = 0, e = len;                              // first i with pf + sc*L[i] > v
+            while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, L[mid], pf) <= v) a = mid + 1; else e = mid; }
+            a = base + min(a, len - 1);
+            Af[(size_t)row * N + j] = a;
+            // ---------------------------------------------------------------- gather parent (pmcmc.py:195-199)
+            const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = (double)Xp[(size_t)c * N + a];
+            // ---------------------------------------------------------------- propagate (pmcmc.py:200-220)
+            Model m;
+            m.setup(P.theta + (size_t)f * P.ntheta, x);
+            PairSource<REPLAY> src;
+            if constexpr (REPLAY) {
+                const size_t q = (size_t)(p - 1) * N + j;
+                src.init(P.ssa_u, P.ssa_off[q], P.ssa_off[q + 1]);
+            } else {
+                src.init(P.key, (uint32_t)j, (uint32_t)p, stream_word(DOM_SSA, fid));
+            }
+            pairs = ssa_run<Model, ARITH, REPLAY>(m, x, P.dt, src, NoRec());
+            if (pairs < 0) { replay_dry = true; pairs = 0; }
+        }
+        // -------------------------------------------------------------------- store X[p] (SoA, coalesced)
+        int32_t *Xr = Xf + (size_t)row * Model::C * N;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
+    }
+    if (replay_dry) atomicExch(&P.status[f], SEM_ERR_REPLAY);
+    if (P.n_events && pairs) atomicAdd(&P.n_events[f], (unsigned long long)pairs);
+    if (p >= P.T - 1) return;                                // the final state is never weighed
+
+    // ------------------------------------------------------------------------ weigh against Y[p] (pmcmc.py:178-181)
+    double lw = -CUDART_INF;
+    if (active) {
+        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs);
+        if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in finalize
+    }
+    const int nwarps = (blockDim.x + 31) >> 5;
+    const double mb = block_max(lw, sm, tid, nwarps);
+    const double e = (active && mb > -CUDART_INF && mb < CUDART_INF) ? exp(lw - mb) : 0.0;
+    double sb;
+    const double incl = block_incl_scan(e, sm, tid, nwarps, &sb);
+    if (active) P.L[par][(size_t)f * N + j] = incl;
+    if (tid == 0) P.part[(size_t)f * P.nb + b] = make_double2(mb, sb);
+
+    // ------------------------------------------------------------------------ last CTA finalizes the step
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(&P.counter[f], 1u) == (unsigned)(P.nb - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double2 *part = P.part + (size_t)f * P.nb;
+    double M = -CUDART_INF;
+    for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
+    M = block_max(M, sm, tid, nwarps);
+    double carry = 0.0;
+    double *pfx = P.pfx[par] + (size_t)f * P.nb, *scale = P.scale[par] + (size_t)f * P.nb;
+    const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
+    for (int i0 = 0; i0 < P.nb; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        double sc = 0.0, val = 0.0;
+        if (i < P.nb && finiteM) {
+            const double mi = __ldcg(&part[i].x), si = __ldcg(&part[i].y);
+            sc = (mi > -CUDART_INF) ? exp(mi - M) : 0.0;
+            val = sc * si;
+        }
+        double chunk;
+        const double incl2 = block_incl_scan(val, sm, tid, nwarps, &chunk);
+        if (i < P.nb) { pfx[i] = carry + (incl2 - val); scale[i] = sc; }
+        carry += chunk;
+    }
+    if (tid == 0) {
+        P.total[par][f] = carry;
+        double *lz = P.log_zetas + (size_t)f * P.T;
+        if (!finiteM || !(carry > 0.0)) {
+            P.status[f] = p + 1;                              // np.random.choice raises at step p+1 (pmcmc.py:191-192)
+            for (int q = p + 1; q < P.T; q++) lz[q] = -CUDART_INF;
+        } else {
+            lz[p + 1] = lz[p] + M + log(carry) - log((double)N);    // zetas[p+1] = zetas[p] * mean(w), pmcmc.py:183
+        }
+        P.counter[f] = 0;
+    }
+}
+
+// (T,C,N) int32 -> (T,N,C) float64, the layout pmcmc.py:151 returns
+__global__ void hist_to_f64_kernel(const int32_t *X, int T, int N, int C, double *out) {
+    const size_t n = (size_t)T * N * C;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t t = i / ((size_t)N * C), r = i - t * (size_t)N * C;
+        const int jj = (int)(r / C), c = (int)(r - (size_t)jj * C);
+        out[i] = (double)X[(t * C + c) * N + jj];
+    }
+}
+
+__global__ void i32_to_f64_kernel(const int32_t *in, size_t n, double *out) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = (double)in[i];
+}
+
+// particle_path_sampler (pmcmc.py:236-248): one thread chases the genealogy backwards.
+__global__ void path_sample_kernel(const int32_t *X, const int32_t *A, int T, int N, int C, int chosen, int exact,
+                                   PhiloxKey key, uint32_t fid, int32_t *traj) {
+    if (blockIdx.x || threadIdx.x) return;
+    if (chosen < 0) {                                          // np.random.randint(0, N) (pmcmc.py:241)
+        const uint4 w = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, fid), key);
+        chosen = min((int)((bits_to_d12(w.x, w.y) - 1.0) * (double)N), N - 1);
+    }
+    for (int c = 0; c < C; c++) traj[(size_t)(T - 1) * C + c] = X[((size_t)(T - 1) * C + c) * N + chosen];
+    for (int p = T - 2; p >= 0; p--) {
+        chosen = A[(size_t)(exact ? p + 1 : p) * N + chosen];  // reference indexes row p
+        for (int c = 0; c < C; c++) traj[(size_t)p * C + c] = X[((size_t)p * C + c) * N + chosen];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- host side
+// particles per CTA: one CTA per SM when the whole population is co-resident, else 256-wide CTAs
+static int choose_ppb(const sem_pf_config *c) {
+    if (c->block_particles > 0) return c->block_particles > kMaxThreads ? kMaxThreads : c->block_particles;
+    const long long all = (long long)c->n_particles * c->n_filters;
+    const long long per_sm = (all + sm_count() - 1) / sm_count();
+    long long ppb = per_sm <= kMaxThreads ? ((per_sm + 31) / 32) * 32 : 256;
+    if (ppb < 32) ppb = 32;
+    const long long nround = ((long long)c->n_particles + 31) / 32 * 32;
+    if (ppb > nround) ppb = nround;
+    return (int)ppb;
+}
+
+static int validate(const sem_pf_config *c) {
+    if (!c) { set_error("null config"); return SEM_ERR_INVALID; }
+    if (c->model < 0 || c->model > 3) { set_error("bad model"); return SEM_ERR_INVALID; }
+    const int G = c->model >= SEM_MODEL_SIR_SUBGROUPS ? c->n_groups : 1;
+    if (G < 1 || G > SEM_MAX_GROUPS) { set_error("n_groups must be 1..4"); return SEM_ERR_INVALID; }
+    if (c->n_particles < 1 || c->n_obs < 1 || c->n_filters < 1) { set_error("bad sizes"); return SEM_ERR_INVALID; }
+    const int C = model_cols(c->model, G);
+    const int want = c->model == SEM_MODEL_SIR_SUBGROUPS2 ? 3 : C;
+    if (c->n_obs_cols != want) { set_error("n_obs_cols does not match the model"); return SEM_ERR_INVALID; }
+    return SEM_OK;
+}
+
+struct WsLayout { size_t L[2], pfx[2], scale[2], total[2], part, counter, bytes; int nb, ppb; };
+static WsLayout ws_layout(const sem_pf_config *c) {
+    WsLayout w;
+    w.ppb = choose_ppb(c);
+    w.nb = (c->n_particles + w.ppb - 1) / w.ppb;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t F = c->n_filters;
+    for (int i = 0; i < 2; i++) w.L[i] = take(F * c->n_particles * sizeof(double));
+    for (int i = 0; i < 2; i++) w.pfx[i] = take(F * w.nb * sizeof(double));
+    for (int i = 0; i < 2; i++) w.scale[i] = take(F * w.nb * sizeof(double));
+    for (int i = 0; i < 2; i++) w.total[i] = take(F * sizeof(double));
+    w.part = take(F * w.nb * sizeof(double2));
+    w.counter = take(F * sizeof(unsigned int));
+    w.bytes = off;
+    return w;
+}
+
+template <class Model>
+static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 grid, int threads, cudaStream_t s) {
+    if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, 0, s>>>(P, p);
+    else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, 0, s>>>(P, p);
+    else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, 0, s>>>(P, p);
+}
+
+}  // namespace sem
+
+using namespace sem;
+
+extern "C" {
+
+const char *sem_last_error(void) { return err_buf(); }
+int sem_abi_version(void) { return SEM_ABI_VERSION; }
+
+int sem_device_info(int *sms, int *major, int *minor) {
+    int dev = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp pr;
+    SEM_CUDA(cudaGetDeviceProperties(&pr, dev));
+    if (sms) *sms = pr.multiProcessorCount;
+    if (major) *major = pr.major;
+    if (minor) *minor = pr.minor;
+    return SEM_OK;
+}
+
+size_t sem_pf_workspace_bytes(const sem_pf_config *cfg) { return validate(cfg) ? 0 : ws_layout(cfg).bytes; }
+
+static int hist_rows(const sem_pf_config *c) { return c->store_history ? c->n_obs : (c->n_obs < 2 ? c->n_obs : 2); }
+
+size_t sem_pf_hist_elems(const sem_pf_config *c) {
+    if (validate(c)) return 0;
+    const int G = c->model >= SEM_MODEL_SIR_SUBGROUPS ? c->n_groups : 1;
+    return (size_t)c->n_filters * hist_rows(c) * model_cols(c->model, G) * c->n_particles;
+}
+size_t sem_pf_ancestry_elems(const sem_pf_config *c) { return validate(c) ? 0 : (size_t)c->n_filters * hist_rows(c) * c->n_particles; }
+int sem_pf_launch_count(const sem_pf_config *c) { return validate(c) ? 0 : c->n_obs; }
+
+int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!buf || !buf->Y || !buf->theta || !buf->X_hist || !buf->ancestry || !buf->log_zetas || !buf->status || !buf->workspace) {
+        set_error("null buffer"); return SEM_ERR_INVALID;
+    }
+    const bool replay = buf->replay_ssa_u != nullptr;
+    if (replay && (!buf->replay_resample_u || !buf->replay_ssa_off || !buf->X0)) { set_error("replay needs resample_u, ssa_off and X0"); return SEM_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    const WsLayout w = ws_layout(cfg);
+    char *ws = (char *)buf->workspace;
+    PfDev P;
+    P.N = cfg->n_particles; P.T = cfg->n_obs; P.Cobs = cfg->n_obs_cols; P.obs_kind = cfg->obs_kind; P.resampler = cfg->resampler;
+    P.nb = w.nb; P.ppb = w.ppb; P.hist_rows = hist_rows(cfg); P.model = cfg->model; P.n_filters = cfg->n_filters;
+    P.ntheta = model_ntheta(cfg->model, G); P.init_poisson = buf->X0 == nullptr;
+    P.probs = cfg->probs; P.dt = cfg->dt;
+    P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32); P.filter_id0 = cfg->filter_id0;
+    for (int g = 0; g < SEM_MAX_GROUPS; g++) { P.mu[g] = cfg->mu[g]; P.npop[g] = cfg->n_population[g]; }
+    P.Y = buf->Y; P.theta = buf->theta; P.X0 = buf->X0;
+    P.res_u = buf->replay_resample_u; P.ssa_u = buf->replay_ssa_u; P.ssa_off = (const long long *)buf->replay_ssa_off;
+    P.X_hist = buf->X_hist; P.ancestry = buf->ancestry; P.status = buf->status; P.log_zetas = buf->log_zetas;
+    P.n_events = (unsigned long long *)buf->n_events;
+    for (int i = 0; i < 2; i++) {
+        P.L[i] = (double *)(ws + w.L[i]); P.pfx[i] = (double *)(ws + w.pfx[i]);
+        P.scale[i] = (double *)(ws + w.scale[i]); P.total[i] = (double *)(ws + w.total[i]);
+    }
+    P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
+    SEM_CUDA(cudaMemsetAsync(P.counter, 0, cfg->n_filters * sizeof(unsigned int), s));
+    SEM_CUDA(cudaMemsetAsync(P.status, 0, cfg->n_filters * sizeof(int32_t), s));
+    SEM_CUDA(cudaMemsetAsync(P.log_zetas, 0, (size_t)cfg->n_filters * cfg->n_obs * sizeof(double), s));   // zetas[0] = 1 (pmcmc.py:154)
+    if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
+    const int threads = (w.ppb + 31) / 32 * 32;
+    const dim3 grid(w.nb, cfg->n_filters);
+    for (int p = 0; p < cfg->n_obs; p++) {
+        switch (cfg->model) {
+            case SEM_MODEL_SIR: launch_model<SirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
+            case SEM_MODEL_SEIR: launch_model<SeirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
+            default:
+                switch (G) {
+                    case 1: launch_model<SubModel<1>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                    case 2: launch_model<SubModel<2>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                    case 3: launch_model<SubModel<3>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                    default: launch_model<SubModel<4>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                }
+        }
+    }
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+int sem_path_sample(const int32_t *X_hist, const int32_t *ancestry, int32_t T, int32_t N, int32_t C, int32_t chosen,
+                    int32_t exact, uint64_t seed, uint32_t filter_id, int32_t *traj, void *stream) {
+    if (!X_hist || !ancestry || !traj || T < 1 || N < 1 || chosen >= N) { set_error("bad path_sample args"); return SEM_ERR_INVALID; }
+    PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    path_sample_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(X_hist, ancestry, T, N, C, chosen, exact, key, filter_id, traj);
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+int sem_hist_to_f64(const int32_t *X_hist, int32_t T, int32_t N, int32_t C, double *out, void *stream) {
+    if (!X_hist || !out) { set_error("null"); return SEM_ERR_INVALID; }
+    const size_t n = (size_t)T * N * C;
+    const int blocks = (int)((n + 255) / 256 < (size_t)sm_count() * 16 ? (n + 255) / 256 : (size_t)sm_count() * 16);
+    hist_to_f64_kernel<<<blocks ? blocks : 1, 256, 0, (cudaStream_t)stream>>>(X_hist, T, N, C, out);
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *theta, const int32_t *X0,
+                    double *log_zetas_out, double *zetas_out, double *hidden_out, double *ancestry_out, uint64_t *n_events_out) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (cfg->n_filters != 1) { set_error("sem_pf_run_host handles one filter"); return SEM_ERR_INVALID; }
+    sem_pf_config c = *cfg;
+    c.store_history = 1;
+    const int G = c.model >= SEM_MODEL_SIR_SUBGROUPS ? c.n_groups : 1, C = model_cols(c.model, G), T = c.n_obs, N = c.n_particles;
+    const size_t nh = sem_pf_hist_elems(&c), na = sem_pf_ancestry_elems(&c), wsb = sem_pf_workspace_bytes(&c);
+    const size_t nY = (size_t)T * c.n_obs_cols, nth = model_ntheta(c.model, G);
+    char *d = nullptr;
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    size_t oY = 0, oth = oY + al(nY * 8), oX0 = oth + al(nth * 8), oH = oX0 + al(X0 ? (size_t)C * N * 4 : 0), oA = oH + al(nh * 4),
+           oZ = oA + al(na * 4), oS = oZ + al((size_t)T * 8), oE = oS + 256, oW = oE + 256, oF = oW + al(wsb),
+           tot = oF + al(((hidden_out ? nh : 0) > (ancestry_out ? na : 0) ? (hidden_out ? nh : 0) : (ancestry_out ? na : 0)) * 8);
+    SEM_CUDA(cudaMalloc(&d, tot));
+    cudaStream_t s = 0;
+    rc = SEM_OK;
+    auto fail = [&](cudaError_t e, const char *what) { if (e != cudaSuccess && rc == SEM_OK) { set_error("%s: %s", what, cudaGetErrorString(e)); rc = SEM_ERR_CUDA; } };
+    fail(cudaMemcpyAsync(d + oY, Y, nY * 8, cudaMemcpyHostToDevice, s), "H2D Y");
+    fail(cudaMemcpyAsync(d + oth, theta, nth * 8, cudaMemcpyHostToDevice, s), "H2D theta");
+    if (X0) fail(cudaMemcpyAsync(d + oX0, X0, (size_t)C * N * 4, cudaMemcpyHostToDevice, s), "H2D X0");
+    sem_pf_buffers b{};
+    b.Y = (const double *)(d + oY); b.theta = (const double *)(d + oth); b.X0 = X0 ? (const int32_t *)(d + oX0) : nullptr;
+    b.X_hist = (int32_t *)(d + oH); b.ancestry = (int32_t *)(d + oA); b.log_zetas = (double *)(d + oZ);
+    b.status = (int32_t *)(d + oS); b.n_events = (uint64_t *)(d + oE); b.workspace = d + oW;
+    if (rc == SEM_OK) rc = sem_pf_run(&c, &b, s);
+    int32_t status = 0;
+    if (rc == SEM_OK) {
+        fail(cudaMemcpyAsync(&status, b.status, 4, cudaMemcpyDeviceToHost, s), "D2H status");
+        if (log_zetas_out || zetas_out) {
+            double *tmp = log_zetas_out ? log_zetas_out : zetas_out;
+            fail(cudaMemcpyAsync(tmp, b.log_zetas, (size_t)T * 8, cudaMemcpyDeviceToHost, s), "D2H log_zetas");
+        }
+        if (n_events_out) fail(cudaMemcpyAsync(n_events_out, b.n_events, 8, cudaMemcpyDeviceToHost, s), "D2H n_events");
+        if (hidden_out) {
+            sem_hist_to_f64(b.X_hist, T, N, C, (double *)(d + oF), s);
+            fail(cudaMemcpyAsync(hidden_out, d + oF, nh * 8, cudaMemcpyDeviceToHost, s), "D2H hidden");
+        }
+        if (ancestry_out) {
+            i32_to_f64_kernel<<<sm_count() * 8, 256, 0, s>>>(b.ancestry, na, (double *)(d + oF));
+            fail(cudaMemcpyAsync(ancestry_out, d + oF, na * 8, cudaMemcpyDeviceToHost, s), "D2H ancestry");
+        }
+        fail(cudaStreamSynchronize(s), "sync");
+        if (rc == SEM_OK && zetas_out) {
+            const double *src = log_zetas_out ? log_zetas_out : zetas_out;
+            for (int i = T - 1; i >= 0; i--) zetas_out[i] = exp(src[i]);
+        }
+    }
+    cudaFree(d);
+    if (rc != SEM_OK) return rc;
+    return status;
+}
+
+}  // extern "C"

@@ -1,0 +1,236 @@
+"""Drop-in for the hot-path functions of the reference's pmcmc.py (pmcmc.py:116-408).
+
+particle_filter / particle_path_sampler / particle_mcmc keep the reference's positional and keyword
+signatures; extra arguments are keyword-only with behaviour-preserving defaults.  The whole filter (X_0,
+weights, likelihood, resampling, SSA propagation, all T steps) runs on the GPU through one sem_pf_run call;
+the Metropolis-Hastings loop stays on the host like the reference's, but in the log domain.
+
+Deliberate, documented differences from the reference:
+  D2  likelihoods are accumulated as log-sums on the device; `zetas` is exp() of that (same numbers where the
+      reference does not underflow, finite log-likelihood where it does).
+  D3  resampler='systematic' (one uniform per step) is the default; resampler='multinomial' is the reference's
+      np.random.choice rule.  Both leave the likelihood estimator unbiased.
+  D4  the MH ratio of pmcmc.py:376-391 reduces algebraically to Z'/Z_prev (symmetric proposal, the "prior" terms
+      cancel); it is evaluated as log u < logZ' - logZ_prev.  The reference's min(1, nan) -> accept quirk on a
+      0/0 underflow is not reproduced.
+  D8  particle_path_sampler keeps the reference's off-by-one ancestry indexing by default (exact_genealogy=False).
+  `jobs` is accepted and ignored (no process pool).
+The ODE data synthesiser (pmcmc.py:16-113) is out of scope.
+"""
+from enum import Enum
+
+import numpy as np
+import torch
+
+from . import engine
+from .gillespie_algo import *  # noqa: F401,F403  (pmcmc.py:13 re-exports the simulators)
+from .gillespie_algo import __all__ as _g_all
+
+__all__ = ["ModelType", "particle_filter", "particle_path_sampler", "particle_mcmc", "pf_loglik"] + list(_g_all)
+
+
+class ModelType(Enum):          # pmcmc.py:116-120
+    SIR = "sir"
+    SEIR = "seir"
+    SIR_SUBGROUPS = "sir_subgroups"
+    SIR_SUBGROUPS2 = "sir_subgroups2"
+
+
+def _model_id(type_model):
+    """pmcmc.py:134-141: SIR, SEIR, SIR_SUBGROUPS2 are recognised; anything else takes the subgroup branch."""
+    v = getattr(type_model, "value", type_model)
+    return {"sir": 0, "seir": 1, "sir_subgroups2": 3}.get(v, 2)
+
+
+def _flatten_theta(model, theta_proposal):
+    if model >= 2:      # (beta[G,G], gamma)  pmcmc.py:214-215
+        betas, gamma = theta_proposal
+        return np.concatenate([np.asarray(betas, dtype=np.float64).reshape(-1), [float(gamma)]])
+    return np.asarray(theta_proposal, dtype=np.float64).reshape(-1)
+
+
+def _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_population, mu, resampler, seed, arith,
+           filter_id, store_history=True, block_particles=0):
+    model = _model_id(type_model)
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError("Y must be (T, columns)")
+    G = len(mu) if model >= 2 else 1
+    theta = _flatten_theta(model, theta_proposal)
+    cfg = engine.make_pf_config(model, n_particles, Y.shape[0], G=G, observations=observations, probs=probs,
+                                resampler=resampler, arith=arith, seed=seed, filter_id0=filter_id,
+                                mu=np.atleast_1d(mu), n_population=np.atleast_1d(n_population),
+                                store_history=store_history, block_particles=block_particles)
+    if Y.shape[1] != cfg.n_obs_cols:
+        raise ValueError(f"Y has {Y.shape[1]} columns, the model observes {cfg.n_obs_cols}")
+    return cfg, Y, theta
+
+
+def particle_filter(Y, type_model, theta_proposal, observations=False, probs=.1, n_particles=1000, n_population=4820,
+                    mu=20, jobs=4, *, resampler="systematic", seed=None, arith="fast", X0=None, replay=None,
+                    output="numpy", filter_id=0, block_particles=0):
+    """Bootstrap particle filter (pmcmc.py:123-233).
+
+    Returns (zetas[T], hidden_process[T,N,C], ancestry_matrix[T,N]) as float64 numpy arrays like the reference,
+    or (None, None, None) when the filter collapses (all weights zero, pmcmc.py:191-192).
+    output='torch' returns CUDA tensors instead (zetas fp64; states / ancestry int32 (T,N,C) / (T,N));
+    output='result' returns the engine.PfResult (adds log_zetas, n_events) or None on collapse.
+    replay = dict(res_u, ssa_u, ssa_off) feeds the reference's uniform stream (needs X0) for bit-exact parity.
+    """
+    seed = engine.new_seed() if seed is None else seed
+    cfg, Y, theta = _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_population, mu,
+                           "multinomial" if replay is not None else resampler, seed, arith, filter_id,
+                           block_particles=block_particles)
+    res = engine.run_pf(cfg, Y, theta, X0=X0, replay=replay)
+    status = int(res.status.cpu()[0])
+    if status == -3:
+        raise RuntimeError("replay buffer exhausted")
+    if status != 0:
+        return None if output == "result" else (None, None, None)
+    if output == "result":
+        return res
+    zetas = torch.exp(res.log_zetas[0])
+    if output == "torch":
+        return zetas, res.X_hist[0].permute(0, 2, 1), res.ancestry[0]
+    hidden = res.hidden_process(0).cpu().numpy()
+    anc = res.ancestry[0].to(torch.float64).cpu().numpy()
+    return zetas.cpu().numpy(), hidden, anc
+
+
+def pf_loglik(Y, type_model, theta_proposal, observations=False, probs=.1, n_particles=1000, n_population=4820,
+              mu=20, *, resampler="systematic", seed=None, arith="fast", filter_id=0):
+    """log of the likelihood estimate zetas[-1] only (no history leaves the device); -inf on collapse."""
+    seed = engine.new_seed() if seed is None else seed
+    cfg, Y, theta = _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_population, mu,
+                           resampler, seed, arith, filter_id, store_history=False)
+    res = engine.run_pf(cfg, Y, theta)
+    st = int(res.status.cpu()[0])
+    return float("-inf") if st != 0 else float(res.log_zetas[0, -1].cpu())
+
+
+def particle_path_sampler(hidden_process, ancestry_matrix, *, exact_genealogy=False, chosen_path=None, seed=None):
+    """pmcmc.py:236-248: pick a final particle uniformly and chase its ancestry backwards.  (T,N,C),(T,N) -> (T,C).
+
+    The index chase runs in the sem_path_sample kernel; host arrays are uploaded first (pass CUDA tensors to avoid
+    that).  exact_genealogy=False keeps the reference's indexing of ancestry_matrix[p]."""
+    dev = engine.require_cuda()
+    hp = torch.as_tensor(np.asarray(hidden_process) if not isinstance(hidden_process, torch.Tensor) else hidden_process)
+    am = torch.as_tensor(np.asarray(ancestry_matrix) if not isinstance(ancestry_matrix, torch.Tensor) else ancestry_matrix)
+    T, N, Cn = hp.shape
+    X = hp.to(dev).to(torch.int32).permute(0, 2, 1).contiguous().unsqueeze(0)      # [1][T][C][N]
+    A = am.to(dev).to(torch.int32).contiguous().unsqueeze(0)
+    if chosen_path is None and seed is None:
+        chosen_path = int(np.random.randint(0, N))                                # pmcmc.py:241
+    res = engine.PfResult(None, X, A, None, None, None, 0)
+    traj = res.path_sample(0, chosen=-1 if chosen_path is None else chosen_path, exact=exact_genealogy, seed=seed or 0)
+    return traj.to(torch.float64).cpu().numpy()
+
+
+def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_chains=1000, observations=False,
+                  probs=.1, n_particles=1000, n_population=4820, mu=20, jobs=4, *, resampler="systematic", seed=None,
+                  arith="fast", exact_genealogy=False, return_log=False, progress=False, stats=None):
+    """Particle marginal Metropolis-Hastings (pmcmc.py:251-408).
+
+    Returns (thetas[n_chains,P], likelihoods[n_chains], sampled_trajs[T,n_chains,C]).  likelihoods are the linear
+    zetas[-1] like the reference (log-likelihoods with return_log=True).  `stats`, if a dict, receives
+    'filter_runs', 'acceptances', 'launches'.
+    """
+    dev = engine.require_cuda()
+    Y = np.asarray(Y, dtype=np.float64)
+    model = _model_id(type_model)
+    n_par = len(parameters)
+    T = Y.shape[0]
+    G = len(mu) if model >= 2 else 1
+    Cn = engine.model_dims(model, G)[0]
+    thetas = np.zeros((n_chains, n_par))
+    loglik = np.zeros(n_chains)
+    sampled_trajs = np.zeros((T, n_chains, Cn))                                  # pmcmc.py:269-272
+    std = np.eye(n_par) if sigma is None else sigma                               # :273-275
+    seed = engine.new_seed() if seed is None else seed
+    counters = dict(filter_runs=0, acceptances=1, launches=0)
+
+    # reusable device buffers + pinned staging for the three small results of one iteration
+    cfg0, _, _ = _setup(Y, type_model, _split(model, G, np.asarray(parameters, dtype=float), probs)[0], observations,
+                        .5, n_particles, n_population, mu, resampler, seed, arith, 0)
+    out = engine.alloc_pf_outputs(cfg0, dev)
+    Yd = torch.from_numpy(Y).to(dev)
+    pin_lz = torch.empty((1,), dtype=torch.float64).pin_memory()
+    pin_st = torch.empty((1,), dtype=torch.int32).pin_memory()
+    pin_tr = torch.empty((T, Cn), dtype=torch.int32).pin_memory()
+
+    def run_filter(theta_vec, it):
+        theta2, probs2 = _split(model, G, theta_vec, probs)
+        cfg, _, th = _setup(Y, type_model, theta2, observations, probs2, n_particles, n_population, mu, resampler, seed,
+                            arith, it)
+        res = engine.run_pf(cfg, Yd, th, out=out)
+        traj = res.path_sample(0, exact=exact_genealogy, seed=seed, filter_id=it)
+        pin_lz.copy_(res.log_zetas[0, -1:], non_blocking=True)
+        pin_st.copy_(res.status, non_blocking=True)
+        pin_tr.copy_(traj, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        counters["filter_runs"] += 1
+        counters["launches"] += res.launches + 1
+        if int(pin_st[0]) != 0:
+            return None, None
+        return float(pin_lz[0]), pin_tr.numpy().astype(np.float64)
+
+    def finish_theta(theta_vec):
+        if probs is None:                                                         # :313-314,373-374: stored p_obs is clipped
+            out_t = np.array(theta_vec, dtype=float)
+            out_t[-1] = max(min(out_t[-1], 1), 0)
+            return out_t
+        return theta_vec
+
+    it = 0
+    while True:                                                                   # :276-310 initial draw
+        theta_proposal = np.random.multivariate_normal(np.array(parameters), h * std)
+        if np.sum(theta_proposal < 0) > 0:
+            continue
+        lz, traj = run_filter(theta_proposal, it)
+        it += 1
+        if lz is not None:
+            break
+    thetas[0] = finish_theta(theta_proposal)
+    loglik[0] = lz
+    sampled_trajs[:, 0, :] = traj
+
+    bar = None
+    if progress:
+        from tqdm import tqdm
+        bar = tqdm(total=n_chains - 1, desc="Chains")
+    for i in range(1, n_chains):                                                  # :325
+        if adaptive and i > 1e3:
+            std = np.cov(thetas[:i].T, ddof=0) + 1e-4 * np.eye(n_par)             # :327-328
+        theta_proposal = np.random.multivariate_normal(thetas[i - 1], h * std)    # :330
+        lz = None
+        if not np.sum(theta_proposal < 0) > 0:                                    # :333
+            lz, traj = run_filter(theta_proposal, it)
+            it += 1
+        if lz is None:                                                            # negative proposal or collapse (:333-337,365-369)
+            thetas[i] = thetas[i - 1]; loglik[i] = loglik[i - 1]; sampled_trajs[:, i, :] = sampled_trajs[:, i - 1, :]
+        elif np.log(np.random.uniform()) < lz - loglik[i - 1]:                    # :376-395, see D4
+            counters["acceptances"] += 1
+            thetas[i] = finish_theta(theta_proposal); loglik[i] = lz; sampled_trajs[:, i, :] = traj
+        else:
+            thetas[i] = thetas[i - 1]; loglik[i] = loglik[i - 1]; sampled_trajs[:, i, :] = sampled_trajs[:, i - 1, :]
+        if bar is not None:
+            bar.update(1)
+            bar.set_postfix_str(f"theta={thetas[i]}, logZ={loglik[i]:.3f}, acc={100 * counters['acceptances'] / (i + 1):.1f}%")
+    if isinstance(stats, dict):
+        stats.update(counters)
+    return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs
+
+
+def _split(model, G, theta_vec, probs):
+    """pmcmc.py:283-296 / 339-352: optional trailing p_obs (probs=None), subgroup reshape to (beta[G,G], gamma)."""
+    theta_vec = np.asarray(theta_vec, dtype=np.float64)
+    probs2 = probs
+    if probs is None:
+        probs2 = max(min(theta_vec[-1], 1), 0)
+        theta_vec = theta_vec[:-1]
+    if model >= 2:
+        beta = np.zeros((G, G))
+        for p in range(G * G):
+            beta[p // G, p % G] = theta_vec[p]
+        return (beta, theta_vec[-1]), probs2
+    return theta_vec, probs2

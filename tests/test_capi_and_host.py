@@ -1,0 +1,150 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol include/sem_b200.h declares (no compute
+calls without a GPU), the ctypes structs match the header's field lists, the product path fails loudly without a
+CUDA device, and the host-side sharding logic (world_size 2 over gloo)."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+
+HEADER = os.path.join(ROOT, "include", "sem_b200.h")
+
+
+def _built_lib():
+    import sem_b200
+    from sem_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        sys.path.insert(0, os.path.join(ROOT, "stochastic-epidemic-modelling_b200"))
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("sem_build", os.path.join(ROOT, "stochastic-epidemic-modelling_b200", "build.py"))
+        mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+        mod.build()
+    return _lib
+
+
+def test_library_exports_every_declared_symbol():
+    _lib = _built_lib()
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    declared = set(re.findall(r"\b(sem_[a-z0-9_]+)\s*\(", src))
+    assert len(declared) >= 15
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), f"{name} declared in include/sem_b200.h but not exported"
+    assert set(_lib.EXPORTS) == declared
+    assert _lib.load().sem_abi_version() == 1
+
+
+def test_struct_layouts_match_header():
+    _lib = _built_lib()
+    src = open(HEADER).read()
+
+    def fields(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), src, flags=re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(u?int\d+_t|double|void|size_t)\s*\**", "", decl)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*\]", "", part).replace("*", "").strip())
+        return names
+
+    for cname, cls in [("sem_pf_config", _lib.PfConfig), ("sem_pf_buffers", _lib.PfBuffers),
+                       ("sem_sim_config", _lib.SimConfig), ("sem_abc_config", _lib.AbcConfig)]:
+        assert fields(cname) == [f[0] for f in cls._fields_], cname
+    assert C.sizeof(_lib.PfConfig) == 12 * 4 + 8 + 8 + 8 + 4 + 4 + 64
+    assert C.sizeof(_lib.AbcConfig) == 16 + 8 + 8 + 8 + 32 + 8
+
+
+def test_product_path_fails_loudly_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import sem_b200
+    with pytest.raises(sem_b200._lib.SemError):
+        sem_b200.particle_filter(np.zeros((3, 3)), sem_b200.ModelType.SIR, np.array([2., 1.]))
+    with pytest.raises(sem_b200._lib.SemError):
+        sem_b200.sir_simulate([10, 1, 0], np.array([2., 1.]), 1, True)
+    with pytest.raises(sem_b200._lib.SemError):
+        sem_b200.abc_algo.abc_algo(np.ones((3, 3)), 1, 10., {"beta": [0, 5], "gamma": [0, 5]})
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "stochastic-epidemic-modelling_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.replace("the CPU oracle", "").replace("CPU oracle", "").lower() or f == "build.py", f
+
+
+def test_model_type_and_split():
+    import sem_b200
+    pm = sem_b200.pmcmc
+    assert [m.value for m in pm.ModelType] == ["sir", "seir", "sir_subgroups", "sir_subgroups2"]
+    assert pm._model_id(pm.ModelType.SIR) == 0 and pm._model_id(pm.ModelType.SEIR) == 1
+    assert pm._model_id(pm.ModelType.SIR_SUBGROUPS2) == 3 and pm._model_id("sir") == 0
+    assert pm._model_id("anything else") == 2                        # pmcmc.py:138-139 falls to the subgroup branch
+    (beta, gamma), p2 = pm._split(2, 2, np.array([5., 2., 1., 3., .5, 1.7]), None)
+    assert np.array_equal(beta, [[5, 2], [1, 3]]) and gamma == .5 and p2 == 1.0      # p_obs clipped to [0,1]
+    th, p2 = pm._split(0, 1, np.array([2., 1.]), .1)
+    assert np.array_equal(th, [2., 1.]) and p2 == .1
+
+
+def test_shard_range_partitions():
+    from sem_b200.abc_algo import shard_range
+    for start, count, world in [(0, 10, 3), (100, 7, 8), (5, 64, 4), (0, 0, 2)]:
+        got = []
+        for r in range(world):
+            lo, n = shard_range(start, count, r, world)
+            got += list(range(lo, lo + n))
+        assert got == list(range(start, start + count))
+
+
+WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import sem_b200
+from oracle import c_oracle as co
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+g = np.load(os.path.join(sys.argv[1], "tests", "golden", "abc_sir_small.npz"))
+obs = g["observed"]
+def run_batch(obs, n, thr, prior4, seed, trial0, arith, er):      # CPU executor standing in for the kernel
+    o = co.abc_trials(obs, n, thr, prior4, arith=1, seed=seed, trial0=trial0, want_traj=False, n_threads=1)
+    acc = np.nonzero(o["distance"] <= thr)[0]
+    return acc + trial0, o["theta"][acc], o["distance"][acc], o["n_events"]
+def run_traj(obs, ids, thr, prior4, seed, arith):
+    return np.stack([co.abc_trials(obs, 1, thr, prior4, arith=1, seed=seed, trial0=int(i), n_threads=1)["traj"][0] for i in ids])
+st = {}
+theta, traj = sem_b200.abc_algo.abc_rejection(obs, 4, 45.0, {"beta": [0, 5], "gamma": [0, 5]}, seed=7, batch=600,
+                                              run_batch=run_batch, run_traj=run_traj, stats=st)
+np.savez(sys.argv[4] + ".%s.npz" % sys.argv[3], theta=theta, traj=traj, ids=st["accepted_ids"])
+dist.destroy_process_group()
+"""
+
+
+def test_abc_sharding_world2_gloo(tmp_path, c_oracle):
+    """Two ranks shard the trial ids; both end with the accepted set a single process finds."""
+    port = str(29500 + os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    out = str(tmp_path / "res")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    assert np.array_equal(r0["ids"], r1["ids"]) and np.array_equal(r0["theta"], r1["theta"]) and np.array_equal(r0["traj"], r1["traj"])
+    obs = golden("abc_sir_small")["observed"]
+    ref = c_oracle.abc_trials(obs, 6000, 45.0, (0, 5, 0, 5), arith=1, seed=7, trial0=0)
+    acc = np.nonzero(ref["distance"] <= 45.0)[0][:4]
+    assert np.array_equal(r0["ids"], acc)
+    assert np.array_equal(r0["theta"], ref["theta"][acc])
+    assert np.array_equal(r0["traj"][:, :, 1:], ref["traj"][acc].astype(float))

@@ -1,0 +1,391 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes -> libsem_b200.so), against the oracle and
+the reference's golden vectors.  Bit-exact for integer states / ancestor indices; fp64 log-likelihoods to 1e-9
+relative (north_star tolerance), in practice ~1e-13."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from conftest import golden, golden_names, mt_doubles
+
+pytestmark = pytest.mark.gpu
+
+MODEL_OF = {"sir": 0, "seir": 1, "subgroups": 2}
+MODEL_IDS = {"SIR": 0, "SEIR": 1, "SIR_SUBGROUPS": 2, "SIR_SUBGROUPS2": 3}
+
+
+@pytest.fixture(scope="module")
+def sem():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    import sem_b200
+    sem_b200._lib.load()
+    return sem_b200
+
+
+# ------------------------------------------------------------------ small device functions
+def test_philox_known_answers(sem, c_oracle):
+    L = sem._lib.load()
+    for ctr, key in [([0, 0, 0, 0], [0, 0]), ([0xffffffff] * 4, [0xffffffff] * 2),
+                     ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]), ([7, 1, 2, 3], [5, 9])]:
+        out = (C.c_uint32 * 4)()
+        assert L.sem_test_philox((C.c_uint32 * 4)(*ctr), (C.c_uint32 * 2)(*key), out) == 0
+        assert [int(v) for v in out] == c_oracle.philox4x32(ctr, key)
+    out = (C.c_uint32 * 4)()
+    L.sem_test_philox((C.c_uint32 * 4)(0, 0, 0, 0), (C.c_uint32 * 2)(0, 0), out)
+    assert [int(v) for v in out] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]      # Random123 KAT
+
+
+def _map3(fn, a, b, c):
+    a, b, c = [np.ascontiguousarray(v, dtype=np.float64) for v in np.broadcast_arrays(a, b, c)]
+    out = np.empty_like(a)
+    p = lambda v: v.ctypes.data_as(C.c_void_p)
+    assert fn(p(a), p(b), p(c), p(out), C.c_int64(a.size)) == 0
+    return out
+
+
+def test_weights_vs_scipy_golden(sem, c_oracle):
+    L = sem._lib.load()
+    g = golden("weights_known_answers")
+    lp = _map3(L.sem_test_binom_logpmf, g["binom_k"], g["binom_n"], g["binom_p"])
+    ref = g["binom_pmf"]
+    zero = ref == 0
+    assert np.all(np.exp(lp[zero]) == 0)
+    np.testing.assert_allclose(np.exp(lp[~zero]), ref[~zero], rtol=2e-12)                   # scipy / Boost values
+    lo = c_oracle.binom_logpmf(g["binom_k"], g["binom_n"], g["binom_p"])
+    fin = np.isfinite(lo)
+    assert np.array_equal(np.isfinite(lp), fin)
+    np.testing.assert_allclose(lp[fin], lo[fin], rtol=1e-13, atol=1e-13)                    # C oracle
+    ln = _map3(L.sem_test_norm_logpdf, g["norm_y"], g["norm_x"], g["norm_probs"])
+    ok = g["norm_pdf"] > 1e-300
+    np.testing.assert_allclose(ln[ok], np.log(g["norm_pdf"][ok]), rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("mu", [0.0, 0.5, 3.0, 9.99, 10.0, 20.0, 4800.0, 8000.0])
+def test_poisson_matches_oracle(sem, c_oracle, mu):
+    L = sem._lib.load()
+    n = 1500
+    out = np.empty(n)
+    assert L.sem_test_poisson(mu, 1234, 3, 7, out.ctypes.data_as(C.c_void_p), n) == 0
+    ref = np.array([c_oracle.poisson_philox(mu, 1234, i, 7, 3) for i in range(n)])
+    assert np.array_equal(out, ref)
+    if mu > 0:
+        assert abs(out.mean() - mu) < 5 * np.sqrt(mu / n) + 1e-9
+
+
+# ------------------------------------------------------------------ SSA replay vs the reference (gillespie_algo.py)
+@pytest.mark.parametrize("name", golden_names("ssa_"))
+def test_ssa_replay_vs_reference(sem, name):
+    g = golden(name)
+    model = str(g["model"])
+    n_ev = g["times"].size - 1
+    u = mt_doubles(g["mt_key"], g["mt_pos"], 2 * (n_ev + 2))
+    ga = sem.gillespie_algo
+    tmax = float(g["max_time"])
+    if model == "sir":
+        out = ga.sir_simulate(list(g["population"]), g["theta"], tmax, False, replay_u=u)
+        last = ga.sir_simulate(list(g["population"]), g["theta"], tmax, True, replay_u=u)
+        cols = ["s", "i", "r"]
+    elif model == "seir":
+        out = ga.seir_simulate(list(g["population"]), g["theta"], tmax, False, replay_u=u)
+        last = ga.seir_simulate(list(g["population"]), g["theta"], tmax, True, replay_u=u)
+        cols = ["s", "e", "i", "r"]
+    else:
+        G = g["population"].shape[0]
+        th = g["theta"]
+        out = ga.sir_subgroups_simulate(g["population"], th[:G * G].reshape(G, G), th[-1], tmax, False, replay_u=u)
+        last = ga.sir_subgroups_simulate(g["population"], th[:G * G].reshape(G, G), th[-1], tmax, True, replay_u=u)
+        last = [v for grp in last for v in grp]
+        cols = [f"{c}_{grp}" for grp in range(G) for c in ("s", "i", "r")]
+    states = np.array([out[c] for c in cols], dtype=float).T
+    assert np.array_equal(states, g["states"])                           # integer trajectory bit-exact
+    np.testing.assert_allclose(out["time"], g["times"], rtol=1e-13, atol=0)   # event times to a few ulp
+    assert list(last) == list(g["states"][-1].astype(int))
+
+
+# ------------------------------------------------------------------ particle filter replay vs the reference
+PF_CASES = [n for n in golden_names("pf_") if n != "pf_sir_collapse"]
+
+
+def _replay_inputs(c_oracle, g):
+    model = MODEL_IDS[str(g["model"])]
+    G = g["mu"].size if model >= 2 else 1
+    n = 4096
+    while True:
+        flat = mt_doubles(g["mt_key"], g["mt_pos"], n)
+        try:
+            o = c_oracle.pf_run(model, g["Y"], g["theta"], bool(g["observations"]), float(g["probs"]),
+                                int(g["n_particles"]), G=G, X0=g["hidden_process"][0], flat_u=flat)
+            break
+        except RuntimeError:
+            n *= 4
+    ssa_u, off = c_oracle.flat_to_csr(flat, o["ssa_start"], o["ssa_end"])
+    return dict(res_u=o["res_u"], ssa_u=ssa_u, ssa_off=off), o
+
+
+def _theta_arg(g):
+    model = MODEL_IDS[str(g["model"])]
+    th = g["theta"]
+    if model >= 2:
+        G = g["mu"].size
+        return (th[:G * G].reshape(G, G), float(th[-1]))
+    return th
+
+
+@pytest.mark.parametrize("name", PF_CASES)
+@pytest.mark.parametrize("block", [0, 32])
+def test_pf_replay_vs_reference(sem, c_oracle, name, block):
+    g = golden(name)
+    replay, _ = _replay_inputs(c_oracle, g)
+    mt = getattr(sem.ModelType, str(g["model"]))
+    model = MODEL_IDS[str(g["model"])]
+    mu = g["mu"] if model >= 2 else float(g["mu"][0])
+    npop = g["n_population"] if model >= 2 else int(g["n_population"][0])
+    zetas, hidden, anc = sem.particle_filter(g["Y"], mt, _theta_arg(g), bool(g["observations"]), float(g["probs"]),
+                                             int(g["n_particles"]), npop, mu, 1, X0=g["hidden_process"][0],
+                                             replay=replay, block_particles=block)
+    assert hidden.dtype == np.float64 and hidden.shape == g["hidden_process"].shape
+    assert np.array_equal(hidden, g["hidden_process"])                   # SSA trajectories bit-exact
+    assert np.array_equal(anc, g["ancestry_matrix"])                     # resampling indices bit-exact
+    np.testing.assert_allclose(np.log(zetas), np.log(g["zetas"]), rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(zetas, g["zetas"], rtol=1e-9)
+
+
+def test_pf_collapse_returns_none(sem):
+    g = golden("pf_sir_collapse")
+    out = sem.particle_filter(g["Y"], sem.ModelType.SIR, g["theta"], False, float(g["probs"]), int(g["n_particles"]),
+                              int(g["n_population"][0]), float(g["mu"][0]), 1, seed=3)
+    assert out == (None, None, None)                                     # pmcmc.py:191-192
+
+
+@pytest.mark.parametrize("name", golden_names("path_"))
+def test_path_sampler_vs_reference(sem, name):
+    g = golden(name)
+    src = golden(str(g["source"]))
+    tr = sem.particle_path_sampler(src["hidden_process"], src["ancestry_matrix"], chosen_path=int(g["chosen"]))
+    assert np.array_equal(tr, g["trajectory"])
+
+
+# ------------------------------------------------------------------ production (Philox) path vs the C oracle
+def _truth_Y(model, T, seed, probs, normal):
+    rng = np.random.RandomState(seed)
+    t = np.arange(T)
+    if model == 1:
+        base = np.stack([900 - 40 * t, 20 + 10 * t, 20 + 15 * t, 15 * t], 1)
+    elif model == 2:
+        base = np.stack([400 - 20 * t, 15 + 8 * t, 12 * t, 600 - 30 * t, 20 + 12 * t, 18 * t], 1)
+    elif model == 3:
+        base = np.stack([1000 - 50 * t, 35 + 20 * t, 30 * t], 1)
+    else:
+        base = np.stack([980 - 45 * t, 20 + 25 * t, 20 * t], 1)
+    base = np.maximum(base, 0)
+    if normal:
+        return np.floor(base * (1 + probs * rng.normal(size=base.shape) * .3))
+    return rng.binomial(base.astype(int), probs).astype(float)
+
+
+PHILOX_CASES = [
+    # model, G, theta, npop, mu, N, T, normal, probs, resampler, arith, block
+    (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 1, 0),
+    (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 0, 1, 64),
+    (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 1, 0, 96),
+    (0, 1, [0.5, 3.0], [300], [3], 777, 8, False, .5, 0, 0, 0),          # many extinctions
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, False, .1, 1, 1, 0),
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, True, .2, 0, 0, 128),
+    (2, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 1, 1, 0),
+    (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 0, 1, 32),
+    (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1000, 7, True, .1, 1, 0, 0),
+    (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 1, 0),
+]
+
+
+@pytest.mark.parametrize("case", PHILOX_CASES, ids=lambda c: f"m{c[0]}G{c[1]}N{c[5]}r{c[9]}a{c[10]}b{c[11]}{'n' if c[7] else 'b'}")
+def test_pf_philox_vs_oracle(sem, c_oracle, case):
+    import torch
+    model, G, theta, npop, mu, N, T, normal, probs, resampler, arith, block = case
+    Y = _truth_Y(model, T, 5, probs, normal)
+    seed = 0xC0FFEE1234
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, observations=normal, probs=probs, resampler=resampler, arith=arith,
+                                    seed=seed, filter_id0=3, mu=mu, n_population=npop, block_particles=block)
+    res = sem.engine.run_pf(cfg, Y, np.array(theta, float))
+    torch.cuda.synchronize()
+    ref = c_oracle.pf_run(model, Y, theta, normal, probs, N, G=G, resampler=resampler, arith=arith, seed=seed,
+                          filter_id=3, mu=mu, npop=npop)
+    assert int(res.status.cpu()[0]) == ref["collapsed"] == 0
+    X = res.X_hist[0].permute(0, 2, 1).cpu().numpy()
+    assert np.array_equal(X[0], ref["X_hist"][0])                        # Poisson X_0
+    assert np.array_equal(res.ancestry[0].cpu().numpy(), ref["ancestry"])
+    assert np.array_equal(X, ref["X_hist"])
+    np.testing.assert_allclose(res.log_zetas[0].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
+    assert int(res.n_events.cpu()[0]) == ref["n_events"]
+
+
+def test_pf_fast_equals_reference_arithmetic(sem):
+    """FAST and REF fp64 operation orders walk the same integer trajectories from the same Philox streams."""
+    import torch
+    Y = _truth_Y(0, 12, 5, .1, False)
+    outs = []
+    for arith in (0, 1):
+        cfg = sem.engine.make_pf_config(0, 5000, 12, probs=.1, resampler=1, arith=arith, seed=99, mu=[20], n_population=[1000])
+        r = sem.engine.run_pf(cfg, Y, np.array([2.0, 1.0]))
+        torch.cuda.synchronize()
+        outs.append((r.X_hist.cpu().numpy(), r.ancestry.cpu().numpy(), r.log_zetas.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    np.testing.assert_allclose(outs[0][2], outs[1][2], rtol=1e-12)
+
+
+def test_pf_multi_filter_batch(sem, c_oracle):
+    """n_filters side by side == the same filters run one at a time (independent chains on one GPU)."""
+    import torch
+    Y = _truth_Y(0, 9, 5, .1, False)
+    thetas = np.array([[2.0, 1.0], [1.5, 0.8], [2.5, 1.2]])
+    cfg = sem.engine.make_pf_config(0, 900, 9, n_filters=3, probs=.1, resampler=1, arith=1, seed=5, filter_id0=10,
+                                    mu=[20], n_population=[1000])
+    res = sem.engine.run_pf(cfg, Y, thetas)
+    torch.cuda.synchronize()
+    for f in range(3):
+        ref = c_oracle.pf_run(0, Y, thetas[f], False, .1, 900, resampler=1, arith=1, seed=5, filter_id=10 + f,
+                              mu=[20], npop=[1000])
+        assert np.array_equal(res.X_hist[f].permute(0, 2, 1).cpu().numpy(), ref["X_hist"])
+        np.testing.assert_allclose(res.log_zetas[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11)
+
+
+# ------------------------------------------------------------------ headline size: size-independent properties
+def test_pf_full_size_properties(sem, c_oracle):
+    """BASELINE config 4 size (SIR, pop 1e4, 1e5 particles, 101 observations): invariants of every particle."""
+    import torch
+    N, T, pop = 100_000, 101, 10_000
+    Y = bench_truth(T, pop)
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=1, seed=2024, mu=[20], n_population=[pop])
+    res = sem.engine.run_pf(cfg, Y, np.array([.4, .2]))
+    torch.cuda.synchronize()
+    assert int(res.status.cpu()[0]) == 0
+    X = res.X_hist[0]                                                     # [T][3][N]
+    assert bool((X.sum(1) == pop).all())                                  # S+I+R conserved (closed population)
+    assert bool((X >= 0).all())
+    A = res.ancestry[0].long()
+    assert bool((A[1:, 1:] >= A[1:, :-1]).all())                          # systematic resampling => sorted ancestors
+    assert bool(((A >= 0) & (A < N)).all())
+    for p in (1, 50, 100):                                                # along every lineage S only falls, R only rises
+        par = X[p - 1][:, A[p]]
+        assert bool((X[p][0] <= par[0]).all()) and bool((X[p][2] >= par[2]).all())
+    lz = res.log_zetas[0].cpu().numpy()
+    assert np.all(np.isfinite(lz)) and np.all(np.diff(lz) < 0)
+    # likelihood estimate agrees with the oracle's at a size it finishes in seconds (Monte-Carlo error only)
+    ref = [c_oracle.pf_run(0, Y, [.4, .2], False, .1, 4000, resampler=1, arith=1, seed=s, mu=[20], npop=[pop])["log_zetas"][-1]
+           for s in range(4)]
+    assert abs(lz[-1] - np.mean(ref)) < 6 * (np.std(ref) + 0.05) + 0.5
+    # and matches the oracle exactly on a 20k-particle filter of the same problem
+    cfg2 = sem.engine.make_pf_config(0, 20_000, T, probs=.1, resampler=1, arith=1, seed=77, mu=[20], n_population=[pop])
+    r2 = sem.engine.run_pf(cfg2, Y, np.array([.4, .2]))
+    o2 = c_oracle.pf_run(0, Y, [.4, .2], False, .1, 20_000, resampler=1, arith=1, seed=77, mu=[20], npop=[pop])
+    assert np.array_equal(r2.X_hist[0].permute(0, 2, 1).cpu().numpy(), o2["X_hist"])
+    assert np.array_equal(r2.ancestry[0].cpu().numpy(), o2["ancestry"])
+    np.testing.assert_allclose(r2.log_zetas[0].cpu().numpy(), o2["log_zetas"], rtol=1e-11)
+
+
+def bench_truth(T, pop, beta=.4, gamma=.2, p=.1, seed=0):
+    """Deterministic SIR ODE truth (RK4, one row per day) observed with binomial(p): the bench workload's Y."""
+    y = np.array([pop - 20.0, 20.0, 0.0])
+    rows = [y.copy()]
+    f = lambda v: np.array([-beta * v[0] * v[1] / pop, beta * v[0] * v[1] / pop - gamma * v[1], gamma * v[1]])
+    for _ in range(T - 1):
+        for _ in range(20):
+            h = 1 / 20
+            k1 = f(y); k2 = f(y + h / 2 * k1); k3 = f(y + h / 2 * k2); k4 = f(y + h * k3)
+            y = y + h / 6 * (k1 + 2 * k2 + 2 * k3 + k4)
+        rows.append(y.copy())
+    truth = np.array(rows)
+    return np.random.RandomState(seed).binomial(truth.astype(int), p).astype(float)
+
+
+# ------------------------------------------------------------------ ABC (abc_algo.py)
+def test_abc_replay_vs_reference(sem):
+    from oracle import sem_oracle as so
+    g = golden("abc_sir_small")
+    obs = g["observed"]
+    n = g["distance"].size
+    streams, offs = [], [0]
+    for i in range(n):
+        st = so.MTStream(g["mt_key"][i], g["mt_pos"][i])
+        so.abc_trial(obs, g["theta"][i, 0], g["theta"][i, 1], g["n_start"][i], st)
+        streams.append(np.array(st.log)); offs.append(offs[-1] + len(st.log))
+    out = sem.engine.abc_trials(obs, n, float(g["threshold"]), [0, 5, 0, 5], want_traj=True,
+                                replay=dict(theta=g["theta"], n_start=g["n_start"], u=np.concatenate(streams), off=np.array(offs)))
+    d = out["distance"].cpu().numpy()
+    tr = out["traj"].cpu().numpy()
+    np.testing.assert_allclose(d, g["distance"], rtol=1e-13)
+    assert np.array_equal(tr[:, :, 1], g["I_sim"].astype(np.int32)) and np.array_equal(tr[:, :, 2], g["R_sim"].astype(np.int32))
+    acc = d <= float(g["threshold"])
+    assert np.array_equal(tr[acc], g["trajectories"][:, :, 1:].astype(np.int32))
+
+
+@pytest.mark.parametrize("arith", [0, 1])
+def test_abc_philox_vs_oracle(sem, c_oracle, arith):
+    g = golden("abc_sir_small")
+    obs = g["observed"]
+    n = 3000
+    out = sem.engine.abc_trials(obs, n, 45.0, [0, 5, 0, 5], seed=42, trial0=1000, arith=arith, want_traj=True)
+    ref = c_oracle.abc_trials(obs, n, 45.0, (0, 5, 0, 5), arith=arith, seed=42, trial0=1000)
+    assert np.array_equal(out["theta"].cpu().numpy(), ref["theta"])
+    assert np.array_equal(out["traj"].cpu().numpy(), ref["traj"])
+    np.testing.assert_allclose(out["distance"].cpu().numpy(), ref["distance"], rtol=1e-13)
+    assert int(out["n_events"].cpu()[0]) == ref["n_events"]
+    # early rejection never changes the accepted set or its distances
+    er = sem.engine.abc_trials(obs, n, 45.0, [0, 5, 0, 5], seed=42, trial0=1000, arith=arith, early_reject=True)
+    d0, d1 = out["distance"].cpu().numpy(), er["distance"].cpu().numpy()
+    assert np.array_equal(d0 <= 45.0, d1 <= 45.0) and np.array_equal(d0[d0 <= 45.0], d1[d1 <= 45.0])
+    assert int(er["n_events"].cpu()[0]) < ref["n_events"]
+
+
+def test_abc_algo_dropin(sem, c_oracle):
+    g = golden("abc_sir_small")
+    obs = g["observed"]
+    st = {}
+    post, traj = sem.abc_algo.abc_algo(obs, 5, 45.0, {"beta": [0, 5], "gamma": [0, 5]}, seed=7, batch=4096, stats=st)
+    assert sorted(post) == ["beta", "gamma"] and len(post["beta"]) == 5 and traj.shape == (5, obs.shape[0], 4)
+    assert np.array_equal(traj[0, :, 0], np.arange(obs.shape[0]))
+    # same accepted trials as the oracle's sequential acceptance over trial ids 0,1,2,...
+    ref = c_oracle.abc_trials(obs, 4096, 45.0, (0, 5, 0, 5), arith=1, seed=7, trial0=0)
+    acc = np.nonzero(ref["distance"] <= 45.0)[0][:5]
+    assert np.array_equal(st["accepted_ids"], acc)
+    assert np.array_equal(np.array(post["beta"]), ref["theta"][acc, 0])
+    assert np.array_equal(traj[:, :, 1:], ref["traj"][acc].astype(float))
+    for k in range(5):
+        d = sem.abc_algo.distance_function(traj[k, :, 2], obs[:, 1], traj[k, :, 3], obs[:, 2])
+        assert d <= 45.0 and abs(d - st["distances"][k]) < 1e-9
+
+
+# ------------------------------------------------------------------ PMCMC drop-in
+def test_particle_mcmc_dropin(sem):
+    np.random.seed(3)
+    Y = _truth_Y(0, 10, 5, .1, False)
+    st = {}
+    thetas, lik, trajs = sem.particle_mcmc(Y, sem.ModelType.SIR, [2.0, 1.0], .01, n_chains=40, probs=.1, n_particles=2000,
+                                           n_population=1000, mu=20, seed=11, stats=st)
+    assert thetas.shape == (40, 2) and lik.shape == (40,) and trajs.shape == (10, 40, 3)
+    assert np.all(thetas > 0) and np.all(lik > 0)
+    assert np.all(trajs.sum(2) == 1000)
+    assert 1 <= st["acceptances"] <= 40 and st["filter_runs"] >= 1
+    # p_obs estimated (probs=None): last theta component is the clipped observation probability (pmcmc.py:283-287)
+    th2, _, _ = sem.particle_mcmc(Y, sem.ModelType.SIR, [2.0, 1.0, .1], .001, n_chains=5, probs=None, n_particles=500,
+                                  n_population=1000, mu=20, seed=12)
+    assert th2.shape == (5, 3) and np.all((th2[:, 2] >= 0) & (th2[:, 2] <= 1))
+
+
+def test_host_buffer_entry_point(sem, c_oracle):
+    """sem_pf_run_host: the C-ABI call with HOST buffers returns the reference's (T,N,C)/(T,N) float64 layout."""
+    L = sem._lib.load()
+    N, T = 640, 9
+    Y = _truth_Y(0, T, 5, .1, False)
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=1, seed=321, mu=[20], n_population=[1000])
+    theta = np.array([2.0, 1.0])
+    lz = np.zeros(T); z = np.zeros(T); H = np.zeros((T, N, 3)); A = np.zeros((T, N)); ev = np.zeros(1, dtype=np.uint64)
+    p = lambda v: v.ctypes.data_as(C.c_void_p)
+    rc = L.sem_pf_run_host(C.byref(cfg), p(Y), p(theta), None, p(lz), p(z), p(H), p(A), p(ev))
+    assert rc == 0
+    ref = c_oracle.pf_run(0, Y, theta, False, .1, N, resampler=1, arith=1, seed=321, mu=[20], npop=[1000])
+    assert np.array_equal(H, ref["X_hist"].astype(float)) and np.array_equal(A, ref["ancestry"].astype(float))
+    np.testing.assert_allclose(lz, ref["log_zetas"], rtol=1e-11)
+    np.testing.assert_allclose(z, np.exp(ref["log_zetas"]), rtol=1e-10)
+    assert int(ev[0]) == ref["n_events"]
