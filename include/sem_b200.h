@@ -179,6 +179,8 @@ int sem_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4
 int sem_test_binom_logpmf(const double *k, const double *n, const double *p, double *out, int64_t count);
 int sem_test_norm_logpdf(const double *y, const double *x, const double *probs, double *out, int64_t count);
 int sem_test_poisson(double mu, uint64_t seed, uint32_t domain, uint32_t c2, double *out, int64_t count);
+/* the FAST arithmetic's -log(x), x in (0,1], and 1/a (host arrays in, host arrays out) */
+int sem_test_fast_math(const double *x, const double *a, double *neglog_out, double *rcp_out, int64_t count);
 
 #ifdef __cplusplus
 }

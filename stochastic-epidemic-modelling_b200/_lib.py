@@ -20,7 +20,7 @@ EXPORTS = [
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
     "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
     "sem_ssa_simulate", "sem_abc_run",
-    "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson",
+    "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson", "sem_test_fast_math",
 ]
 
 
@@ -102,6 +102,8 @@ def load():
     L.sem_test_binom_logpmf.restype = C.c_int
     L.sem_test_norm_logpdf.restype = C.c_int
     L.sem_test_poisson.restype = C.c_int
+    L.sem_test_fast_math.restype = C.c_int
+    L.sem_test_fast_math.argtypes = [C.c_void_p] * 4 + [C.c_int64]
     L.sem_test_poisson.argtypes = [C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64]
     if L.sem_abi_version() != 1:
         raise SemError("libsem_b200.so ABI version mismatch")

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsem_b200.so")
 SOURCES = ["sem_pf.cu", "sem_sim_abc.cu"]
-HEADERS = ["sem_common.cuh", "sem_host.h", os.path.join("..", "..", "include", "sem_b200.h")]
+HEADERS = ["sem_common.cuh", "sem_host.h", "sem_logtab.inc", os.path.join("..", "..", "include", "sem_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -58,6 +58,47 @@ struct PairSource<false> {
     }
 };
 
+// ------------------------------------------------------------------------------------------ fast fp64 helpers
+// -log(x) for x in (0,1] without a division: x = z * 2^k with z in [0.6875, 1.375); a 128-entry table gives
+// (1/c, log c) for the mantissa-bit subinterval of z; r = z/c - 1 (one FMA, |r| < 2^-8) and
+// log1p(r) = r - r^2/2 + ... - r^6/6 (truncation < 3e-18).  Absolute error ~1e-16 + 1e-16*|log x| (checked against
+// libm on the GPU by tests/test_gpu_parity.py::test_fast_math).  The table lives in shared memory.
+static __constant__ double2 kLogTab[128] = {
+#include "sem_logtab.inc"
+};
+
+__device__ __forceinline__ void load_logtab(double2 *smem_tab) {
+    for (int i = threadIdx.x; i < 128; i += blockDim.x) smem_tab[i] = kLogTab[i];
+}
+
+__device__ __forceinline__ double neg_log_fast(double x, const double2 *tab) {
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int tmp = hi - 0x3fe60000;
+    const int i = (tmp >> 13) & 127;
+    const int k = tmp >> 20;                                   // arithmetic shift: floor exponent offset (<= 0 here)
+    const double z = __hiloint2double(hi - (tmp & 0xfff00000), lo);
+    const double2 tc = tab[i];
+    const double r = __fma_rn(z, tc.x, -1.0);
+    const double w = __fma_rn((double)k, 0x1.62e42fefa39efp-1, tc.y);
+    const double r2 = __dmul_rn(r, r);
+    double p = __fma_rn(r, -1.0 / 6, 1.0 / 5);
+    p = __fma_rn(r, p, -1.0 / 4);
+    p = __fma_rn(r, p, 1.0 / 3);
+    p = __fma_rn(r, p, -1.0 / 2);
+    return -__fma_rn(r2, p, __dadd_rn(w, r));
+}
+
+// 1/a for normal positive a: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps, no IEEE fix-up path.
+__device__ __forceinline__ double rcp_nr(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = __fma_rn(-a, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-a, y, 1.0);
+    y = __fma_rn(y, e, y);
+    return y;
+}
+
 template <>
 struct PairSource<true> {
     const double *u; long long pos, end;
@@ -169,12 +210,15 @@ struct SirModel {
         else r[0] = __dmul_rn(__dmul_rn(bN, x[0]), x[1]);
         r[1] = __dmul_rn(gamma, x[1]);                                                                  // :39
     }
+    // TRACK_R = false leaves the removed count to fix_removed() (R = N - S - I): one fp64 op less per event
+    template <bool TRACK_R = true>
     __device__ __forceinline__ void apply(double *x, int j) const {                                     // :43-46
         const bool inf = (j == 0);
         x[0] = inf ? x[0] - 1.0 : x[0];
         x[1] = inf ? x[1] + 1.0 : x[1] - 1.0;
-        x[2] = inf ? x[2] : x[2] + 1.0;
+        if (TRACK_R) x[2] = inf ? x[2] : x[2] + 1.0;
     }
+    __device__ __forceinline__ void fix_removed(double *x) const { x[2] = N - x[0] - x[1]; }
 };
 
 struct SeirModel {
@@ -193,18 +237,20 @@ struct SeirModel {
         r[1] = __dmul_rn(alpha, x[1]);                                                                  // :108
         r[2] = __dmul_rn(gamma, x[2]);                                                                  // :109
     }
+    template <bool TRACK_R = true>
     __device__ __forceinline__ void apply(double *x, int j) const {                                     // :113-117
         x[0] = (j == 0) ? x[0] - 1.0 : x[0];
         x[1] = (j == 0) ? x[1] + 1.0 : ((j == 1) ? x[1] - 1.0 : x[1]);
         x[2] = (j == 1) ? x[2] + 1.0 : ((j == 2) ? x[2] - 1.0 : x[2]);
-        x[3] = (j == 2) ? x[3] + 1.0 : x[3];
+        if (TRACK_R) x[3] = (j == 2) ? x[3] + 1.0 : x[3];
     }
+    __device__ __forceinline__ void fix_removed(double *x) const { x[3] = N - x[0] - x[1] - x[2]; }
 };
 
 template <int G_>
 struct SubModel {
     static constexpr int G = G_, C = 3 * G_, R = G_ * G_ + G_, NTHETA = G_ * G_ + 1;
-    double betas[G_ * G_], bN[G_ * G_], gamma, N;
+    double betas[G_ * G_], bN[G_ * G_], gamma, N, Ng[G_];
     __device__ __forceinline__ void setup(const double *th, const double *x) {
 #pragma unroll
         for (int i = 0; i < G * G; i++) betas[i] = th[i];                 // betas[a*G+b]: infector a -> susceptible b (:182)
@@ -214,6 +260,7 @@ struct SubModel {
         for (int g = 0; g < G; g++) {                                      // :176 per-group builtin sum, then sum(N) (:182)
             const double ng = __dadd_rn(__dadd_rn(__dadd_rn(0.0, x[3 * g]), x[3 * g + 1]), x[3 * g + 2]);
             tot = __dadd_rn(tot, ng);
+            Ng[g] = ng;
         }
         N = tot;
         const double invN = __ddiv_rn(1.0, N);
@@ -240,6 +287,7 @@ struct SubModel {
             r[a * (G + 1) + G] = __dmul_rn(gamma, x[3 * a + 1]);         // :184
         }
     }
+    template <bool TRACK_R = true>
     __device__ __forceinline__ void apply(double *x, int j) const {       // :183,185
         const int a = j / (G + 1), k = j - a * (G + 1);
 #pragma unroll
@@ -248,62 +296,72 @@ struct SubModel {
             const bool recover = (k == G) && (a == g);
             x[3 * g] = infect ? x[3 * g] - 1.0 : x[3 * g];
             x[3 * g + 1] = infect ? x[3 * g + 1] + 1.0 : (recover ? x[3 * g + 1] - 1.0 : x[3 * g + 1]);
-            x[3 * g + 2] = recover ? x[3 * g + 2] + 1.0 : x[3 * g + 2];
+            if (TRACK_R) x[3 * g + 2] = recover ? x[3 * g + 2] + 1.0 : x[3 * g + 2];
         }
+    }
+    __device__ __forceinline__ void fix_removed(double *x) const {
+#pragma unroll
+        for (int g = 0; g < G; g++) x[3 * g + 2] = Ng[g] - x[3 * g] - x[3 * g + 1];
     }
 };
 
 // One Gillespie draw (split so that no uniform is consumed when the total propensity is not positive):
-//   ssa_total : propensities r[] in the reference's reaction order and a0 = builtin sum() = 0 + r0 + r1 ...
-//   ssa_pick  : waiting time tau and reaction index j from (u1,u2).
-// REF reproduces numpy's legacy exponential / choice arithmetic (gillespie_algo.py:62-63):
-//   tau = -log(1-u1) * (1/a0);  p = r/a0; cdf = cumsum(p); cdf /= cdf[-1]; j = #(cdf <= u2)
-// FAST: tau = -log(1-u1)/a0;  j = #(prefix(r) <= u2*a0)
+//   ssa_total     : propensities r[] in the reference's reaction order and a0 = builtin sum() = 0 + r0 + r1 ...
+//   ssa_pick_ref  : numpy's legacy exponential / choice arithmetic (gillespie_algo.py:62-63):
+//                   tau = -log(1-u1) * (1/a0);  p = r/a0; cdf = cumsum(p); cdf /= cdf[-1]; j = #(cdf <= u2)
+//   ssa_pick_fast : tau = -log(1-u1) / a0 with the table log and a Newton reciprocal; j = #(prefix(r) <= u2*a0).
+//                   Takes the Philox doubles d = 1+u in [1,2): 1-u1 = 2-d1 and u2*a0 = fma(d2,a0,-a0), both exact
+//                   rewrites.  tau agrees with the IEEE value to ~2 ulp; an integer outcome can differ from the CPU
+//                   oracle's FAST order only when t+tau hits the interval end to within those ulps.
 template <class Model, int ARITH>
 __device__ __forceinline__ double ssa_total(const Model &m, const double *x, double *r) {
     m.template rates<ARITH>(x, r);
-    double a0 = 0.0;
+    double a0 = (ARITH == SEM_ARITH_REFERENCE) ? __dadd_rn(0.0, r[0]) : r[0];   // 0 + r0 is r0 (rates are never -0)
 #pragma unroll
-    for (int i = 0; i < Model::R; i++) a0 = __dadd_rn(a0, r[i]);
+    for (int i = 1; i < Model::R; i++) a0 = __dadd_rn(a0, r[i]);
     return a0;
 }
 
-template <class Model, int ARITH>
-__device__ __forceinline__ void ssa_pick(const double *r, double a0, double u1, double u2, double &tau, int &j) {
+template <class Model>
+__device__ __forceinline__ void ssa_pick_ref(const double *r, double a0, double u1, double u2, double &tau, int &j) {
     const double E = -log(__dsub_rn(1.0, u1));
+    tau = __dmul_rn(E, __ddiv_rn(1.0, a0));
+    double cdf[Model::R], acc = 0.0;
+#pragma unroll
+    for (int i = 0; i < Model::R; i++) { acc = __dadd_rn(acc, __ddiv_rn(r[i], a0)); cdf[i] = acc; }
     j = 0;
-    if (ARITH == SEM_ARITH_REFERENCE) {
-        tau = __dmul_rn(E, __ddiv_rn(1.0, a0));
-        double cdf[Model::R], acc = 0.0;
 #pragma unroll
-        for (int i = 0; i < Model::R; i++) { acc = __dadd_rn(acc, __ddiv_rn(r[i], a0)); cdf[i] = acc; }
+    for (int i = 0; i < Model::R; i++) j += (__ddiv_rn(cdf[i], acc) <= u2) ? 1 : 0;
+    j = min(j, Model::R - 1);
+}
+
+template <class Model>
+__device__ __forceinline__ void ssa_pick_fast(const double *r, double a0, double d1, double d2, const double2 *tab,
+                                              double &tau, int &j) {
+    const double E = neg_log_fast(__dsub_rn(2.0, d1), tab);
+    tau = __dmul_rn(E, rcp_nr(a0));
+    const double v = __fma_rn(d2, a0, -a0);
+    double acc = 0.0;
+    j = 0;
 #pragma unroll
-        for (int i = 0; i < Model::R; i++) j += (__ddiv_rn(cdf[i], acc) <= u2) ? 1 : 0;
-        j = min(j, Model::R - 1);
-    } else {
-        tau = __ddiv_rn(E, a0);
-        const double v = __dmul_rn(u2, a0);
-        double acc = 0.0;
-#pragma unroll
-        for (int i = 0; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
-    }
+    for (int i = 0; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
 }
 
 // Direct method from t = 0 to max_time (gillespie_algo.py:48-70).  Both uniforms are drawn before the
 // overshoot test, so the discarded last event consumes a pair too (:62-66).  Returns pairs drawn, or -1 when a
 // replay buffer ran dry.  Rec(t, x) is called after every accepted event.
-template <class Model, int ARITH, bool REPLAY, class Rec>
-__device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src, Rec rec) {
+template <class Model, bool REPLAY, class Rec>
+__device__ __forceinline__ long long ssa_run_ref(const Model &m, double *x, double max_time, PairSource<REPLAY> &src, Rec rec) {
     double t = 0.0;
     long long pairs = 0;
     while (m.alive(x)) {
         double r[Model::R], u1, u2, tau;
         int j;
-        const double a0 = ssa_total<Model, ARITH>(m, x, r);
+        const double a0 = ssa_total<Model, SEM_ARITH_REFERENCE>(m, x, r);
         if (!(a0 > 0)) break;                                              // (the reference would raise inside choice())
         if (!src.next(u1, u2)) return -1;
         pairs++;
-        ssa_pick<Model, ARITH>(r, a0, u1, u2, tau, j);
+        ssa_pick_ref<Model>(r, a0, u1, u2, tau, j);
         const double tn = __dadd_rn(t, tau);
         if (tn > max_time) break;                                          // :65
         t = tn;
@@ -311,6 +369,46 @@ __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double m
         rec(t, x);
     }
     return pairs;
+}
+
+// FAST order, Philox only.  The words of event k+1 are generated while event k's fp64 chain runs (they do not
+// depend on the state), which gives every thread two independent instruction streams.
+template <class Model, bool TRACK_R, class Rec>
+__device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, double max_time, PairSource<false> &src,
+                                                  const double2 *tab, Rec rec) {
+    double t = 0.0;
+    long long pairs = 0;
+    uint4 w = src.raw();
+    bool go = m.alive(x);
+    // Single basic block per event (the overshoot test is a predicate, not a loop exit) so that the scheduler can
+    // interleave the integer Philox chain of event k+1 with the fp64 chain of event k.
+    while (go) {
+        double r[Model::R], tau;
+        int j;
+        const double a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+        const uint4 wn = src.raw();
+        ssa_pick_fast<Model>(r, a0, bits_to_d12(w.x, w.y), bits_to_d12(w.z, w.w), tab, tau, j);
+        const double tn = __dadd_rn(t, tau);
+        const bool drew = a0 > 0;                                          // no draw when nothing can happen
+        const bool fire = drew && !(tn > max_time);                        // gillespie_algo.py:65
+        pairs += drew ? 1 : 0;
+        if (fire) {
+            t = tn;
+            m.template apply<TRACK_R>(x, j);
+            rec(t, x);
+        }
+        w = wn;
+        go = fire && m.alive(x);
+    }
+    if (!TRACK_R) m.fix_removed(x);
+    return pairs;
+}
+
+template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
+__device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,
+                                             const double2 *tab, Rec rec) {
+    if constexpr (ARITH == SEM_ARITH_FAST && !REPLAY) return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, rec);
+    else return ssa_run_ref<Model, REPLAY>(m, x, max_time, src, rec);
 }
 
 struct NoRec { __device__ __forceinline__ void operator()(double, const double *) const {} };

@@ -91,9 +91,14 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int p) {
     __shared__ double sm[32];
+    __shared__ double2 s_tab[128];
+    __shared__ unsigned long long s_pairs;
     __shared__ bool is_last;
     const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
     if (P.status[f] != 0) return;                            // collapsed (or replay exhausted) earlier
+    if (ARITH == SEM_ARITH_FAST && !REPLAY && p > 0) load_logtab(s_tab);
+    if (tid == 0) s_pairs = 0ull;
+    __syncthreads();
     const int N = P.N, j = b * P.ppb + tid;
     const bool active = tid < P.ppb && j < N;
     const int par = p & 1;
@@ -162,7 +167,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
             } else {
                 src.init(P.key, (uint32_t)j, (uint32_t)p, stream_word(DOM_SSA, fid));
             }
-            pairs = ssa_run<Model, ARITH, REPLAY>(m, x, P.dt, src, NoRec());
+            pairs = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.dt, src, s_tab, NoRec());
             if (pairs < 0) { replay_dry = true; pairs = 0; }
         }
         // -------------------------------------------------------------------- store X[p] (SoA, coalesced)
@@ -171,7 +176,14 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
         for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
     }
     if (replay_dry) atomicExch(&P.status[f], SEM_ERR_REPLAY);
-    if (P.n_events && pairs) atomicAdd(&P.n_events[f], (unsigned long long)pairs);
+    if (P.n_events && p > 0) {                               // one global atomic per CTA, not per particle
+        unsigned long long wp = (unsigned long long)pairs;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) wp += __shfl_xor_sync(0xffffffffu, wp, d);
+        if ((tid & 31) == 0 && wp) atomicAdd(&s_pairs, wp);
+        __syncthreads();
+        if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
+    }
     if (p >= P.T - 1) return;                                // the final state is never weighed
 
     // ------------------------------------------------------------------------ weigh against Y[p] (pmcmc.py:178-181)
@@ -263,10 +275,11 @@ static int choose_ppb(const sem_pf_config *c) {
     if (c->block_particles > 0) return c->block_particles > kMaxThreads ? kMaxThreads : c->block_particles;
     const long long all = (long long)c->n_particles * c->n_filters;
     const long long per_sm = (all + sm_count() - 1) / sm_count();
-    long long ppb = per_sm <= kMaxThreads ? ((per_sm + 31) / 32) * 32 : 256;
+    // co-resident population: exactly ceil(N*F/SMs) particles per CTA (threads = that rounded up to a warp), so the
+    // grid is one CTA per SM; larger populations use 256-wide CTAs scheduled in waves
+    long long ppb = per_sm <= kMaxThreads ? per_sm : 256;
     if (ppb < 32) ppb = 32;
-    const long long nround = ((long long)c->n_particles + 31) / 32 * 32;
-    if (ppb > nround) ppb = nround;
+    if (ppb > c->n_particles) ppb = c->n_particles;
     return (int)ppb;
 }
 

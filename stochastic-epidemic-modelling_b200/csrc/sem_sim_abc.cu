@@ -42,6 +42,9 @@ struct EventLogRef { EventLog<C> *l; __device__ __forceinline__ void operator()(
 
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
+    __shared__ double2 s_tab[128];
+    if (ARITH == SEM_ARITH_FAST && !REPLAY) load_logtab(s_tab);
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_sims) return;
     double x[Model::C];
@@ -57,10 +60,10 @@ __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
     if (P.cap > 0) {
         EventLog<Model::C> log{P.times + (size_t)i * P.cap, P.states + (size_t)i * P.cap * Model::C, P.cap, 0};
         log(0.0, x);                                                      // row 0 = initial state at time 0 (gillespie_algo.py:28-33)
-        const long long pr = ssa_run<Model, ARITH, REPLAY>(m, x, P.max_time, src, EventLogRef<Model::C>{&log});
+        const long long pr = ssa_run<Model, ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
         rows = pr < 0 ? -1 : log.n;
     } else {
-        const long long pr = ssa_run<Model, ARITH, REPLAY>(m, x, P.max_time, src, NoRec());
+        const long long pr = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.max_time, src, s_tab, NoRec());
         rows = pr < 0 ? -1 : 0;
     }
 #pragma unroll
@@ -97,6 +100,9 @@ constexpr int kAbcMaxDays = 128;
 template <int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
     __shared__ double s_obs[kAbcMaxDays * 2];                            // (I_obs, R_obs) per day
+    __shared__ double2 s_tab[128];
+    constexpr bool FAST = (ARITH == SEM_ARITH_FAST) && !REPLAY;
+    if (FAST) load_logtab(s_tab);
     for (int i = threadIdx.x; i < P.T; i += blockDim.x) { s_obs[2 * i] = P.obs[3 * i + 1]; s_obs[2 * i + 1] = P.obs[3 * i + 2]; }
     __syncthreads();
     const int T = P.T;
@@ -159,12 +165,13 @@ __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
             bool rejected = false, dry = false;
             if (!done) {
                 double r[2], u1, u2, tau; int j;
-                const double a0 = ssa_total<SirModel, ARITH>(m, x, r);
+                const double a0 = ssa_total<SirModel, FAST ? SEM_ARITH_FAST : SEM_ARITH_REFERENCE>(m, x, r);
                 if (!(a0 > 0)) done = true;
                 else if (!src.next(u1, u2)) { done = true; dry = true; }
                 else {
                     my_events++;
-                    ssa_pick<SirModel, ARITH>(r, a0, u1, u2, tau, j);
+                    if constexpr (FAST) ssa_pick_fast<SirModel>(r, a0, u1 + 1.0, u2 + 1.0, s_tab, tau, j);   // u+1 exact (52-bit u)
+                    else ssa_pick_ref<SirModel>(r, a0, u1, u2, tau, j);
                     const double tn = __dadd_rn(t, tau);
                     if (tn > t_stop) done = true;
                     else {
@@ -275,6 +282,14 @@ __global__ void k_poisson(double mu, PhiloxKey key, uint32_t domain, uint32_t c2
     if (i < cnt) { PairSource<false> s; s.init(key, (uint32_t)i, c2, stream_word(domain, 0)); out[i] = poisson_draw(s, mu); }
 }
 
+__global__ void k_fast_math(const double *x, const double *a, double *nl, double *rc, long long cnt) {
+    __shared__ double2 s_tab[128];
+    load_logtab(s_tab);
+    __syncthreads();
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i < cnt) { nl[i] = neg_log_fast(x[i], s_tab); rc[i] = rcp_nr(a[i]); }
+}
+
 template <class F>
 static int host_map3(const double *a, const double *b, const double *c, double *out, int64_t n, F launch) {
     double *d = nullptr;
@@ -304,6 +319,17 @@ int sem_test_binom_logpmf(const double *k, const double *n, const double *p, dou
 }
 int sem_test_norm_logpdf(const double *y, const double *x, const double *probs, double *out, int64_t count) {
     return host_map3(y, x, probs, out, count, [&](double *a, double *b, double *c, double *o) { k_norm<<<(unsigned)((count + 127) / 128), 128>>>(a, b, c, o, count); });
+}
+int sem_test_fast_math(const double *x, const double *a, double *neglog_out, double *rcp_out, int64_t count) {
+    double *d = nullptr;
+    SEM_CUDA(cudaMalloc(&d, (size_t)count * 4 * sizeof(double)));
+    cudaMemcpy(d, x, count * 8, cudaMemcpyHostToDevice); cudaMemcpy(d + count, a, count * 8, cudaMemcpyHostToDevice);
+    k_fast_math<<<(unsigned)((count + 127) / 128), 128>>>(d, d + count, d + 2 * count, d + 3 * count, count);
+    cudaMemcpy(neglog_out, d + 2 * count, count * 8, cudaMemcpyDeviceToHost);
+    cudaError_t e = cudaMemcpy(rcp_out, d + 3 * count, count * 8, cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    if (e != cudaSuccess) { set_error("fast math test: %s", cudaGetErrorString(e)); return SEM_ERR_CUDA; }
+    return SEM_OK;
 }
 int sem_test_poisson(double mu, uint64_t seed, uint32_t domain, uint32_t c2, double *out, int64_t count) {
     double *d = nullptr;

@@ -73,6 +73,23 @@ def test_poisson_matches_oracle(sem, c_oracle, mu):
         assert abs(out.mean() - mu) < 5 * np.sqrt(mu / n) + 1e-9
 
 
+def test_fast_math(sem):
+    """-log(x) (table + polynomial) and the Newton reciprocal of the FAST arithmetic against libm / IEEE."""
+    L = sem._lib.load()
+    rng = np.random.RandomState(0)
+    u = np.floor(rng.random_sample(200000) * 2.0**52) / 2.0**52                     # what the Philox mapping produces
+    x = np.concatenate([1.0 - u, [1.0, 2.0**-52, 0.5, 0.6875, 0.687499999, 0.75, 1 - 2.0**-52], 2.0**-rng.randint(0, 53, 1000)])
+    a = np.concatenate([10 ** rng.uniform(-6, 9, x.size - 3), [1.0, 3.0, 1e-300]])
+    nl = np.empty_like(x); rc = np.empty_like(x)
+    p = lambda v: v.ctypes.data_as(C.c_void_p)
+    assert L.sem_test_fast_math(p(x), p(a), p(nl), p(rc), C.c_int64(x.size)) == 0
+    ref = -np.log(x)
+    err = np.abs(nl - ref)
+    assert np.all(err <= 2.3e-16 * np.maximum(ref, 1.0)), err.max()                  # ~1 ulp of max(E, 1)
+    assert nl[x == 1.0][0] == 0.0
+    np.testing.assert_allclose(rc[:-1], 1.0 / a[:-1], rtol=2.3e-16)                   # <= 1 ulp
+
+
 # ------------------------------------------------------------------ SSA replay vs the reference (gillespie_algo.py)
 @pytest.mark.parametrize("name", golden_names("ssa_"))
 def test_ssa_replay_vs_reference(sem, name):
@@ -167,11 +184,15 @@ def test_path_sampler_vs_reference(sem, name):
 
 
 # ------------------------------------------------------------------ production (Philox) path vs the C oracle
-def _truth_Y(model, T, seed, probs, normal):
+def _truth_Y(model, T, seed, probs, normal, dying=False, G=2):
     rng = np.random.RandomState(seed)
     t = np.arange(T)
-    if model == 1:
-        base = np.stack([900 - 40 * t, 20 + 10 * t, 20 + 15 * t, 15 * t], 1)
+    if dying:       # sub-critical outbreak: I dies out, a few recoveries; many particles get weight exactly 0 (k > n)
+        base = np.stack([290 - 0 * t, 0 * t, np.minimum(t, 2)], 1)
+    elif model == 1:
+        base = np.stack([900 - 40 * t, 10 * t, 20 + 15 * t, 15 * t], 1)       # E_0 = 0 (pmcmc.py:163)
+    elif model == 2 and G == 3:
+        base = np.stack([190 - 8 * t, 5 + 3 * t, 5 * t, 280 - 12 * t, 8 + 5 * t, 7 * t, 140 - 6 * t, 4 + 3 * t, 3 * t], 1)
     elif model == 2:
         base = np.stack([400 - 20 * t, 15 + 8 * t, 12 * t, 600 - 30 * t, 20 + 12 * t, 18 * t], 1)
     elif model == 3:
@@ -203,7 +224,7 @@ PHILOX_CASES = [
 def test_pf_philox_vs_oracle(sem, c_oracle, case):
     import torch
     model, G, theta, npop, mu, N, T, normal, probs, resampler, arith, block = case
-    Y = _truth_Y(model, T, 5, probs, normal)
+    Y = _truth_Y(model, T, 5, probs, normal, dying=(model == 0 and theta[1] > theta[0]), G=G)
     seed = 0xC0FFEE1234
     cfg = sem.engine.make_pf_config(model, N, T, G=G, observations=normal, probs=probs, resampler=resampler, arith=arith,
                                     seed=seed, filter_id0=3, mu=mu, n_population=npop, block_particles=block)
