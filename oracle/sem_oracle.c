@@ -245,28 +245,28 @@ static const double SFE[16] = {0.0, 0.08106146679532726, 0.04134069595540929, 0.
     0.01041126526197209, 0.009255462182712733, 0.008330563433362871, 0.007573675487951841,
     0.006942840107209530, 0.006408994188004207, 0.005951370112758848, 0.005554733551962801};
 
-/* stirlerr(n) = log(n!) - log(sqrt(2 pi n) (n/e)^n), integer n >= 0 (Loader 2000) */
+/* stirlerr(n) = log(n!) - log(sqrt(2 pi n) (n/e)^n), integer n >= 0 (Loader 2000); one reciprocal for n >= 16 */
 static double stirlerr(double n) {
     const double S0 = 1.0 / 12, S1 = 1.0 / 360, S2 = 1.0 / 1260, S3 = 1.0 / 1680, S4 = 1.0 / 1188;
     if (n < 16) return SFE[(int)n];
-    double nn = n * n;
-    if (n > 500) return (S0 - S1 / nn) / n;
-    if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
-    if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
-    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+    double inv = 1.0 / n, i2 = inv * inv;
+    if (n > 500) return (S0 - S1 * i2) * inv;
+    if (n > 80) return (S0 - (S1 - S2 * i2) * i2) * inv;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 * i2) * i2) * i2) * inv;
+    return (S0 - (S1 - (S2 - (S3 - S4 * i2) * i2) * i2) * i2) * inv;
 }
 
-/* bd0(x, np) = x log(x/np) + np - x, evaluated stably near x = np (Loader 2000) */
+/* bd0(x, np) = x log(x/np) + np - x.  Near x = np (|x-np| < 0.1 (x+np)) Loader's series
+ * (x-np) v + 2 x v sum_{j>=1} v^(2j)/(2j+1), v = (x-np)/(x+np), summed as a fixed degree-8 polynomial in v^2
+ * (|v| < 0.1: the first dropped term is < 1e-19 of the leading one). */
 static double bd0(double x, double np) {
-    if (fabs(x - np) < 0.1 * (x + np)) {
-        double v = (x - np) / (x + np), s = (x - np) * v, ej = 2 * x * v;
-        v = v * v;
-        for (int j = 1; j < 1000; j++) {
-            ej *= v;
-            double s1 = s + ej / (2 * j + 1);
-            if (s1 == s) return s1;
-            s = s1;
-        }
+    double d = x - np;
+    if (fabs(d) < 0.1 * (x + np)) {
+        double v = d / (x + np), v2 = v * v;
+        double q = 1.0 / 17;
+        q = q * v2 + 1.0 / 15; q = q * v2 + 1.0 / 13; q = q * v2 + 1.0 / 11; q = q * v2 + 1.0 / 9;
+        q = q * v2 + 1.0 / 7; q = q * v2 + 1.0 / 5; q = q * v2 + 1.0 / 3;
+        return d * v + (2 * x * v) * (v2 * q);
     }
     return x * log(x / np) + np - x;
 }

@@ -63,7 +63,9 @@ struct PairSource<false> {
 // (1/c, log c) for the mantissa-bit subinterval of z; r = z/c - 1 (one FMA, |r| < 2^-8) and
 // log1p(r) = r - r^2/2 + ... - r^6/6 (truncation < 3e-18).  Absolute error ~1e-16 + 1e-16*|log x| (checked against
 // libm on the GPU by tests/test_gpu_parity.py::test_fast_math).  The table lives in shared memory.
-static __constant__ double2 kLogTab[128] = {
+// (global memory, not __constant__: the copy into shared memory indexes it by thread id, which the constant cache
+// would serialise)
+static __device__ const double2 kLogTab[128] = {
 #include "sem_logtab.inc"
 };
 
@@ -88,15 +90,15 @@ __device__ __forceinline__ double neg_log_fast(double x, const double2 *tab) {
     return -__fma_rn(r2, p, __dadd_rn(w, r));
 }
 
-// 1/a for normal positive a: hardware seed (rcp.approx.ftz.f64, ~20 bits) + two Newton steps, no IEEE fix-up path.
+// 1/a for normal positive a, no IEEE fix-up path: hardware seed y0 (rcp.approx.ftz.f64, rel. error e ~ 2^-20 or
+// better), then 1/a = y0 (1 + e + e^2 + e^3 + ...) cut after e^3 (a 4th-order step, 2^-80) and rounded: <= 1 ulp.
 __device__ __forceinline__ double rcp_nr(double a) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double e = __fma_rn(-a, y, 1.0);
-    y = __fma_rn(y, e, y);
-    e = __fma_rn(-a, y, 1.0);
-    y = __fma_rn(y, e, y);
-    return y;
+    const double e = __fma_rn(-a, y, 1.0);
+    const double e2 = __dmul_rn(e, e);
+    const double q = __fma_rn(e2, e, __dadd_rn(e2, e));     // e + e^2 + e^3
+    return __fma_rn(y, q, y);
 }
 
 template <>
@@ -119,23 +121,23 @@ static __constant__ double kSfe[16] = {0.0, 0.08106146679532726, 0.0413406959554
 __device__ __forceinline__ double stirlerr(double n) {   // log(n!) - log(sqrt(2 pi n)(n/e)^n), Loader (2000)
     const double S0 = 1.0 / 12, S1 = 1.0 / 360, S2 = 1.0 / 1260, S3 = 1.0 / 1680, S4 = 1.0 / 1188;
     if (n < 16) return kSfe[(int)n];
-    const double nn = n * n;
-    if (n > 500) return (S0 - S1 / nn) / n;
-    if (n > 80) return (S0 - (S1 - S2 / nn) / nn) / n;
-    if (n > 35) return (S0 - (S1 - (S2 - S3 / nn) / nn) / nn) / n;
-    return (S0 - (S1 - (S2 - (S3 - S4 / nn) / nn) / nn) / nn) / n;
+    const double inv = 1.0 / n, i2 = inv * inv;
+    if (n > 500) return (S0 - S1 * i2) * inv;
+    if (n > 80) return (S0 - (S1 - S2 * i2) * i2) * inv;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 * i2) * i2) * i2) * inv;
+    return (S0 - (S1 - (S2 - (S3 - S4 * i2) * i2) * i2) * i2) * inv;
 }
 
-__device__ __forceinline__ double bd0(double x, double np) {   // x log(x/np) + np - x, stable near x = np
-    if (fabs(x - np) < 0.1 * (x + np)) {
-        double v = (x - np) / (x + np), s = (x - np) * v, ej = 2 * x * v;
-        v = v * v;
-        for (int j = 1; j < 1000; j++) {
-            ej *= v;
-            const double s1 = s + ej / (2 * j + 1);
-            if (s1 == s) return s1;
-            s = s1;
-        }
+// bd0(x, np) = x log(x/np) + np - x; near x = np Loader's series as a fixed degree-8 polynomial in v^2,
+// v = (x-np)/(x+np), |v| < 0.1 (no data-dependent loop, one division)
+__device__ __forceinline__ double bd0(double x, double np) {
+    const double d = x - np;
+    if (fabs(d) < 0.1 * (x + np)) {
+        const double v = d / (x + np), v2 = v * v;
+        double q = 1.0 / 17;
+        q = q * v2 + 1.0 / 15; q = q * v2 + 1.0 / 13; q = q * v2 + 1.0 / 11; q = q * v2 + 1.0 / 9;
+        q = q * v2 + 1.0 / 7; q = q * v2 + 1.0 / 5; q = q * v2 + 1.0 / 3;
+        return d * v + (2 * x * v) * (v2 * q);
     }
     return x * log(x / np) + np - x;
 }

@@ -22,7 +22,7 @@
 namespace sem {
 
 struct PfDev {
-    int N, T, Cobs, obs_kind, resampler, nb, ppb, hist_rows, model, n_filters, ntheta, init_poisson;
+    int N, T, Cobs, obs_kind, resampler, nb, ppb, hist_rows, model, n_filters, ntheta, init_poisson, pfx_in_smem;
     double probs, dt;
     PhiloxKey key;
     uint32_t filter_id0;
@@ -88,104 +88,12 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
     return lw;
 }
 
-template <class Model, int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int p) {
-    __shared__ double sm[32];
-    __shared__ double2 s_tab[128];
-    __shared__ unsigned long long s_pairs;
-    __shared__ bool is_last;
-    const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
-    if (P.status[f] != 0) return;                            // collapsed (or replay exhausted) earlier
-    if (ARITH == SEM_ARITH_FAST && !REPLAY && p > 0) load_logtab(s_tab);
-    if (tid == 0) s_pairs = 0ull;
-    __syncthreads();
-    const int N = P.N, j = b * P.ppb + tid;
-    const bool active = tid < P.ppb && j < N;
-    const int par = p & 1;
-    const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
-    int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
-    int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
-    const uint32_t fid = P.filter_id0 + f;
-    double x[Model::C];
-    long long pairs = 0;
-    bool replay_dry = false;
-
-    if (active) {
-        if (p == 0) {
-            // ---------------------------------------------------------------- X_0 (pmcmc.py:156-170)
-            if (!P.init_poisson) {
-#pragma unroll
-                for (int c = 0; c < Model::C; c++) x[c] = (double)P.X0[(size_t)c * N + j];
-            } else {
-#pragma unroll
-                for (int c = 0; c < Model::C; c++) x[c] = 0.0;
-#pragma unroll
-                for (int g = 0; g < Model::G; g++) {
-                    PairSource<false> src; src.init(P.key, (uint32_t)j, (uint32_t)g, stream_word(DOM_INIT, fid));
-                    const double i0 = poisson_draw(src, P.mu[g]);
-                    constexpr bool seir = (Model::C == 4);
-                    x[seir ? 2 : 3 * g + 1] = i0;
-                    x[seir ? 0 : 3 * g] = P.npop[g] - i0;
-                }
-            }
-            Af[(size_t)row * N + j] = 0;
-        } else {
-            // ---------------------------------------------------------------- resample (pmcmc.py:187-193)
-            const double total = P.total[par ^ 1][f];
-            double u;
-            if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
-            else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
-                const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
-                const double u0 = bits_to_d12(w.x, w.y) - 1.0;
-                u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
-            } else {
-                const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
-                u = bits_to_d12(w.x, w.y) - 1.0;
-            }
-            const double v = __dmul_rn(u, total);
-            const double *pfx = P.pfx[par ^ 1] + (size_t)f * P.nb;
-            int lo = 0, hi = P.nb;                          // last CTA index with pfx[b] <= v  (pfx[0] = 0)
-            while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= v) lo = mid; else hi = mid; }
-            const int base = lo * P.ppb, len = min(P.ppb, N - base);
-            const double sc = P.scale[par ^ 1][(size_t)f * P.nb + lo], pf = pfx[lo];
-            const double *L = P.L[par ^ 1] + (size_t)f * N + base;
-            int a = 0, e = len;                              // first i with pf + sc*L[i] > v
-            while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, L[mid], pf) <= v) a = mid + 1; else e = mid; }
-            a = base + min(a, len - 1);
-            Af[(size_t)row * N + j] = a;
-            // ---------------------------------------------------------------- gather parent (pmcmc.py:195-199)
-            const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
-#pragma unroll
-            for (int c = 0; c < Model::C; c++) x[c] = (double)Xp[(size_t)c * N + a];
-            // ---------------------------------------------------------------- propagate (pmcmc.py:200-220)
-            Model m;
-            m.setup(P.theta + (size_t)f * P.ntheta, x);
-            PairSource<REPLAY> src;
-            if constexpr (REPLAY) {
-                const size_t q = (size_t)(p - 1) * N + j;
-                src.init(P.ssa_u, P.ssa_off[q], P.ssa_off[q + 1]);
-            } else {
-                src.init(P.key, (uint32_t)j, (uint32_t)p, stream_word(DOM_SSA, fid));
-            }
-            pairs = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.dt, src, s_tab, NoRec());
-            if (pairs < 0) { replay_dry = true; pairs = 0; }
-        }
-        // -------------------------------------------------------------------- store X[p] (SoA, coalesced)
-        int32_t *Xr = Xf + (size_t)row * Model::C * N;
-#pragma unroll
-        for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
-    }
-    if (replay_dry) atomicExch(&P.status[f], SEM_ERR_REPLAY);
-    if (P.n_events && p > 0) {                               // one global atomic per CTA, not per particle
-        unsigned long long wp = (unsigned long long)pairs;
-#pragma unroll
-        for (int d = 16; d; d >>= 1) wp += __shfl_xor_sync(0xffffffffu, wp, d);
-        if ((tid & 31) == 0 && wp) atomicAdd(&s_pairs, wp);
-        __syncthreads();
-        if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
-    }
-    if (p >= P.T - 1) return;                                // the final state is never weighed (SURVEY D7)
-
+// Weigh the CTA's particles against Y[p], CTA-local scan, and (last CTA to arrive) the step's global combine.
+template <class Model>
+__device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p, const int f, const int b, const int tid,
+                                                    const bool active, const int j, const double *x, double *sm,
+                                                    bool *is_last) {
+    const int N = P.N, par = p & 1;
     // ------------------------------------------------------------------------ weigh against Y[p] (pmcmc.py:178-181)
     double lw = -CUDART_INF;
     if (active) {
@@ -203,9 +111,9 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
     // ------------------------------------------------------------------------ last CTA finalizes the step
     __threadfence();
     __syncthreads();
-    if (tid == 0) is_last = (atomicAdd(&P.counter[f], 1u) == (unsigned)(P.nb - 1));
+    if (tid == 0) *is_last = (atomicAdd(&P.counter[f], 1u) == (unsigned)(P.nb - 1));
     __syncthreads();
-    if (!is_last) return;
+    if (!*is_last) return;
     __threadfence();
     const double2 *part = P.part + (size_t)f * P.nb;
     double M = -CUDART_INF;
@@ -238,6 +146,124 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
         }
         P.counter[f] = 0;
     }
+}
+
+// Step 0: X_0 (pmcmc.py:156-170), given or I_0 ~ Poisson(mu), then weigh against Y[0].
+template <class Model>
+__global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
+    __shared__ double sm[32];
+    __shared__ bool is_last;
+    const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+    const int N = P.N, j = b * P.ppb + tid;
+    const bool active = tid < P.ppb && j < N;
+    const uint32_t fid = P.filter_id0 + f;
+    double x[Model::C];
+    if (active) {
+        if (!P.init_poisson) {
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = (double)P.X0[(size_t)c * N + j];
+        } else {
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = 0.0;
+#pragma unroll
+            for (int g = 0; g < Model::G; g++) {
+                PairSource<false> src; src.init(P.key, (uint32_t)j, (uint32_t)g, stream_word(DOM_INIT, fid));
+                const double i0 = poisson_draw(src, P.mu[g]);
+                constexpr bool seir = (Model::C == 4);
+                x[seir ? 2 : 3 * g + 1] = i0;
+                x[seir ? 0 : 3 * g] = P.npop[g] - i0;
+            }
+        }
+        P.ancestry[(size_t)f * P.hist_rows * N + j] = 0;
+        int32_t *Xr = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
+    }
+    if (P.T > 1) weigh_scan_finalize<Model>(P, 0, f, b, tid, active, j, x, sm, &is_last);
+}
+
+// Step p >= 1: resample, gather, propagate, store, weigh (see the file header).
+template <class Model, int ARITH, bool REPLAY>
+__global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int p) {
+    extern __shared__ double s_pfx[];                        // previous step's CTA prefixes (when they fit)
+    __shared__ double sm[32];
+    __shared__ double2 s_tab[128];
+    __shared__ unsigned long long s_pairs;
+    __shared__ bool is_last;
+    const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+    if (P.status[f] != 0) return;                            // collapsed (or replay exhausted) earlier
+    const int N = P.N, j = b * P.ppb + tid;
+    const bool active = tid < P.ppb && j < N;
+    const int par = p & 1;
+    const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
+    const double *pfx_g = P.pfx[par ^ 1] + (size_t)f * P.nb;
+    if (ARITH == SEM_ARITH_FAST && !REPLAY) load_logtab(s_tab);
+    if (P.pfx_in_smem) for (int i = tid; i < P.nb; i += blockDim.x) s_pfx[i] = pfx_g[i];
+    if (tid == 0) s_pairs = 0ull;
+    __syncthreads();
+    const double *pfx = P.pfx_in_smem ? s_pfx : pfx_g;
+    int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
+    int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
+    const uint32_t fid = P.filter_id0 + f;
+    double x[Model::C];
+    long long pairs = 0;
+    bool replay_dry = false;
+
+    if (active) {
+        // -------------------------------------------------------------------- resample (pmcmc.py:187-193)
+        const double total = P.total[par ^ 1][f];
+        double u;
+        if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
+        else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
+            const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+            const double u0 = bits_to_d12(w.x, w.y) - 1.0;
+            u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
+        } else {
+            const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+            u = bits_to_d12(w.x, w.y) - 1.0;
+        }
+        const double v = __dmul_rn(u, total);
+        int lo = 0, hi = P.nb;                              // last CTA index with pfx[b] <= v  (pfx[0] = 0)
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= v) lo = mid; else hi = mid; }
+        const int base = lo * P.ppb, len = min(P.ppb, N - base);
+        const double sc = P.scale[par ^ 1][(size_t)f * P.nb + lo], pf = pfx[lo];
+        const double *L = P.L[par ^ 1] + (size_t)f * N + base;
+        int a = 0, e = len;                                  // first i with pf + sc*L[i] > v
+        while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, L[mid], pf) <= v) a = mid + 1; else e = mid; }
+        a = base + min(a, len - 1);
+        Af[(size_t)row * N + j] = a;
+        // -------------------------------------------------------------------- gather parent (pmcmc.py:195-199)
+        const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) x[c] = (double)Xp[(size_t)c * N + a];
+        // -------------------------------------------------------------------- propagate (pmcmc.py:200-220)
+        Model m;
+        m.setup(P.theta + (size_t)f * P.ntheta, x);
+        PairSource<REPLAY> src;
+        if constexpr (REPLAY) {
+            const size_t q = (size_t)(p - 1) * N + j;
+            src.init(P.ssa_u, P.ssa_off[q], P.ssa_off[q + 1]);
+        } else {
+            src.init(P.key, (uint32_t)j, (uint32_t)p, stream_word(DOM_SSA, fid));
+        }
+        pairs = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.dt, src, s_tab, NoRec());
+        if (pairs < 0) { replay_dry = true; pairs = 0; }
+        // -------------------------------------------------------------------- store X[p] (SoA, coalesced)
+        int32_t *Xr = Xf + (size_t)row * Model::C * N;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
+    }
+    if (replay_dry) atomicExch(&P.status[f], SEM_ERR_REPLAY);
+    if (P.n_events) {                                        // one global atomic per CTA, not per particle
+        unsigned long long wp = (unsigned long long)pairs;
+#pragma unroll
+        for (int d = 16; d; d >>= 1) wp += __shfl_xor_sync(0xffffffffu, wp, d);
+        if ((tid & 31) == 0 && wp) atomicAdd(&s_pairs, wp);
+        __syncthreads();
+        if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
+    }
+    if (p >= P.T - 1) return;                                // the final state is never weighed (SURVEY D7)
+    weigh_scan_finalize<Model>(P, p, f, b, tid, active, j, x, sm, &is_last);
 }
 
 // (T,C,N) int32 -> (T,N,C) float64, the layout pmcmc.py:151 returns
@@ -315,9 +341,11 @@ static WsLayout ws_layout(const sem_pf_config *c) {
 
 template <class Model>
 static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 grid, int threads, cudaStream_t s) {
-    if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, 0, s>>>(P, p);
-    else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, 0, s>>>(P, p);
-    else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, 0, s>>>(P, p);
+    const size_t smem = P.pfx_in_smem ? (size_t)P.nb * sizeof(double) : 0;
+    if (p == 0) pf_init<Model><<<grid, threads, 0, s>>>(P);
+    else if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, smem, s>>>(P, p);
+    else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, smem, s>>>(P, p);
+    else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, smem, s>>>(P, p);
 }
 
 }  // namespace sem
@@ -368,6 +396,7 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     P.N = cfg->n_particles; P.T = cfg->n_obs; P.Cobs = cfg->n_obs_cols; P.obs_kind = cfg->obs_kind; P.resampler = cfg->resampler;
     P.nb = w.nb; P.ppb = w.ppb; P.hist_rows = hist_rows(cfg); P.model = cfg->model; P.n_filters = cfg->n_filters;
     P.ntheta = model_ntheta(cfg->model, G); P.init_poisson = buf->X0 == nullptr;
+    P.pfx_in_smem = w.nb <= 4096;                           // 32 KB of dynamic shared memory at most
     P.probs = cfg->probs; P.dt = cfg->dt;
     P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32); P.filter_id0 = cfg->filter_id0;
     for (int g = 0; g < SEM_MAX_GROUPS; g++) { P.mu[g] = cfg->mu[g]; P.npop[g] = cfg->n_population[g]; }
