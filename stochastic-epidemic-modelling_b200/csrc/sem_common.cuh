@@ -73,6 +73,8 @@ __device__ __forceinline__ void load_logtab(double2 *smem_tab) {
     for (int i = threadIdx.x; i < 128; i += blockDim.x) smem_tab[i] = kLogTab[i];
 }
 
+static __constant__ double kLogPoly[6] = {-1.0 / 6, 1.0 / 5, -1.0 / 4, 1.0 / 3, -1.0 / 2, 0x1.62e42fefa39efp-1 /* ln 2 */};
+
 __device__ __forceinline__ double neg_log_fast(double x, const double2 *tab) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int tmp = hi - 0x3fe60000;
@@ -81,12 +83,12 @@ __device__ __forceinline__ double neg_log_fast(double x, const double2 *tab) {
     const double z = __hiloint2double(hi - (tmp & 0xfff00000), lo);
     const double2 tc = tab[i];
     const double r = __fma_rn(z, tc.x, -1.0);
-    const double w = __fma_rn((double)k, 0x1.62e42fefa39efp-1, tc.y);
+    const double w = __fma_rn((double)k, kLogPoly[5], tc.y);
     const double r2 = __dmul_rn(r, r);
-    double p = __fma_rn(r, -1.0 / 6, 1.0 / 5);
-    p = __fma_rn(r, p, -1.0 / 4);
-    p = __fma_rn(r, p, 1.0 / 3);
-    p = __fma_rn(r, p, -1.0 / 2);
+    double p = __fma_rn(r, kLogPoly[0], kLogPoly[1]);
+    p = __fma_rn(r, p, kLogPoly[2]);
+    p = __fma_rn(r, p, kLogPoly[3]);
+    p = __fma_rn(r, p, kLogPoly[4]);
     return -__fma_rn(r2, p, __dadd_rn(w, r));
 }
 
@@ -343,10 +345,10 @@ __device__ __forceinline__ void ssa_pick_fast(const double *r, double a0, double
     const double E = neg_log_fast(__dsub_rn(2.0, d1), tab);
     tau = __dmul_rn(E, rcp_nr(a0));
     const double v = __fma_rn(d2, a0, -a0);
-    double acc = 0.0;
-    j = 0;
+    double acc = r[0];
+    j = (acc <= v) ? 1 : 0;
 #pragma unroll
-    for (int i = 0; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
+    for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
 }
 
 // Direct method from t = 0 to max_time (gillespie_algo.py:48-70).  Both uniforms are drawn before the
@@ -379,7 +381,7 @@ template <class Model, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, double max_time, PairSource<false> &src,
                                                   const double2 *tab, Rec rec) {
     double t = 0.0;
-    long long pairs = 0;
+    int pairs = 0;                                                         // < 2^31 events per particle-step
     uint4 w = src.raw();
     bool go = m.alive(x);
     // Single basic block per event (the overshoot test is a predicate, not a loop exit) so that the scheduler can

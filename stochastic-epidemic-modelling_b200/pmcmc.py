@@ -92,9 +92,15 @@ def particle_filter(Y, type_model, theta_proposal, observations=False, probs=.1,
     zetas = torch.exp(res.log_zetas[0])
     if output == "torch":
         return zetas, res.X_hist[0].permute(0, 2, 1), res.ancestry[0]
-    hidden = res.hidden_process(0).cpu().numpy()
-    anc = res.ancestry[0].to(torch.float64).cpu().numpy()
-    return zetas.cpu().numpy(), hidden, anc
+    # device -> pinned host memory (torch's caching host allocator recycles the blocks once the arrays are dropped)
+    hd = res.hidden_process(0)
+    ad = res.ancestry[0].to(torch.float64)
+    hidden = torch.empty(hd.shape, dtype=torch.float64, pin_memory=True)
+    anc = torch.empty(ad.shape, dtype=torch.float64, pin_memory=True)
+    zh = torch.empty(zetas.shape, dtype=torch.float64, pin_memory=True)
+    hidden.copy_(hd, non_blocking=True); anc.copy_(ad, non_blocking=True); zh.copy_(zetas, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return zh.numpy(), hidden.numpy(), anc.numpy()
 
 
 def pf_loglik(Y, type_model, theta_proposal, observations=False, probs=.1, n_particles=1000, n_population=4820,
