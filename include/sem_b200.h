@@ -118,6 +118,37 @@ int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *the
                     double *log_zetas_out, double *zetas_out, double *hidden_process_out, double *ancestry_out,
                     uint64_t *n_events_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Particle-sharded filter (one filter too large for one GPU): every rank owns a contiguous slice
+ * of the N_global particles and runs these three calls per step; the host (torch.distributed / NCCL) all-gathers the
+ * per-shard weight summaries (max logw M_r, sum exp(logw - M_r)) and all-to-all-v's the children records.
+ * cfg->n_particles is the LOCAL particle count, n_filters = 1.  Resampling is global systematic: slot j draws
+ * v_j = ((j+u0)/N_global)*total and takes the first particle whose global cdf G_r + s_r*cdf_local exceeds it.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct sem_shard_step {
+    int32_t step;               /* p >= 1 */
+    int32_t particle_offset;    /* global index of this shard's particle 0 (keys the Philox streams) */
+    int64_t n_global;           /* N_global */
+    double u0;                  /* the step's single systematic uniform */
+    double total;               /* global weight total, in units of exp(-M_global) */
+    double total_local;         /* this shard's total in its own units (summary[1] of the previous step) */
+    double G, G_next;           /* global cdf at this shard's first particle / at the next shard's first particle */
+    double s;                   /* exp(M_r - M_global) */
+    int64_t slot0;              /* first global slot whose ancestor lives on this shard */
+} sem_shard_step;
+
+/* X_0 of the local slice + weights against Y[0]; summary: device double[2] <- (M_r, total_r) */
+int sem_shard_init(const sem_pf_config *cfg, const sem_pf_buffers *buf, int32_t particle_offset, double *summary,
+                   void *stream);
+/* writes one record int32[C+1] = (state, global ancestor index) per child of this shard's particles, ordered by slot,
+ * into send_records (device, capacity = number of slots in [slot0, slot0 + children)) */
+int sem_shard_offspring(const sem_pf_config *cfg, const sem_pf_buffers *buf, const sem_shard_step *st,
+                        int32_t *send_records, void *stream);
+/* recv_records: device int32 [n_particles][C+1] for the local slots; propagates them to time p, stores X[p] /
+ * ancestry[p] (global indices), weighs against Y[p] and refreshes summary */
+int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, const sem_shard_step *st,
+                        const int32_t *recv_records, double *summary, void *stream);
+
 /* particle_path_sampler (pmcmc.py:236-248).  chosen < 0: pick uniformly with Philox(seed); exact = 0 keeps
  * the reference's off-by-one ancestry indexing, 1 follows the true genealogy.  traj: device [T][C] int32. */
 int sem_path_sample(const int32_t *X_hist, const int32_t *ancestry, int32_t T, int32_t N, int32_t C,

@@ -19,7 +19,7 @@ EXPORTS = [
     "sem_abi_version", "sem_last_error", "sem_device_info",
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
     "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
-    "sem_ssa_simulate", "sem_abc_run",
+    "sem_ssa_simulate", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
     "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson", "sem_test_fast_math",
 ]
 
@@ -40,6 +40,14 @@ class PfBuffers(C.Structure):
         ("replay_resample_u", C.c_void_p), ("replay_ssa_u", C.c_void_p), ("replay_ssa_off", C.c_void_p),
         ("X_hist", C.c_void_p), ("ancestry", C.c_void_p), ("log_zetas", C.c_void_p), ("status", C.c_void_p),
         ("n_events", C.c_void_p), ("workspace", C.c_void_p),
+    ]
+
+
+class ShardStep(C.Structure):
+    _fields_ = [
+        ("step", C.c_int32), ("particle_offset", C.c_int32), ("n_global", C.c_int64), ("u0", C.c_double),
+        ("total", C.c_double), ("total_local", C.c_double), ("G", C.c_double), ("G_next", C.c_double), ("s", C.c_double),
+        ("slot0", C.c_int64),
     ]
 
 
@@ -87,6 +95,13 @@ def load():
     L.sem_pf_run.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p]
     L.sem_pf_run_host.restype = C.c_int
     L.sem_pf_run_host.argtypes = [C.POINTER(PfConfig)] + [C.c_void_p] * 8
+    L.sem_shard_init.restype = C.c_int
+    L.sem_shard_init.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_int32, C.c_void_p, C.c_void_p]
+    L.sem_shard_offspring.restype = C.c_int
+    L.sem_shard_offspring.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(ShardStep), C.c_void_p, C.c_void_p]
+    L.sem_shard_propagate.restype = C.c_int
+    L.sem_shard_propagate.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(ShardStep), C.c_void_p, C.c_void_p,
+                                      C.c_void_p]
     L.sem_path_sample.restype = C.c_int
     L.sem_path_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]

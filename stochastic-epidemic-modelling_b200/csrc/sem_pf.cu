@@ -41,6 +41,11 @@ struct PfDev {
     double *total[2];    // [F]
     double2 *part;       // [F][nb]  (m_b, s_b)
     unsigned int *counter;  // [F]
+    // particle-sharded filter (one shard of a larger filter, see sem_shard_*): global index of particle 0, the
+    // pre-gathered children records [N][C+1] (state, global ancestor) and the (M, total) summary of the local weights
+    int j0, sharded;
+    const int32_t *X_in;
+    double *summary;
 };
 
 constexpr int kMaxThreads = 768;
@@ -137,6 +142,11 @@ __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p,
     }
     if (tid == 0) {
         P.total[par][f] = carry;
+        if (P.sharded) {                                     // the host combines the shards' (M, total) summaries
+            P.summary[0] = M; P.summary[1] = carry;
+            P.counter[f] = 0;
+            return;
+        }
         double *lz = P.log_zetas + (size_t)f * P.T;
         if (!finiteM || !(carry > 0.0)) {
             P.status[f] = p + 1;                              // np.random.choice raises at step p+1 (pmcmc.py:191-192)
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
             for (int c = 0; c < Model::C; c++) x[c] = 0.0;
 #pragma unroll
             for (int g = 0; g < Model::G; g++) {
-                PairSource<false> src; src.init(P.key, (uint32_t)j, (uint32_t)g, stream_word(DOM_INIT, fid));
+                PairSource<false> src; src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)g, stream_word(DOM_INIT, fid));
                 const double i0 = poisson_draw(src, P.mu[g]);
                 constexpr bool seir = (Model::C == 4);
                 x[seir ? 2 : 3 * g + 1] = i0;
@@ -198,7 +208,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
     const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
     const double *pfx_g = P.pfx[par ^ 1] + (size_t)f * P.nb;
     if (ARITH == SEM_ARITH_FAST && !REPLAY) load_logtab(s_tab);
-    if (P.pfx_in_smem) for (int i = tid; i < P.nb; i += blockDim.x) s_pfx[i] = pfx_g[i];
+    if (P.pfx_in_smem && !P.sharded) for (int i = tid; i < P.nb; i += blockDim.x) s_pfx[i] = pfx_g[i];
     if (tid == 0) s_pairs = 0ull;
     __syncthreads();
     const double *pfx = P.pfx_in_smem ? s_pfx : pfx_g;
@@ -209,7 +219,14 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
     long long pairs = 0;
     bool replay_dry = false;
 
-    if (active) {
+    if (active && P.sharded) {
+        // -------------------------------------------------------------------- children records delivered by the exchange
+        const int32_t *rec = P.X_in + (size_t)j * (Model::C + 1);
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) x[c] = (double)rec[c];
+        Af[(size_t)row * N + j] = rec[Model::C];             // global ancestor index
+    }
+    if (active && !P.sharded) {
         // -------------------------------------------------------------------- resample (pmcmc.py:187-193)
         const double total = P.total[par ^ 1][f];
         double u;
@@ -236,6 +253,8 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
         const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
 #pragma unroll
         for (int c = 0; c < Model::C; c++) x[c] = (double)Xp[(size_t)c * N + a];
+    }
+    if (active) {
         // -------------------------------------------------------------------- propagate (pmcmc.py:200-220)
         Model m;
         m.setup(P.theta + (size_t)f * P.ntheta, x);
@@ -244,7 +263,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
             const size_t q = (size_t)(p - 1) * N + j;
             src.init(P.ssa_u, P.ssa_off[q], P.ssa_off[q + 1]);
         } else {
-            src.init(P.key, (uint32_t)j, (uint32_t)p, stream_word(DOM_SSA, fid));
+            src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
         }
         pairs = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.dt, src, s_tab, NoRec());
         if (pairs < 0) { replay_dry = true; pairs = 0; }
@@ -264,6 +283,58 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
     }
     if (p >= P.T - 1) return;                                // the final state is never weighed
     weigh_scan_finalize<Model>(P, p, f, b, tid, active, j, x, sm, &is_last);
+}
+
+// ---------------------------------------------------------------------------------------------- sharded filter
+// Global systematic resampling across shards.  Slot j of the global next generation draws
+// v_j = ((j + u0)/N) * Total and takes the first particle i whose global cdf exceeds v_j.  In offspring form:
+// particle i owns the slots [J(lower_i), J(upper_i)) with J(c) = smallest j with v_j >= c, and every boundary is
+// shared bit-for-bit by its two neighbours (CTA prefixes inside a shard, G_r / G_next between shards), so the
+// slots are covered without gaps.  Each shard writes one record (state, global ancestor index) per child, ordered
+// by slot; the host all-to-all-v's the records to the shards that own the slots.
+struct SlotMap { double u0, Nd, total; long long N; };
+
+__device__ __forceinline__ double slot_v(const SlotMap &sm, long long j) {
+    return __dmul_rn(__ddiv_rn(__dadd_rn((double)j, sm.u0), sm.Nd), sm.total);
+}
+__device__ __forceinline__ long long first_slot_ge(const SlotMap &sm, double c) {
+    if (c >= sm.total) return sm.N;                          // the global total closes the last particle's range
+    const double g = ceil(__dsub_rn(__dmul_rn(__ddiv_rn(c, sm.total), sm.Nd), sm.u0));
+    long long j = g < 0.0 ? 0 : (g > sm.Nd ? sm.N : (long long)g);
+    while (j > 0 && slot_v(sm, j - 1) >= c) j--;
+    while (j < sm.N && slot_v(sm, j) < c) j++;
+    return j;
+}
+
+struct OffDev {
+    int N, C, nb, ppb, j0;
+    const int32_t *X;            // [C][N] states of the generation being resampled
+    const double *L, *pfx, *scale;
+    double total_local, G, G_next, s;   // this shard's cdf = G + s * local cdf; G_next = next shard's G (or Total)
+    SlotMap sm;
+    long long slot0;             // J(G): first slot owned by this shard's particles
+    int32_t *send;               // [n_children][C+1]
+};
+
+__global__ void pf_offspring(const OffDev P) {
+    const int b = blockIdx.x, t = threadIdx.x, i = b * P.ppb + t;
+    if (t >= P.ppb || i >= P.N) return;
+    const int len = min(P.ppb, P.N - b * P.ppb);
+    const double pf = P.pfx[b], sc = P.scale[b];
+    const double lower = (t == 0) ? pf : __fma_rn(sc, P.L[i - 1], pf);
+    const bool last_in_cta = (t == len - 1), last_cta = (b == P.nb - 1);
+    const double upper = last_in_cta ? (last_cta ? P.total_local : P.pfx[b + 1]) : __fma_rn(sc, P.L[i], pf);
+    const double glo = (i == 0) ? P.G : __fma_rn(P.s, lower, P.G);
+    const double ghi = (last_in_cta && last_cta) ? P.G_next : __fma_rn(P.s, upper, P.G);
+    const long long c_lo = first_slot_ge(P.sm, glo), c_hi = first_slot_ge(P.sm, ghi);
+    if (c_hi <= c_lo) return;
+    int32_t st[SEM_MAX_GROUPS * 3];
+    for (int c = 0; c < P.C; c++) st[c] = P.X[(size_t)c * P.N + i];
+    for (long long ch = c_lo; ch < c_hi; ch++) {
+        int32_t *rec = P.send + (size_t)(ch - P.slot0) * (P.C + 1);
+        for (int c = 0; c < P.C; c++) rec[c] = st[c];
+        rec[P.C] = P.j0 + i;
+    }
 }
 
 // (T,C,N) int32 -> (T,N,C) float64, the layout pmcmc.py:151 returns
@@ -380,19 +451,17 @@ size_t sem_pf_hist_elems(const sem_pf_config *c) {
 size_t sem_pf_ancestry_elems(const sem_pf_config *c) { return validate(c) ? 0 : (size_t)c->n_filters * hist_rows(c) * c->n_particles; }
 int sem_pf_launch_count(const sem_pf_config *c) { return validate(c) ? 0 : c->n_obs; }
 
-int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream) {
+static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &P, WsLayout &w, bool &replay) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (!buf || !buf->Y || !buf->theta || !buf->X_hist || !buf->ancestry || !buf->log_zetas || !buf->status || !buf->workspace) {
         set_error("null buffer"); return SEM_ERR_INVALID;
     }
-    const bool replay = buf->replay_ssa_u != nullptr;
+    replay = buf->replay_ssa_u != nullptr;
     if (replay && (!buf->replay_resample_u || !buf->replay_ssa_off || !buf->X0)) { set_error("replay needs resample_u, ssa_off and X0"); return SEM_ERR_INVALID; }
-    cudaStream_t s = (cudaStream_t)stream;
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
-    const WsLayout w = ws_layout(cfg);
+    w = ws_layout(cfg);
     char *ws = (char *)buf->workspace;
-    PfDev P;
     P.N = cfg->n_particles; P.T = cfg->n_obs; P.Cobs = cfg->n_obs_cols; P.obs_kind = cfg->obs_kind; P.resampler = cfg->resampler;
     P.nb = w.nb; P.ppb = w.ppb; P.hist_rows = hist_rows(cfg); P.model = cfg->model; P.n_filters = cfg->n_filters;
     P.ntheta = model_ntheta(cfg->model, G); P.init_poisson = buf->X0 == nullptr;
@@ -409,25 +478,93 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
         P.scale[i] = (double *)(ws + w.scale[i]); P.total[i] = (double *)(ws + w.total[i]);
     }
     P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
+    P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr;
+    return SEM_OK;
+}
+
+static void launch_step(const sem_pf_config *cfg, const PfDev &P, const WsLayout &w, int p, bool replay, cudaStream_t s) {
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    const int threads = (w.ppb + 31) / 32 * 32;
+    const dim3 grid(w.nb, cfg->n_filters);
+    switch (cfg->model) {
+        case SEM_MODEL_SIR: launch_model<SirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
+        case SEM_MODEL_SEIR: launch_model<SeirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
+        default:
+            switch (G) {
+                case 1: launch_model<SubModel<1>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                case 2: launch_model<SubModel<2>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                case 3: launch_model<SubModel<3>>(P, p, cfg->arith, replay, grid, threads, s); break;
+                default: launch_model<SubModel<4>>(P, p, cfg->arith, replay, grid, threads, s); break;
+            }
+    }
+}
+
+int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream) {
+    PfDev P; WsLayout w; bool replay;
+    int rc = fill_dev(cfg, buf, P, w, replay);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
     SEM_CUDA(cudaMemsetAsync(P.counter, 0, cfg->n_filters * sizeof(unsigned int), s));
     SEM_CUDA(cudaMemsetAsync(P.status, 0, cfg->n_filters * sizeof(int32_t), s));
     SEM_CUDA(cudaMemsetAsync(P.log_zetas, 0, (size_t)cfg->n_filters * cfg->n_obs * sizeof(double), s));   // zetas[0] = 1 (pmcmc.py:154)
     if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
-    const int threads = (w.ppb + 31) / 32 * 32;
-    const dim3 grid(w.nb, cfg->n_filters);
-    for (int p = 0; p < cfg->n_obs; p++) {
-        switch (cfg->model) {
-            case SEM_MODEL_SIR: launch_model<SirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
-            case SEM_MODEL_SEIR: launch_model<SeirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
-            default:
-                switch (G) {
-                    case 1: launch_model<SubModel<1>>(P, p, cfg->arith, replay, grid, threads, s); break;
-                    case 2: launch_model<SubModel<2>>(P, p, cfg->arith, replay, grid, threads, s); break;
-                    case 3: launch_model<SubModel<3>>(P, p, cfg->arith, replay, grid, threads, s); break;
-                    default: launch_model<SubModel<4>>(P, p, cfg->arith, replay, grid, threads, s); break;
-                }
-        }
-    }
+    for (int p = 0; p < cfg->n_obs; p++) launch_step(cfg, P, w, p, replay, s);
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+// ---- one shard of a particle-sharded filter; the host drives the steps and the exchanges
+static int shard_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, int32_t particle_offset, double *summary,
+                     PfDev &P, WsLayout &w) {
+    bool replay;
+    int rc = fill_dev(cfg, buf, P, w, replay);
+    if (rc) return rc;
+    if (replay || cfg->n_filters != 1 || !summary) { set_error("shard calls need n_filters = 1, Philox mode and a summary buffer"); return SEM_ERR_INVALID; }
+    P.j0 = particle_offset; P.sharded = 1; P.summary = summary;
+    return SEM_OK;
+}
+
+int sem_shard_init(const sem_pf_config *cfg, const sem_pf_buffers *buf, int32_t particle_offset, double *summary, void *stream) {
+    PfDev P; WsLayout w;
+    int rc = shard_dev(cfg, buf, particle_offset, summary, P, w);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    SEM_CUDA(cudaMemsetAsync(P.counter, 0, sizeof(unsigned int), s));
+    SEM_CUDA(cudaMemsetAsync(P.status, 0, sizeof(int32_t), s));
+    if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, sizeof(unsigned long long), s));
+    launch_step(cfg, P, w, 0, false, s);
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+int sem_shard_offspring(const sem_pf_config *cfg, const sem_pf_buffers *buf, const sem_shard_step *st, int32_t *send_records,
+                        void *stream) {
+    PfDev P; WsLayout w; bool replay;
+    int rc = fill_dev(cfg, buf, P, w, replay);
+    if (rc) return rc;
+    if (!st || !send_records || st->step < 1 || st->step >= cfg->n_obs) { set_error("bad shard step"); return SEM_ERR_INVALID; }
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
+    const int par = (st->step - 1) & 1, prow = (st->step - 1) % P.hist_rows;
+    OffDev O;
+    O.N = P.N; O.C = C; O.nb = w.nb; O.ppb = w.ppb; O.j0 = st->particle_offset;
+    O.X = P.X_hist + (size_t)prow * C * P.N;
+    O.L = P.L[par]; O.pfx = P.pfx[par]; O.scale = P.scale[par];
+    O.total_local = st->total_local; O.G = st->G; O.G_next = st->G_next; O.s = st->s;
+    O.sm.u0 = st->u0; O.sm.Nd = (double)st->n_global; O.sm.total = st->total; O.sm.N = st->n_global;
+    O.slot0 = st->slot0; O.send = send_records;
+    pf_offspring<<<w.nb, (w.ppb + 31) / 32 * 32, 0, (cudaStream_t)stream>>>(O);
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, const sem_shard_step *st,
+                        const int32_t *recv_records, double *summary, void *stream) {
+    PfDev P; WsLayout w;
+    int rc = shard_dev(cfg, buf, st ? st->particle_offset : 0, summary, P, w);
+    if (rc) return rc;
+    if (!st || !recv_records || st->step < 1 || st->step >= cfg->n_obs) { set_error("bad shard step"); return SEM_ERR_INVALID; }
+    P.X_in = recv_records;
+    launch_step(cfg, P, w, st->step, false, (cudaStream_t)stream);
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }

@@ -150,3 +150,126 @@ def test_abc_sharding_world2_gloo(tmp_path, c_oracle):
     assert np.array_equal(r0["ids"], acc)
     assert np.array_equal(r0["theta"], ref["theta"][acc])
     assert np.array_equal(r0["traj"][:, :, 1:], ref["traj"][acc].astype(float))
+
+
+# ------------------------------------------------------------------ sharded filter: host-side logic
+def test_sharded_host_arithmetic(c_oracle):
+    from sem_b200 import sharded
+    # host Philox == oracle Philox; the step uniform is the first word pair mapped to [0,1)
+    for ctr, key in [((0, 0, 0, 0), (0, 0)), ((7, 1, 2, 3), (5, 9)), ((0, 0, 9, (2 << 24) | 5), (0x1234, 0xC0FFEE))]:
+        assert list(sharded.philox4x32_10(ctr, key)) == c_oracle.philox4x32(list(ctr), list(key))
+    u_ref, _ = c_oracle.philox_uniform_pair(0xC0FFEE00001234, 0, 0, 9, 2, 5)
+    assert sharded.step_uniform(0xC0FFEE00001234, 9, 5) == u_ref
+    # J(c) against brute force, and the exchange plan partitions every slot exactly once
+    rng = np.random.RandomState(0)
+    for n, world in [(10, 2), (101, 3), (64, 8), (7, 4)]:
+        w = rng.gamma(.5, size=n) * (rng.random_sample(n) > .3)
+        w[rng.randint(n)] += 1.0
+        u0 = float(rng.random_sample())
+        cdf = np.cumsum(w); total = float(cdf[-1])
+        v = ((np.arange(n) + u0) / float(n)) * total
+        for c in list(cdf[:-1]) + [0.0, total, total * .5]:
+            brute = int(np.argmax(v >= c)) if np.any(v >= c) else n
+            assert sharded.first_slot_ge(float(c), u0, n, total) == (n if c >= total else brute)
+        bounds = sharded.shard_bounds(n, world)
+        assert sum(c for _, c in bounds) == n and bounds[0][0] == 0
+        G = np.array([0.0] + [float(cdf[lo + cnt - 1]) for lo, cnt in bounds])
+        slot, counts = sharded.exchange_plan(G, total, u0, n, world)
+        assert slot[0] == 0 and slot[-1] == n and all(a <= b for a, b in zip(slot, slot[1:]))
+        assert np.array_equal(counts.sum(0), [c for _, c in bounds])             # every rank receives exactly its slots
+        assert np.array_equal(counts.sum(1), np.diff(slot))                      # every rank sends exactly its children
+        # ancestors implied by the plan == searchsorted on the global cdf
+        anc = np.searchsorted(cdf, v, side="right")
+        for r, (lo, cnt) in enumerate(bounds):
+            mine = anc[slot[r]:slot[r + 1]]
+            assert np.all((mine >= lo) & (mine < lo + cnt))
+    comb = sharded.combine_summaries(np.array([[-3.0, 2.0], [-1.0, 4.0], [-np.inf, 0.0]]))
+    assert comb["ok"] and comb["M"] == -1.0 and np.allclose(comb["G"], [0, 2 * np.exp(-2.0), 2 * np.exp(-2.0) + 4, 2 * np.exp(-2.0) + 4])
+    assert not sharded.combine_summaries(np.array([[-np.inf, 0.0], [-np.inf, 0.0]]))["ok"]
+
+
+SHARD_WORKER = r"""
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import sem_b200
+from sem_b200 import sharded
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+
+class FakeShard:
+    '''CPU stand-in for the three shard kernels: state = (id, generation, weight key); propagation is a
+    deterministic map; weights depend on the state.  Exercises the host logic + collectives of run_distributed.'''
+    def __init__(self, rank, world, model, Y, theta, n_global, **kw):
+        self.rank, self.world, self.n_global = rank, world, n_global
+        self.j0, self.n_local = sharded.shard_bounds(n_global, world)[rank]
+        self.dev = torch.device("cpu"); self.seed, self.filter_id, self.Cn = 99, 0, 3
+        self.x = None; self.hist = []; self.anc = []
+    def _summary(self):
+        lw = -((self.x[:, 0] * 7 + self.x[:, 1] * 3) % 11) / 3.0
+        lw[self.x[:, 0] % 5 == 0] = -np.inf
+        self.lw = lw
+        M = lw.max(); self.e = np.where(np.isfinite(lw), np.exp(lw - M), 0.0)
+        return torch.tensor([M, self.e.sum()], dtype=torch.float64)
+    def init(self):
+        j = np.arange(self.j0, self.j0 + self.n_local)
+        self.x = np.stack([j, 0 * j, (j * 13) % 17], 1).astype(np.int64)
+        self.hist.append(self.x.copy()); self.anc.append(np.zeros(self.n_local, np.int64))
+        return self._summary()
+    def offspring(self, p, comb, summ, u0, slot):
+        r = self.rank
+        cdf = comb["G"][r] + comb["s"][r] * np.cumsum(self.e)
+        cdf[-1] = comb["G"][r + 1]
+        lo = np.concatenate([[comb["G"][r]], cdf[:-1]])
+        recs = []
+        for i in range(self.n_local):
+            a, b = sharded.first_slot_ge(float(lo[i]), u0, self.n_global, comb["total"]), sharded.first_slot_ge(float(cdf[i]), u0, self.n_global, comb["total"])
+            for _ in range(a, b):
+                recs.append(list(self.x[i]) + [self.j0 + i])
+        assert len(recs) == slot[r + 1] - slot[r]
+        return torch.tensor(np.array(recs, dtype=np.int32).reshape(-1, 4))
+    def propagate(self, p, comb, summ, u0, slot, recv):
+        rec = recv.numpy().astype(np.int64)
+        self.x = np.stack([rec[:, 0], rec[:, 1] + 1, (rec[:, 2] * 5 + p + np.arange(self.j0, self.j0 + self.n_local)) % 17], 1)
+        self.hist.append(self.x.copy()); self.anc.append(rec[:, 3].copy())
+        return self._summary()
+
+Y = np.zeros((6, 3))
+out = sharded.run_distributed(Y, 0, np.zeros(2), 53, shard_cls=FakeShard)
+sh = out["shard"]
+np.savez(sys.argv[4] + ".%d.npz" % rank, logz=out["log_zetas"], hist=np.array(sh.hist), anc=np.array(sh.anc))
+dist.destroy_process_group()
+"""
+
+
+def test_sharded_exchange_world2_gloo(tmp_path):
+    """run_distributed over gloo (2 ranks) == the same toy filter run unsharded in numpy: global systematic
+    resampling, all-gather of summaries and all-to-all-v particle migration."""
+    from sem_b200 import sharded
+    port = str(31500 + os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(SHARD_WORKER)
+    out = str(tmp_path / "res")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    assert np.array_equal(r0["logz"], r1["logz"])
+    hist = np.concatenate([r0["hist"], r1["hist"]], axis=1); anc = np.concatenate([r0["anc"], r1["anc"]], axis=1)
+    # unsharded numpy reference of the same toy filter
+    n, T = 53, 6
+    j = np.arange(n)
+    x = np.stack([j, 0 * j, (j * 13) % 17], 1).astype(np.int64)
+    logz = np.zeros(T)
+    for p in range(1, T):
+        assert np.array_equal(hist[p - 1], x)
+        lw = -((x[:, 0] * 7 + x[:, 1] * 3) % 11) / 3.0
+        lw[x[:, 0] % 5 == 0] = -np.inf
+        M = lw.max(); e = np.where(np.isfinite(lw), np.exp(lw - M), 0.0)
+        logz[p] = logz[p - 1] + M + np.log(e.sum()) - np.log(n)
+        u0 = sharded.step_uniform(99, p, 0)
+        cdf = np.cumsum(e)
+        a = np.minimum(np.searchsorted(cdf, ((j + u0) / float(n)) * cdf[-1], side="right"), n - 1)
+        assert np.array_equal(anc[p], a)
+        x = np.stack([x[a, 0], x[a, 1] + 1, (x[a, 2] * 5 + p + j) % 17], 1)
+    assert np.array_equal(hist[T - 1], x)
+    np.testing.assert_allclose(r0["logz"], logz, rtol=1e-12)

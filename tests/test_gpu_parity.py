@@ -410,3 +410,31 @@ def test_host_buffer_entry_point(sem, c_oracle):
     np.testing.assert_allclose(lz, ref["log_zetas"], rtol=1e-11)
     np.testing.assert_allclose(z, np.exp(ref["log_zetas"]), rtol=1e-10)
     assert int(ev[0]) == ref["n_events"]
+
+
+# ------------------------------------------------------------------ particle-sharded filter
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("model,G,theta,npop,mu", [(0, 1, [2.0, 1.0], [1000], [20]), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20])])
+def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta, npop, mu):
+    """W shards with global systematic resampling + particle migration (lock-step emulation of the ranks on one GPU,
+    same kernels and host logic as the NCCL path) reproduce the unsharded filter and the oracle exactly."""
+    import torch
+    from sem_b200 import sharded
+    N, T = 3001, 9
+    Y = _truth_Y(model, T, 5, .1, False, G=G)
+    out = sharded.run_local(Y, model, np.array(theta, float), N, world, G=G, probs=.1, seed=4242, filter_id=5, mu=mu,
+                            n_population=npop)
+    torch.cuda.synchronize()
+    assert out["collapsed"] == 0
+    X = torch.cat([sh.X_hist for sh in out["shards"]], dim=2).permute(0, 2, 1).cpu().numpy()       # (T,N,C)
+    A = torch.cat([sh.ancestry for sh in out["shards"]], dim=1).cpu().numpy()
+    ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=1, seed=4242, filter_id=5, mu=mu, npop=npop)
+    assert np.array_equal(A, ref["ancestry"])
+    assert np.array_equal(X, ref["X_hist"])
+    np.testing.assert_allclose(out["log_zetas"], ref["log_zetas"], rtol=1e-11)
+    assert sum(sh.n_events for sh in out["shards"]) == ref["n_events"]
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=1, seed=4242, filter_id0=5, mu=mu,
+                                    n_population=npop)
+    one = sem.engine.run_pf(cfg, Y, np.array(theta, float))
+    assert np.array_equal(one.X_hist[0].permute(0, 2, 1).cpu().numpy(), X)
+    assert np.array_equal(one.ancestry[0].cpu().numpy(), A)
