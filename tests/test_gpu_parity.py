@@ -420,7 +420,7 @@ def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta,
     same kernels and host logic as the NCCL path) reproduce the unsharded filter and the oracle exactly."""
     import torch
     from sem_b200 import sharded
-    N, T = 3001, 9
+    N, T = 3001, (9 if model == 0 else 6)
     Y = _truth_Y(model, T, 5, .1, False, G=G)
     out = sharded.run_local(Y, model, np.array(theta, float), N, world, G=G, probs=.1, seed=4242, filter_id=5, mu=mu,
                             n_population=npop)
