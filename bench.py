@@ -127,6 +127,60 @@ def run_reference_arm(args):
     }))
 
 
+def run_abc(args):
+    """Extra measurement (not the driver's headline): ABC rejection trials of BASELINE config 2
+    (tests/test_abc_sir.py: y0=(4800,20,0), beta=2, gamma=1, T=15, priors U(0,5)^2, threshold 150)."""
+    import torch
+    import torch.distributed as dist
+    from sem_b200 import engine
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    obs = workloads.observe_normal(workloads.sir_truth((4800, 20, 0), 15, 2.0, 1.0), .1, seed=0)
+    n, K, W = args.trials, args.steps, max(args.warmup, 3)
+    for i in range(W):
+        engine.abc_trials(obs, n, 150.0, [0, 5, 0, 5], seed=5, trial0=(rank * 1000 + i) * n, arith=args.arith, early_reject=args.early_reject)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    events = acc = 0
+    ev0.record()
+    outs = []
+    for i in range(K):
+        outs.append(engine.abc_trials(obs, n, 150.0, [0, 5, 0, 5], seed=5, trial0=(rank * 1000 + W + i) * n, arith=args.arith,
+                                      early_reject=args.early_reject))
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    for o in outs:
+        events += int(o["n_events"].cpu()[0]); acc += int((o["distance"] <= 150.0).sum().cpu())
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.cpu()[0])
+    if rank == 0:
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle as co
+            t0 = time.perf_counter()
+            o = co.abc_trials(obs, 2000, 150.0, (0, 5, 0, 5), arith=0, seed=5, trial0=0, want_traj=False, n_threads=1)
+            dt = time.perf_counter() - t0
+            cb = dict(value=2000 / dt, unit="epidemics/s", cores=1, kind="port", sample="2000 trials, reference operation order",
+                      events_per_s=o["n_events"] / dt)
+        print(json.dumps({"metric": "simulated epidemics/s", "value": world * K * n / (ms / 1e3), "unit": "epidemics/s",
+                          "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms / K, "higher_is_better": True,
+                          "scaling": "weak", "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": "abc_sir_pop4820_T15_prior_U(0,5)^2_thr150", "trials_per_step_per_gpu": n,
+                                     "early_reject": bool(args.early_reject), "arith": args.arith},
+                          "events_per_s": world * events / (ms / 1e3), "events_per_trial": events / (K * n),
+                          "acceptance_rate": acc / (K * n), "gpu_launches": K, "cpu_baseline": cb}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,9 +193,15 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="pf", choices=["pf", "abc"],
+                    help="pf = the BASELINE metric workload (default); abc = ABC rejection trials (config 2), extra measurement")
+    ap.add_argument("--trials", type=int, default=1 << 20, help="ABC trials per step per GPU")
+    ap.add_argument("--early-reject", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.workload == "abc":
+        return run_abc(args)
 
     import torch
     import torch.distributed as dist
