@@ -169,7 +169,7 @@ typedef struct sem_sim_config {
     double max_time;
     uint64_t seed;
     uint32_t sim_index0;    /* Philox item id of sim 0 */
-    uint32_t reserved;
+    int32_t daily_rows;     /* H > 0: states receives [n_sims][H][C] = state at the integer times 1..H (max_time >= H) */
 } sem_sim_config;
 
 /* x0 device int32; theta device; replay_u/replay_off device or NULL (Philox); x_out device [n_sims][C] int32;

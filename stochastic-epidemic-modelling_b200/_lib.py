@@ -55,7 +55,7 @@ class SimConfig(C.Structure):
     _fields_ = [
         ("model", C.c_int32), ("n_groups", C.c_int32), ("arith", C.c_int32), ("n_sims", C.c_int32),
         ("shared_theta", C.c_int32), ("shared_x0", C.c_int32), ("record_capacity", C.c_int64),
-        ("max_time", C.c_double), ("seed", C.c_uint64), ("sim_index0", C.c_uint32), ("reserved", C.c_uint32),
+        ("max_time", C.c_double), ("seed", C.c_uint64), ("sim_index0", C.c_uint32), ("daily_rows", C.c_int32),
     ]
 
 

@@ -12,7 +12,7 @@ namespace sem {
 
 // ------------------------------------------------------------------------------------------ simulate
 struct SimDev {
-    int n_sims, shared_theta, shared_x0, ntheta;
+    int n_sims, shared_theta, shared_x0, ntheta, daily;
     long long cap;
     double max_time;
     PhiloxKey key;
@@ -37,6 +37,27 @@ struct EventLog {
         n++;
     }
 };
+// state at the integer times 1..H (what the reference's forward-prediction script extracts per day,
+// tests/pred_tmps.py:55-64): days strictly before an event's time keep the pre-event state
+template <int C>
+struct DailyLog {
+    int32_t *rows; int H, day; double prev[C];
+    __device__ __forceinline__ void flush_to(double t) {
+        while (day <= H && (double)day < t) {
+#pragma unroll
+            for (int c = 0; c < C; c++) rows[(size_t)(day - 1) * C + c] = (int32_t)prev[c];
+            day++;
+        }
+    }
+    __device__ __forceinline__ void operator()(double t, const double *x) {
+        flush_to(t);
+#pragma unroll
+        for (int c = 0; c < C; c++) prev[c] = x[c];
+    }
+};
+template <int C>
+struct DailyLogRef { DailyLog<C> *l; __device__ __forceinline__ void operator()(double t, const double *x) const { (*l)(t, x); } };
+
 template <int C>
 struct EventLogRef { EventLog<C> *l; __device__ __forceinline__ void operator()(double t, const double *x) const { (*l)(t, x); } };
 
@@ -57,7 +78,15 @@ __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
     if constexpr (REPLAY) src.init(P.replay_u, P.replay_off[i], P.replay_off[i + 1]);
     else src.init(P.key, P.sim0 + (uint32_t)i, 0u, stream_word(DOM_SIM, 0));
     long long rows = 1;
-    if (P.cap > 0) {
+    if (P.daily > 0) {
+        DailyLog<Model::C> log;
+        log.rows = P.states + (size_t)i * P.daily * Model::C; log.H = P.daily; log.day = 1;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) log.prev[c] = x[c];
+        const long long pr = ssa_run<Model, ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, DailyLogRef<Model::C>{&log});
+        log.flush_to(1e300);                                              // forward fill to the horizon
+        rows = pr < 0 ? -1 : P.daily;
+    } else if (P.cap > 0) {
         EventLog<Model::C> log{P.times + (size_t)i * P.cap, P.states + (size_t)i * P.cap * Model::C, P.cap, 0};
         log(0.0, x);                                                      // row 0 = initial state at time 0 (gillespie_algo.py:28-33)
         const long long pr = ssa_run<Model, ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
@@ -207,10 +236,11 @@ int sem_ssa_simulate(const sem_sim_config *cfg, const int32_t *x0, const double 
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
     if (G < 1 || G > SEM_MAX_GROUPS) { set_error("n_groups must be 1..4"); return SEM_ERR_INVALID; }
     if (cfg->record_capacity > 0 && (!times || !states)) { set_error("record buffers missing"); return SEM_ERR_INVALID; }
+    if (cfg->daily_rows > 0 && (!states || cfg->record_capacity > 0)) { set_error("daily_rows needs states and no event log"); return SEM_ERR_INVALID; }
     if ((replay_u == nullptr) != (replay_off == nullptr)) { set_error("replay_u and replay_off go together"); return SEM_ERR_INVALID; }
     SimDev P;
     P.n_sims = cfg->n_sims; P.shared_theta = cfg->shared_theta; P.shared_x0 = cfg->shared_x0;
-    P.ntheta = model_ntheta(cfg->model, G); P.cap = cfg->record_capacity; P.max_time = cfg->max_time;
+    P.ntheta = model_ntheta(cfg->model, G); P.cap = cfg->record_capacity; P.max_time = cfg->max_time; P.daily = cfg->daily_rows;
     P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32); P.sim0 = cfg->sim_index0;
     P.x0 = x0; P.theta = theta; P.replay_u = replay_u; P.replay_off = (const long long *)replay_off;
     P.x_out = x_out; P.states = states; P.n_rows = (long long *)n_rows; P.times = times;

@@ -158,7 +158,7 @@ def alloc_pf_outputs(cfg, device=None):
 
 
 def simulate(model, x0, theta, max_time, G=1, arith="fast", seed=0, sim_index0=0, record_capacity=0, replay=None,
-             n_sims=None, device=None):
+             n_sims=None, daily_rows=0, device=None):
     """Batch of independent SSA runs (sem_ssa_simulate).  x0 (n,C) or (C,), theta (n,P) or (P,).
     Returns dict(x (n,C) int32, n_rows (n,), times (n,cap), states (n,cap,C)) as device tensors."""
     L = _lib.load()
@@ -180,13 +180,16 @@ def simulate(model, x0, theta, max_time, G=1, arith="fast", seed=0, sim_index0=0
             n = int(n_sims)
         cfg = _lib.SimConfig(model=model, n_groups=G, arith=ARITH.get(arith, arith), n_sims=n,
                              shared_theta=int(shared_th), shared_x0=int(shared_x0), record_capacity=int(record_capacity),
-                             max_time=float(max_time), seed=int(seed) & (2**64 - 1), sim_index0=int(sim_index0))
+                             max_time=float(max_time), seed=int(seed) & (2**64 - 1), sim_index0=int(sim_index0),
+                             daily_rows=int(daily_rows))
         x_out = torch.empty((n, Cn), dtype=torch.int32, device=dev)
         n_rows = torch.empty((n,), dtype=torch.int64, device=dev)
         times = states = ru = ro = None
         if record_capacity > 0:
             times = torch.empty((n, record_capacity), dtype=torch.float64, device=dev)
             states = torch.empty((n, record_capacity, Cn), dtype=torch.int32, device=dev)
+        elif daily_rows > 0:
+            states = torch.empty((n, daily_rows, Cn), dtype=torch.int32, device=dev)
         if replay is not None:
             ru = _dev_f64(replay["u"], dev)
             ro = torch.from_numpy(np.ascontiguousarray(replay["off"], dtype=np.int64)).to(dev)

@@ -8,7 +8,7 @@ import numpy as np
 
 from . import engine
 
-__all__ = ["sir_simulate", "seir_simulate", "sir_subgroups_simulate", "simulate_batch"]
+__all__ = ["sir_simulate", "seir_simulate", "sir_subgroups_simulate", "simulate_batch", "predict_forward"]
 
 
 def _max_rows(model, x0):
@@ -79,3 +79,14 @@ def simulate_batch(model, populations, thetas, max_time, *, n_groups=1, seed=Non
     m = engine.MODEL_NAMES[model] if isinstance(model, str) else int(model)
     out = engine.simulate(m, populations, thetas, max_time, G=n_groups, arith=arith, seed=seed, n_sims=n_sims)
     return out["x"]
+
+
+def predict_forward(model, thetas, last_states, horizon, *, n_groups=1, seed=None, arith="fast"):
+    """Forward-prediction fan-out of tests/pred_tmps.py:55-73: from every posterior sample's last
+    state simulate `horizon` more days with its own theta; returns (n, horizon, C) int32 CUDA tensor whose row d is
+    the state at integer time d+1 (the state the reference extracts as "last event with floor(time) == d",
+    forward-filled on days without events)."""
+    seed = engine.new_seed() if seed is None else seed
+    m = engine.MODEL_NAMES[model] if isinstance(model, str) else int(model)
+    out = engine.simulate(m, last_states, thetas, float(horizon), G=n_groups, arith=arith, seed=seed, daily_rows=int(horizon))
+    return out["states"]

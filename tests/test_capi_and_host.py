@@ -273,3 +273,40 @@ def test_sharded_exchange_world2_gloo(tmp_path):
         x = np.stack([x[a, 0], x[a, 1] + 1, (x[a, 2] * 5 + p + j) % 17], 1)
     assert np.array_equal(hist[T - 1], x)
     np.testing.assert_allclose(r0["logz"], logz, rtol=1e-12)
+
+
+# ------------------------------------------------------------------ "next" rows N2 / N3 (host utilities)
+def test_helpers_match_reference_formulas(tmp_path):
+    from sem_b200 import helpers, results_io
+    rng = np.random.RandomState(0)
+    chains = [rng.normal(size=(400, 3)) + .1 * i for i in range(3)]
+    # helpers.py:15-43 restated literally
+    M, N = 3, 400
+    means = np.array([c.mean(0) for c in chains]); var = np.array([((c - c.mean(0)) ** 2).sum(0) / (N - 1) for c in chains])
+    W = var.mean(0); B = N / (M - 1) * ((means - means.mean(0)) ** 2).sum(0); V = (N - 1) / N * W + (M + 1) / (M * N) * B
+    np.testing.assert_allclose(helpers.gelman_rubin_test(chains), np.sqrt(V / W), rtol=1e-13)
+    x = rng.normal(size=2000)
+    cs = np.cumsum(np.insert(x, 0, 0))
+    assert np.array_equal(helpers.running_mean(x, 7), (cs[7:] - cs[:-7]) / 7.0)                       # helpers.py:46-48
+    assert helpers.posterior_mse(np.array([.1, .2, .3]), chains[0]) == np.mean((chains[0] - np.array([.1, .2, .3])) ** 2)
+    lo, hi = helpers.hdi(x, .95)
+    assert abs(lo + 1.96) < .15 and abs(hi - 1.96) < .15 and np.mean((x >= lo) & (x <= hi)) >= .95 - 1e-9
+    m, lo2, hi2 = helpers.mean_credible_interval(x)
+    assert m == x.mean() and (lo2, hi2) == (lo, hi)
+    ar = np.zeros(5000); e = rng.normal(size=5000)
+    for i in range(1, 5000):
+        ar[i] = .9 * ar[i - 1] + e[i]
+    assert 150 < helpers.effective_sample_size(ar) < 450 and helpers.effective_sample_size(e) > 3500        # (1-.9)/(1+.9)*5000 = 263
+    th = np.repeat(rng.normal(size=(50, 2)), 4, axis=0)
+    assert abs(helpers.acceptance_rate(th) - 49 / 199) < 1e-12
+    # results I/O + warm start (tests/experiments/noise/noise_.1.py:18-26,45-56)
+    thetas = np.repeat(rng.normal(size=(60, 2)) + 2, 5, axis=0); lik = rng.random_sample(300); trajs = rng.randint(0, 500, (15, 300, 3)).astype(float)
+    d = str(tmp_path / "run1")
+    results_io.save_results(d, thetas, lik, trajs)
+    assert sorted(os.listdir(d)) == ["likelihoods.csv", "sampled_trajs_infected.csv", "sampled_trajs_recovered.csv",
+                                     "sampled_trajs_susceptible.csv", "thetas.csv"]
+    t2, l2, tr2 = results_io.load_results(d)
+    assert np.array_equal(t2, thetas) and np.array_equal(l2, lik) and np.array_equal(tr2, trajs)
+    theta0, sigma = results_io.warm_start(d)
+    uniq = np.unique(thetas[100:][::20], axis=0)
+    assert theta0 == thetas[-1].tolist() and np.array_equal(sigma, np.cov(uniq.T, ddof=0))

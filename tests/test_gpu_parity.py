@@ -438,3 +438,19 @@ def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta,
     one = sem.engine.run_pf(cfg, Y, np.array(theta, float))
     assert np.array_equal(one.X_hist[0].permute(0, 2, 1).cpu().numpy(), X)
     assert np.array_equal(one.ancestry[0].cpu().numpy(), A)
+
+
+def test_predict_forward_daily_states(sem, c_oracle):
+    """Forward-prediction fan-out (tests/pred_tmps.py:55-73): daily states of many simulations == the oracle's event
+    logs sampled at the integer times."""
+    n, H = 200, 6
+    rng = np.random.RandomState(3)
+    thetas = np.stack([rng.uniform(1, 3, n), rng.uniform(.5, 1.5, n)], 1)
+    last = np.stack([rng.randint(200, 480, n), rng.randint(0, 30, n), rng.randint(0, 100, n)], 1)
+    out = sem.gillespie_algo.predict_forward("sir", thetas, last, H, seed=17).cpu().numpy()
+    assert out.shape == (n, H, 3)
+    for i in range(0, n, 7):
+        ref = c_oracle.ssa(0, 1, last[i], thetas[i], float(H), arith=1, seed=17, sim_index=i, max_rec=4000)
+        for d in range(1, H + 1):
+            k = np.searchsorted(ref["times"], d, side="right") - 1          # last event with time <= d
+            assert np.array_equal(out[i, d - 1], ref["states"][k].astype(np.int32)), (i, d)
