@@ -40,9 +40,13 @@ enum { SEM_MODEL_SIR = 0, SEM_MODEL_SEIR = 1, SEM_MODEL_SIR_SUBGROUPS = 2, SEM_M
 enum { SEM_OBS_BINOMIAL = 0, SEM_OBS_NORMAL = 1 };
 /* pmcmc.py:188-190 is multinomial; systematic is the production resampler (one uniform per step) */
 enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
-/* fp64 operation order of one SSA event: the reference's own (gillespie_algo.py:38-39,62-63) or an
- * algebraically equal form with a single division */
-enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1 };
+/* How one observation interval is simulated.  REFERENCE / FAST are the Gillespie direct method in the reference's
+ * own fp64 operation order (gillespie_algo.py:38-39,62-63) or an algebraically equal form with a single division.
+ * UNIFORMIZED is exact too (same law of the state at the end of the interval) but draws no waiting times: the jump
+ * chain is thinned from a rate-B Poisson stream of candidates whose NUMBER in the interval is drawn once; if a
+ * fired event lifts the total propensity above B, that candidate's time is drawn from its order-statistic (Beta)
+ * law and the rest of the interval restarts with a new bound. */
+enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2 };
 
 enum {
     SEM_OK = 0,

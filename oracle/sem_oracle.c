@@ -44,8 +44,8 @@
 #define SO_MAX_R (SO_MAX_G * SO_MAX_G + SO_MAX_G)
 
 enum { M_SIR = 0, M_SEIR = 1, M_SUB = 2, M_SUB2 = 3 };
-enum { ARITH_REF = 0, ARITH_FAST = 1 };
-enum { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7 };
+enum { ARITH_REF = 0, ARITH_FAST = 1, ARITH_UNIF = 2 };
+enum { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7, DOM_AUX = 8 };
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
 void so_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
@@ -177,8 +177,12 @@ static inline void model_apply(const so_model *m, double *x, int j) {
 
 /* Run the direct method until max_time or extinction.  Returns number of uniform PAIRS drawn (events incl. the
  * discarded overshoot, gillespie_algo.py:62-66).  If times/states given, records accepted events. */
+static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_stream *s);
+
 static int64_t ssa_run(const so_model *m, double *x, double max_time, int arith, so_stream *s,
                        double *times, double *states, int64_t max_rec, int64_t *n_rec) {
+    if (arith == ARITH_UNIF && s->philox && !times) return ssa_run_unif(m, x, max_time, s);
+    if (arith == ARITH_UNIF) arith = ARITH_FAST;
     double r[SO_MAX_R], cdf[SO_MAX_R];
     const int R = m->R, C = m->C;
     double N = model_popsize(m, x), invN = 1.0 / N;
@@ -338,6 +342,68 @@ static double poisson_draw(so_stream *s, double mu) {
 double so_poisson_philox(double mu, uint64_t seed, uint32_t c1, uint32_t c2, uint32_t domain, uint32_t fid) {
     so_stream s; philox_stream(&s, seed, c1, c2, domain, fid);
     return poisson_draw(&s, mu);
+}
+
+/* ------------------------------------------------------------------ uniformized interval (ARITH_UNIF)
+ * Exact law of the state at the end of the interval without waiting times (uniformization + restart rule); the
+ * specification is the comment above ssa_run_unif in csrc/sem_common.cuh -- this is its independent C statement.
+ * Candidates: the particle's SSA Philox stream, two 52-bit uniforms per call.  K ~ Poisson(B t_rem) and the
+ * Marsaglia-Tsang gammas of the Beta(m, K-m+1) restart time: the DOM_AUX stream of the same particle/step. */
+static double gamma_draw(so_stream *aux, double shape) {
+    double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        double u1, u2, u3, u4;
+        stream_pair(aux, &u1, &u2);
+        stream_pair(aux, &u3, &u4);
+        double n = sqrt(-2.0 * log(1.0 - u1)) * cos(3.141592653589793 * (2.0 * u2));
+        double v = 1.0 + c * n;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(1.0 - u3) < 0.5 * n * n + d - d * v + d * log(v)) return d * v;
+    }
+}
+
+static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_stream *s) {
+    const double c0 = 1.25, c1 = 3.0, direct_below = 24.0;
+    so_stream aux = *s;
+    aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
+    const int R = m->R;
+    double r[SO_MAX_R], N = model_popsize(m, x), invN = 1.0 / N, t_rem = max_time;
+    int64_t fired = 0;
+    while (model_alive(m, x)) {
+        double a0 = 0;
+        model_rates_fast(m, x, invN, r);
+        for (int i = 0; i < R; i++) a0 = a0 + r[i];
+        if (!(a0 > 0)) break;
+        double expect = a0 * t_rem;
+        if (expect < direct_below) return fired + ssa_run(m, x, t_rem, ARITH_FAST, s, NULL, NULL, 0, NULL);
+        double B = a0 * (c0 + c1 / sqrt(expect + 1.0));
+        double K = poisson_draw(&aux, B * t_rem), done = 0.0;
+        int violated = 0, half = 0;
+        uint32_t w[4] = {0, 0, 0, 0};
+        while (done < K) {
+            if (!half) { uint32_t ctr[4] = {s->k++, s->c1, s->c2, s->c3}; so_philox4x32(ctr, s->key, w); }
+            double u = half ? u52(w[2], w[3]) : u52(w[0], w[1]);
+            half = !half;
+            double v = fma(u + 1.0, B, -B);                    /* u*B with one rounding, as the kernel's fma(d,B,-B) */
+            done += 1.0;
+            if (v < a0) {
+                double acc = r[0]; int j = (acc <= v);
+                for (int i = 1; i < R - 1; i++) { acc = acc + r[i]; j += (acc <= v); }
+                model_apply(m, x, j);
+                fired++;
+                if (!model_alive(m, x)) break;
+                model_rates_fast(m, x, invN, r);
+                a0 = 0; for (int i = 0; i < R; i++) a0 = a0 + r[i];
+                if (a0 > B) { violated = 1; break; }
+            }
+        }
+        if (!violated) break;
+        double g1 = gamma_draw(&aux, done), g2 = gamma_draw(&aux, K - done + 1.0);
+        t_rem = t_rem - t_rem * (g1 / (g1 + g2));
+        if (!(t_rem > 0)) break;
+    }
+    return fired;
 }
 
 /* ------------------------------------------------------------------ particle filter */

@@ -16,7 +16,7 @@
 
 namespace sem {
 
-enum : uint32_t { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7 };
+enum : uint32_t { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7, DOM_AUX = 8 };
 
 // ------------------------------------------------------------------------------------------ Philox4x32-10
 struct PhiloxKey { uint32_t k0, k1; };
@@ -309,6 +309,8 @@ struct SubModel {
     }
 };
 
+struct NoRec { __device__ __forceinline__ void operator()(double, const double *) const {} };
+
 // One Gillespie draw (split so that no uniform is consumed when the total propensity is not positive):
 //   ssa_total     : propensities r[] in the reference's reaction order and a0 = builtin sum() = 0 + r0 + r1 ...
 //   ssa_pick_ref  : numpy's legacy exponential / choice arithmetic (gillespie_algo.py:62-63):
@@ -408,14 +410,94 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
     return pairs;
 }
 
+// ------------------------------------------------------------------------------------------ uniformized interval
+// Exact simulation of the state at the end of an interval WITHOUT waiting times (Jensen's uniformization with a
+// restart rule).  While the total propensity a0(x) stays <= B, the jump process is a rate-B Poisson stream of
+// candidates thinned with probability r_j(x)/B (null event otherwise); only the NUMBER K ~ Poisson(B * t_rem) of
+// candidates in the remaining time matters, not their times.  If a fired event lifts a0 above B, the bound was valid
+// up to that candidate (the m-th of K): its time is the m-th order statistic of K uniforms, t_rem * Beta(m, K-m+1),
+// drawn exactly (ratio of Marsaglia-Tsang gammas); the later candidates are discarded (strong Markov property) and
+// the rest of the interval restarts from the current state with a fresh bound.  Per candidate: half a Philox call
+// (one 52-bit uniform), no logarithm, no reciprocal.
+// Streams: candidates consume the particle's SSA stream (two per call); K and the gammas use the DOM_AUX stream.
+template <class Src>
+__device__ __noinline__ double gamma_draw(Src &aux, double shape) {        // shape >= 1 (Marsaglia & Tsang 2000)
+    const double d = shape - 1.0 / 3.0, c = 1.0 / sqrt(9.0 * d);
+    for (;;) {
+        double u1, u2, u3, u4;
+        aux.next(u1, u2);
+        aux.next(u3, u4);
+        const double n = sqrt(-2.0 * log(1.0 - u1)) * cos(3.141592653589793 * (2.0 * u2));   // Box-Muller normal
+        double v = 1.0 + c * n;
+        if (v <= 0.0) continue;
+        v = v * v * v;
+        if (log(1.0 - u3) < 0.5 * n * n + d - d * v + d * log(v)) return d * v;
+    }
+}
+
+struct UnifTuning { double c0, c1, direct_below; };
+// B = a0 * (c0 + c1 / sqrt(a0 * t_rem + 1)); intervals expecting fewer than direct_below events use the direct method
+__device__ __forceinline__ UnifTuning unif_tuning() { return UnifTuning{1.25, 3.0, 24.0}; }
+
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, double max_time, PairSource<false> &src,
+                                                  PairSource<false> &aux, const double2 *tab) {
+    const UnifTuning tune = unif_tuning();
+    double t_rem = max_time;
+    long long fired = 0;
+    while (m.alive(x)) {
+        double r[Model::R];
+        double a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+        if (!(a0 > 0)) break;
+        const double expect = a0 * t_rem;
+        if (expect < tune.direct_below) {                                  // short: finish with the direct method
+            fired += ssa_run_fast<Model, TRACK_R>(m, x, t_rem, src, tab, NoRec());
+            return fired;
+        }
+        const double B = a0 * (tune.c0 + tune.c1 / sqrt(expect + 1.0));
+        const double K = poisson_draw(aux, B * t_rem);
+        double done = 0.0;                                                 // candidates processed in this batch (exact in fp64)
+        bool violated = false, half = false;
+        uint4 w = make_uint4(0, 0, 0, 0);
+        while (done < K) {
+            if (!half) w = src.raw();                                      // two candidates per Philox call
+            const double d = half ? bits_to_d12(w.z, w.w) : bits_to_d12(w.x, w.y);
+            half = !half;
+            const double v = __fma_rn(d, B, -B);                           // u * B
+            done += 1.0;
+            if (v < a0) {                                                  // a real event (else: null candidate)
+                double acc = r[0];
+                int j = (acc <= v) ? 1 : 0;
+#pragma unroll
+                for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
+                m.template apply<TRACK_R>(x, j);
+                fired++;
+                if (!m.alive(x)) break;                                    // absorbed: every later candidate is null
+                a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+                if (a0 > B) { violated = true; break; }
+            }
+        }
+        if (!violated) break;                                              // the batch covered the rest of the interval
+        // the bound held up to candidate `done`; its time is the done-th order statistic of K uniforms on [0, t_rem]
+        const double g1 = gamma_draw(aux, done), g2 = gamma_draw(aux, K - done + 1.0);
+        t_rem = t_rem - t_rem * (g1 / (g1 + g2));
+        if (!(t_rem > 0)) break;
+    }
+    if (!TRACK_R) m.fix_removed(x);
+    return fired;
+}
+
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,
                                              const double2 *tab, Rec rec) {
     if constexpr (ARITH == SEM_ARITH_FAST && !REPLAY) return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, rec);
+    else if constexpr (ARITH == SEM_ARITH_UNIFORMIZED && !REPLAY) {
+        PairSource<false> aux; aux.init(src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
+        return ssa_run_unif<Model, TRACK_R>(m, x, max_time, src, aux, tab);
+    }
     else return ssa_run_ref<Model, REPLAY>(m, x, max_time, src, rec);
 }
 
-struct NoRec { __device__ __forceinline__ void operator()(double, const double *) const {} };
 
 // ------------------------------------------------------------------------------------------ block primitives
 __device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }

@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int 
     const int par = p & 1;
     const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
     const double *pfx_g = P.pfx[par ^ 1] + (size_t)f * P.nb;
-    if (ARITH == SEM_ARITH_FAST && !REPLAY) load_logtab(s_tab);
+    if (ARITH != SEM_ARITH_REFERENCE && !REPLAY) load_logtab(s_tab);
     if (P.pfx_in_smem && !P.sharded) for (int i = tid; i < P.nb; i += blockDim.x) s_pfx[i] = pfx_g[i];
     if (tid == 0) s_pairs = 0ull;
     __syncthreads();
@@ -416,6 +416,7 @@ static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 gri
     if (p == 0) pf_init<Model><<<grid, threads, 0, s>>>(P);
     else if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, smem, s>>>(P, p);
+    else if (arith == SEM_ARITH_UNIFORMIZED) pf_step<Model, SEM_ARITH_UNIFORMIZED, false><<<grid, threads, smem, s>>>(P, p);
     else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, smem, s>>>(P, p);
 }
 

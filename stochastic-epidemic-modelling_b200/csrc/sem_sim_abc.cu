@@ -64,7 +64,7 @@ struct EventLogRef { EventLog<C> *l; __device__ __forceinline__ void operator()(
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
     __shared__ double2 s_tab[128];
-    if (ARITH == SEM_ARITH_FAST && !REPLAY) load_logtab(s_tab);
+    if (ARITH != SEM_ARITH_REFERENCE && !REPLAY) load_logtab(s_tab);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= P.n_sims) return;
@@ -83,13 +83,13 @@ __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
         log.rows = P.states + (size_t)i * P.daily * Model::C; log.H = P.daily; log.day = 1;
 #pragma unroll
         for (int c = 0; c < Model::C; c++) log.prev[c] = x[c];
-        const long long pr = ssa_run<Model, ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, DailyLogRef<Model::C>{&log});
+        const long long pr = ssa_run<Model, ARITH == SEM_ARITH_UNIFORMIZED ? SEM_ARITH_FAST : ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, DailyLogRef<Model::C>{&log});
         log.flush_to(1e300);                                              // forward fill to the horizon
         rows = pr < 0 ? -1 : P.daily;
     } else if (P.cap > 0) {
         EventLog<Model::C> log{P.times + (size_t)i * P.cap, P.states + (size_t)i * P.cap * Model::C, P.cap, 0};
         log(0.0, x);                                                      // row 0 = initial state at time 0 (gillespie_algo.py:28-33)
-        const long long pr = ssa_run<Model, ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
+        const long long pr = ssa_run<Model, ARITH == SEM_ARITH_UNIFORMIZED ? SEM_ARITH_FAST : ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
         rows = pr < 0 ? -1 : log.n;
     } else {
         const long long pr = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.max_time, src, s_tab, NoRec());
@@ -105,6 +105,8 @@ static void launch_sim(const SimDev &P, int arith, bool replay, cudaStream_t s) 
     const int threads = 128, blocks = (P.n_sims + threads - 1) / threads;
     if (replay) sim_kernel<Model, SEM_ARITH_REFERENCE, true><<<blocks, threads, 0, s>>>(P);
     else if (arith == SEM_ARITH_REFERENCE) sim_kernel<Model, SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
+    else if (arith == SEM_ARITH_UNIFORMIZED && P.cap == 0 && P.daily == 0)      // no event times exist to log
+        sim_kernel<Model, SEM_ARITH_UNIFORMIZED, false><<<blocks, threads, 0, s>>>(P);
     else sim_kernel<Model, SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);
 }
 
@@ -287,7 +289,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     const int blocks = (int)(want < cap ? want : cap);
     if (replay) abc_kernel<SEM_ARITH_REFERENCE, true><<<blocks, threads, 0, s>>>(P);
     else if (cfg->arith == SEM_ARITH_REFERENCE) abc_kernel<SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
-    else abc_kernel<SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);
+    else abc_kernel<SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);     // (UNIFORMIZED: the ABC loop needs event times)
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }

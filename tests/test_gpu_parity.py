@@ -217,6 +217,12 @@ PHILOX_CASES = [
     (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 0, 1, 32),
     (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1000, 7, True, .1, 1, 0, 0),
     (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 1, 0),
+    # uniformized intervals (arith 2): exact law without waiting times, bit-checked against the oracle's statement
+    (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 2, 0),
+    (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 0, 2, 96),
+    (0, 1, [0.5, 3.0], [300], [3], 777, 8, False, .5, 0, 2, 0),
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, False, .1, 1, 2, 0),
+    (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 1, 2, 0),
 ]
 
 
@@ -454,3 +460,25 @@ def test_predict_forward_daily_states(sem, c_oracle):
         for d in range(1, H + 1):
             k = np.searchsorted(ref["times"], d, side="right") - 1          # last event with time <= d
             assert np.array_equal(out[i, d - 1], ref["states"][k].astype(np.int32)), (i, d)
+
+
+def test_uniformized_headline_workload_vs_oracle(sem, c_oracle):
+    """arith='uniformized' on the BASELINE workload shape (pop 1e4, 101 rows) at 8000 particles: exact match with the
+    oracle, and the likelihood estimate agrees with the direct method's within Monte-Carlo error."""
+    import torch
+    N, T, pop = 8000, 101, 10_000
+    Y = bench_truth(T, pop)
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=2, seed=31, mu=[20], n_population=[pop])
+    r = sem.engine.run_pf(cfg, Y, np.array([.4, .2]))
+    o = c_oracle.pf_run(0, Y, [.4, .2], False, .1, N, resampler=1, arith=2, seed=31, mu=[20], npop=[pop])
+    torch.cuda.synchronize()
+    assert np.array_equal(r.ancestry[0].cpu().numpy(), o["ancestry"])
+    assert np.array_equal(r.X_hist[0].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+    np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
+    lz = {a: [] for a in (1, 2)}
+    for a in (1, 2):
+        for sd in range(6):
+            c = sem.engine.make_pf_config(0, 20000, T, probs=.1, resampler=1, arith=a, seed=100 + sd, mu=[20], n_population=[pop])
+            lz[a].append(float(sem.engine.run_pf(c, Y, np.array([.4, .2])).log_zetas[0, -1].cpu()))
+    se = np.sqrt(np.var(lz[1]) / 6 + np.var(lz[2]) / 6) + 0.02
+    assert abs(np.mean(lz[1]) - np.mean(lz[2])) < 5 * se, (lz, se)
