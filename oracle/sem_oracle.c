@@ -363,8 +363,11 @@ static double gamma_draw(so_stream *aux, double shape) {
     }
 }
 
+/* diagnostics (single-threaded use): batches, violations, candidates, fired, direct fallbacks */
+int64_t so_unif_counters[5];
+
 static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_stream *s) {
-    const double c0 = 1.25, c1 = 3.0, direct_below = 24.0;
+    const double c0 = 1.25, c1 = 3.0, direct_below = 2.0;
     so_stream aux = *s;
     aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
     const int R = m->R;
@@ -376,7 +379,8 @@ static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_st
         for (int i = 0; i < R; i++) a0 = a0 + r[i];
         if (!(a0 > 0)) break;
         double expect = a0 * t_rem;
-        if (expect < direct_below) return fired + ssa_run(m, x, t_rem, ARITH_FAST, s, NULL, NULL, 0, NULL);
+        if (expect < direct_below) { so_unif_counters[4]++; return fired + ssa_run(m, x, t_rem, ARITH_FAST, s, NULL, NULL, 0, NULL); }
+        so_unif_counters[0]++;
         double B = a0 * (c0 + c1 / sqrt(expect + 1.0));
         double K = poisson_draw(&aux, B * t_rem), done = 0.0;
         int violated = 0, half = 0;
@@ -387,7 +391,9 @@ static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_st
             half = !half;
             double v = fma(u + 1.0, B, -B);                    /* u*B with one rounding, as the kernel's fma(d,B,-B) */
             done += 1.0;
+            so_unif_counters[2]++;
             if (v < a0) {
+                so_unif_counters[3]++;
                 double acc = r[0]; int j = (acc <= v);
                 for (int i = 1; i < R - 1; i++) { acc = acc + r[i]; j += (acc <= v); }
                 model_apply(m, x, j);
@@ -399,6 +405,7 @@ static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_st
             }
         }
         if (!violated) break;
+        so_unif_counters[1]++;
         double g1 = gamma_draw(&aux, done), g2 = gamma_draw(&aux, K - done + 1.0);
         t_rem = t_rem - t_rem * (g1 / (g1 + g2));
         if (!(t_rem > 0)) break;

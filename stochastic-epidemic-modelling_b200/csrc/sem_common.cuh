@@ -384,7 +384,8 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
                                                   const double2 *tab, Rec rec) {
     double t = 0.0;
     int pairs = 0;                                                         // < 2^31 events per particle-step
-    uint4 w = src.raw();
+    PairSource<false> loc = src;                                           // register copy of the stream state
+    uint4 w = loc.raw();
     bool go = m.alive(x);
     // Single basic block per event (the overshoot test is a predicate, not a loop exit) so that the scheduler can
     // interleave the integer Philox chain of event k+1 with the fp64 chain of event k.
@@ -392,7 +393,7 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
         double r[Model::R], tau;
         int j;
         const double a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
-        const uint4 wn = src.raw();
+        const uint4 wn = loc.raw();
         ssa_pick_fast<Model>(r, a0, bits_to_d12(w.x, w.y), bits_to_d12(w.z, w.w), tab, tau, j);
         const double tn = __dadd_rn(t, tau);
         const bool drew = a0 > 0;                                          // no draw when nothing can happen
@@ -406,6 +407,7 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
         w = wn;
         go = fire && m.alive(x);
     }
+    src.k = loc.k;
     if (!TRACK_R) m.fix_removed(x);
     return pairs;
 }
@@ -435,56 +437,75 @@ __device__ __noinline__ double gamma_draw(Src &aux, double shape) {        // sh
     }
 }
 
+// out-of-line copy of the direct loop for the tail of a uniformized interval (keeps its registers out of the batch loop)
+template <class Model, bool TRACK_R>
+__device__ __noinline__ long long ssa_run_fast_call(const Model &m, double *x, double max_time, PairSource<false> &src,
+                                                    const double2 *tab) {
+    return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, NoRec());
+}
+
 struct UnifTuning { double c0, c1, direct_below; };
 // B = a0 * (c0 + c1 / sqrt(a0 * t_rem + 1)); intervals expecting fewer than direct_below events use the direct method
-__device__ __forceinline__ UnifTuning unif_tuning() { return UnifTuning{1.25, 3.0, 24.0}; }
+__device__ __forceinline__ UnifTuning unif_tuning() { return UnifTuning{1.25, 3.0, 2.0}; }
+
+// one candidate of the thinned stream, branch-free: returns true when the batch must stop (absorbed or bound violated)
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ bool unif_candidate(const Model &m, double *x, double *r, double &a0, const double B, const double d,
+                                               int &fired, bool &violated) {
+    const double v = __fma_rn(d, B, -B);                                   // u * B
+    const bool hit = v < a0;                                               // a real event (else a null candidate)
+    double acc = r[0];
+    int j = (acc <= v) ? 1 : 0;
+#pragma unroll
+    for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
+    if (hit) m.template apply<TRACK_R>(x, j);
+    fired += hit ? 1 : 0;
+    a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+    const bool alive = m.alive(x);
+    violated = hit && alive && (a0 > B);
+    return hit && (!alive || a0 > B);
+}
 
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, double max_time, PairSource<false> &src,
                                                   PairSource<false> &aux, const double2 *tab) {
     const UnifTuning tune = unif_tuning();
     double t_rem = max_time;
-    long long fired = 0;
+    long long total_fired = 0;
     while (m.alive(x)) {
         double r[Model::R];
         double a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
         if (!(a0 > 0)) break;
         const double expect = a0 * t_rem;
-        if (expect < tune.direct_below) {                                  // short: finish with the direct method
-            fired += ssa_run_fast<Model, TRACK_R>(m, x, t_rem, src, tab, NoRec());
-            return fired;
+        if (expect < tune.direct_below) {                                  // nearly nothing left: direct method
+            total_fired += ssa_run_fast_call<Model, TRACK_R>(m, x, t_rem, src, tab);
+            return total_fired;
         }
         const double B = a0 * (tune.c0 + tune.c1 / sqrt(expect + 1.0));
-        const double K = poisson_draw(aux, B * t_rem);
-        double done = 0.0;                                                 // candidates processed in this batch (exact in fp64)
-        bool violated = false, half = false;
-        uint4 w = make_uint4(0, 0, 0, 0);
-        while (done < K) {
-            if (!half) w = src.raw();                                      // two candidates per Philox call
-            const double d = half ? bits_to_d12(w.z, w.w) : bits_to_d12(w.x, w.y);
-            half = !half;
-            const double v = __fma_rn(d, B, -B);                           // u * B
-            done += 1.0;
-            if (v < a0) {                                                  // a real event (else: null candidate)
-                double acc = r[0];
-                int j = (acc <= v) ? 1 : 0;
-#pragma unroll
-                for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
-                m.template apply<TRACK_R>(x, j);
-                fired++;
-                if (!m.alive(x)) break;                                    // absorbed: every later candidate is null
-                a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
-                if (a0 > B) { violated = true; break; }
+        const double Kd = poisson_draw(aux, B * t_rem);
+        const int K = Kd < 2.0e9 ? (int)Kd : 2000000000;
+        int done = 0, fired = 0;                                           // candidates processed / events fired in this batch
+        bool violated = false, stop = false;
+        PairSource<false> loc = src;                                       // register copy (src's address escapes to out-of-line calls)
+        while (done < K && !stop) {                                        // two candidates per Philox call
+            const uint4 w = loc.raw();
+            stop = unif_candidate<Model, TRACK_R>(m, x, r, a0, B, bits_to_d12(w.x, w.y), fired, violated);
+            done++;
+            if (!stop && done < K) {
+                stop = unif_candidate<Model, TRACK_R>(m, x, r, a0, B, bits_to_d12(w.z, w.w), fired, violated);
+                done++;
             }
         }
+        src.k = loc.k;
+        total_fired += fired;
         if (!violated) break;                                              // the batch covered the rest of the interval
         // the bound held up to candidate `done`; its time is the done-th order statistic of K uniforms on [0, t_rem]
-        const double g1 = gamma_draw(aux, done), g2 = gamma_draw(aux, K - done + 1.0);
+        const double g1 = gamma_draw(aux, (double)done), g2 = gamma_draw(aux, (double)(K - done) + 1.0);
         t_rem = t_rem - t_rem * (g1 / (g1 + g2));
         if (!(t_rem > 0)) break;
     }
     if (!TRACK_R) m.fix_removed(x);
-    return fired;
+    return total_fired;
 }
 
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>

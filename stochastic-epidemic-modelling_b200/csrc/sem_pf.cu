@@ -49,6 +49,7 @@ struct PfDev {
 };
 
 constexpr int kMaxThreads = 768;
+constexpr int kMaxThreadsUnif = 352;      // the uniformized step keeps more live state: two 352-thread CTAs per SM, <= 93 registers
 
 __device__ __forceinline__ double block_max(double v, double *sm, int tid, int nwarps) {
     v = warp_max_d(v);
@@ -194,7 +195,8 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
 
 // Step p >= 1: resample, gather, propagate, store, weigh (see the file header).
 template <class Model, int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(kMaxThreads) pf_step(const PfDev P, const int p) {
+__global__ void __launch_bounds__(ARITH == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads)
+__maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, const int p) {
     extern __shared__ double s_pfx[];                        // previous step's CTA prefixes (when they fit)
     __shared__ double sm[32];
     __shared__ double2 s_tab[128];
@@ -369,12 +371,18 @@ __global__ void path_sample_kernel(const int32_t *X, const int32_t *A, int T, in
 // ---------------------------------------------------------------------------------------------- host side
 // particles per CTA: one CTA per SM when the whole population is co-resident, else 256-wide CTAs
 static int choose_ppb(const sem_pf_config *c) {
-    if (c->block_particles > 0) return c->block_particles > kMaxThreads ? kMaxThreads : c->block_particles;
+    if (c->block_particles > 0) {
+        const int lim = c->arith == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads;
+        return c->block_particles > lim ? lim : c->block_particles;
+    }
     const long long all = (long long)c->n_particles * c->n_filters;
     const long long per_sm = (all + sm_count() - 1) / sm_count();
-    // co-resident population: exactly ceil(N*F/SMs) particles per CTA (threads = that rounded up to a warp), so the
-    // grid is one CTA per SM; larger populations use 256-wide CTAs scheduled in waves
-    long long ppb = per_sm <= kMaxThreads ? per_sm : 256;
+    // co-resident population: ceil(N*F/SMs) particles per SM split over as few CTAs as the thread cap allows (threads =
+    // particles rounded up to a warp), so the grid is a whole number of CTAs per SM; larger populations use 256-wide
+    // CTAs scheduled in waves
+    const int cap = c->arith == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads;
+    const long long per_cta = (per_sm + (per_sm + cap - 1) / cap - 1) / ((per_sm + cap - 1) / cap > 0 ? (per_sm + cap - 1) / cap : 1);
+    long long ppb = per_sm <= 1536 ? per_cta : 256;
     if (ppb < 32) ppb = 32;
     if (ppb > c->n_particles) ppb = c->n_particles;
     return (int)ppb;
