@@ -11,7 +11,7 @@ unmodified reference script (`from pmcmc import *`) picks them up.
 import sys
 
 from . import _lib, engine  # noqa: F401
-from . import gillespie_algo, pmcmc, abc_algo  # noqa: F401
+from . import gillespie_algo, pmcmc, abc_algo, helpers, results_io, sharded  # noqa: F401
 from .pmcmc import ModelType, particle_filter, particle_path_sampler, particle_mcmc  # noqa: F401
 from .gillespie_algo import sir_simulate, seir_simulate, sir_subgroups_simulate  # noqa: F401
 from .abc_algo import distance_function  # noqa: F401

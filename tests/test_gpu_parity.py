@@ -482,3 +482,52 @@ def test_uniformized_headline_workload_vs_oracle(sem, c_oracle):
             lz[a].append(float(sem.engine.run_pf(c, Y, np.array([.4, .2])).log_zetas[0, -1].cpu()))
     se = np.sqrt(np.var(lz[1]) / 6 + np.var(lz[2]) / 6) + 0.02
     assert abs(np.mean(lz[1]) - np.mean(lz[2])) < 5 * se, (lz, se)
+
+
+# ------------------------------------------------------------------ statistical parity with the reference (north_star check 3)
+def test_logz_distribution_vs_reference(sem):
+    """Likelihood-estimate distribution of the CUDA filter vs 300 runs of the unmodified reference particle_filter
+    at the same N (tests/golden/make_golden_stats.py): equal means (both unbiased for the same likelihood); with the
+    reference's multinomial resampling also the same law of log Z (KS)."""
+    import torch
+    from scipy import stats
+    g = golden("stat_logz_sir")
+    N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
+    ref = g["zetas_last"]
+    runs = 1200
+    for resampler, arith in [(0, 1), (0, 0), (1, 1), (0, 2)]:
+        cfg = sem.engine.make_pf_config(0, N, len(g["Y"]), n_filters=runs, probs=float(g["probs"]), resampler=resampler,
+                                        arith=arith, seed=2024 + 7 * resampler + arith, mu=[mu], n_population=[npop])
+        res = sem.engine.run_pf(cfg, g["Y"], np.tile(g["theta"], (runs, 1)))
+        torch.cuda.synchronize()
+        assert int((res.status != 0).sum()) == 0
+        z = np.exp(res.log_zetas[:, -1].cpu().numpy())
+        se = np.sqrt(ref.var() / ref.size + z.var() / z.size)
+        assert abs(z.mean() - ref.mean()) < 4 * se, (resampler, arith, z.mean(), ref.mean(), se)
+        if resampler == 0:
+            assert stats.ks_2samp(np.log(z), np.log(ref)).pvalue > 1e-3, (arith,)
+        else:
+            assert np.log(z).std() <= np.log(ref).std() * 1.1                       # systematic resampling: no more variance
+
+
+def test_pmcmc_posterior_vs_reference(sem):
+    """Posterior of (beta, gamma) from the drop-in particle_mcmc vs a chain of the unmodified reference particle_mcmc on
+    the same data and settings: means agree within Monte-Carlo error (standard errors from the chains' ESS)."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "stat_pmcmc_sir.npz")):
+        pytest.skip("reference PMCMC chain golden not generated")
+    g = golden("stat_pmcmc_sir")
+    ref = g["thetas"][300:]
+    np.random.seed(11)
+    thetas, lik, _ = sem.particle_mcmc(g["Y"], sem.ModelType.SIR, list(g["parameters"]), float(g["h"]), n_chains=6000,
+                                       probs=float(g["probs"]), n_particles=int(g["n_particles"]),
+                                       n_population=int(g["n_population"]), mu=float(g["mu"]), seed=5, resampler="multinomial")
+    ours = thetas[500:]
+    ess = sem.helpers.effective_sample_size
+    for k in range(2):
+        se = np.sqrt(ref[:, k].var() / max(ess(ref[:, k]), 4) + ours[:, k].var() / max(ess(ours[:, k]), 4))
+        assert abs(ours[:, k].mean() - ref[:, k].mean()) < 4.5 * se, (k, ours[:, k].mean(), ref[:, k].mean(), se)
+        assert 0.5 < ours[:, k].std() / ref[:, k].std() < 2.0
+    acc_ref, acc_ours = sem.helpers.acceptance_rate(g["thetas"]), sem.helpers.acceptance_rate(thetas)
+    assert abs(acc_ref - acc_ours) < 0.12, (acc_ref, acc_ours)

@@ -168,3 +168,19 @@ def test_philox_known_answers(c_oracle):
     assert c_oracle.philox4x32([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert c_oracle.philox4x32([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+
+
+# ---------------------------------------------------------------- statistical pin of the Philox mode (Pattern A)
+def test_oracle_philox_logz_distribution_vs_reference(c_oracle):
+    """The oracle's free-running (Philox) filter samples the same likelihood-estimate distribution as 300 runs of the
+    unmodified reference particle_filter (tests/golden/make_golden_stats.py)."""
+    from scipy import stats
+    g = golden("stat_logz_sir")
+    N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
+    ref = g["zetas_last"]
+    for arith in (0, 1, 2):
+        z = np.array([np.exp(c_oracle.pf_run(0, g["Y"], g["theta"], False, float(g["probs"]), N, resampler=0, arith=arith,
+                                             seed=1000 + s, mu=[mu], npop=[npop])["log_zetas"][-1]) for s in range(300)])
+        se = np.sqrt(ref.var() / ref.size + z.var() / z.size)
+        assert abs(z.mean() - ref.mean()) < 4 * se, (arith, z.mean(), ref.mean(), se)      # unbiased for the same Z
+        assert stats.ks_2samp(np.log(z), np.log(ref)).pvalue > 1e-3, arith             # same N, multinomial => same law
