@@ -304,10 +304,11 @@ static double log_weight(int model, int G, int obs_kind, double probs, const dou
         double xc;
         if (model == M_SUB2) { xc = 0; for (int g = 0; g < G; g++) xc = xc + x[3 * g + c]; }   /* pmcmc.py:172-173 */
         else xc = x[c];
+        if (Yrow[c] != Yrow[c]) continue;   /* extension: NaN in Y = unobserved column (e.g. the hidden E of SEIR) */
         double l = obs_kind == 0 ? so_binom_logpmf(Yrow[c], xc, probs) : so_norm_logpdf(Yrow[c], xc, probs);
         if (l < lw || l != l) lw = l;
     }
-    return lw;
+    return lw == INFINITY ? 0.0 : lw;       /* nothing observed: weight 1 */
 }
 
 /* ------------------------------------------------------------------ Poisson sampler (philox init domain) */

@@ -87,11 +87,12 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
                 for (int g = 0; g < Model::G; g++) xc += x[3 * g + (c % 3)];
             }
             const double y = Yrow[c];
+            if (y != y) continue;                            // extension: a NaN entry of Y marks an unobserved column
             const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf(y, xc, P.probs) : norm_logpdf(y, xc, P.probs);
             lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
         }
     }
-    return lw;
+    return lw == CUDART_INF ? 0.0 : lw;                      // nothing observed at this time: weight 1
 }
 
 // Weigh the CTA's particles against Y[p], CTA-local scan, and (last CTA to arrive) the step's global combine.

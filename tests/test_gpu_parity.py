@@ -531,3 +531,56 @@ def test_pmcmc_posterior_vs_reference(sem):
         assert 0.5 < ours[:, k].std() / ref[:, k].std() < 2.0
     acc_ref, acc_ours = sem.helpers.acceptance_rate(g["thetas"]), sem.helpers.acceptance_rate(thetas)
     assert abs(acc_ref - acc_ours) < 0.12, (acc_ref, acc_ours)
+
+
+# ------------------------------------------------------------------ robustness / edge cases
+def test_many_ctas_global_prefix_path(sem, c_oracle):
+    """More CTAs than fit the shared-memory prefix stage (nb > 4096) and than one finalize chunk: same answers."""
+    import torch
+    N, T = 150_001, 4
+    Y = _truth_Y(0, T, 5, .1, False)
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=1, seed=8, mu=[20], n_population=[1000], block_particles=32)
+    r = sem.engine.run_pf(cfg, Y, np.array([2.0, 1.0]))
+    o = c_oracle.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=1, seed=8, mu=[20], npop=[1000])
+    torch.cuda.synchronize()
+    assert np.array_equal(r.ancestry[0].cpu().numpy(), o["ancestry"])
+    assert np.array_equal(r.X_hist[0].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+    np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
+
+
+def test_one_filter_of_a_batch_collapses(sem, c_oracle):
+    """Filters of a batch are independent: one collapsing (its status = step) leaves the others untouched."""
+    import torch
+    T = 8
+    Y = _truth_Y(0, T, 5, .1, False)
+    thetas = np.array([[2.0, 1.0], [0.01, 50.0], [1.8, 0.9]])          # filter 1: everyone recovers at once -> Y_I impossible
+    cfg = sem.engine.make_pf_config(0, 800, T, n_filters=3, probs=.1, resampler=1, arith=1, seed=5, filter_id0=0, mu=[20], n_population=[1000])
+    r = sem.engine.run_pf(cfg, Y, thetas)
+    torch.cuda.synchronize()
+    st = r.status.cpu().numpy()
+    assert st[0] == 0 and st[2] == 0 and st[1] > 0
+    for f in (0, 1, 2):
+        o = c_oracle.pf_run(0, Y, thetas[f], False, .1, 800, resampler=1, arith=1, seed=5, filter_id=f, mu=[20], npop=[1000])
+        assert o["collapsed"] == st[f]
+        if st[f] == 0:
+            assert np.array_equal(r.X_hist[f].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+    assert np.isneginf(r.log_zetas[1, -1].item())
+
+
+def test_seir_hidden_exposed_column(sem, c_oracle):
+    """Extension: a NaN column of Y is not weighed -- SEIR with the E compartment hidden (config 3)."""
+    import torch
+    T = 8
+    Y = _truth_Y(1, T, 5, .1, False)
+    Yh = Y.copy(); Yh[:, 1] = np.nan
+    cfg = sem.engine.make_pf_config(1, 1500, T, probs=.1, resampler=1, arith=1, seed=77, mu=[20], n_population=[1000])
+    r = sem.engine.run_pf(cfg, Yh, np.array([4.0, 1.0, 1.0]))
+    o = c_oracle.pf_run(1, Yh, [4.0, 1.0, 1.0], False, .1, 1500, resampler=1, arith=1, seed=77, mu=[20], npop=[1000])
+    torch.cuda.synchronize()
+    assert int(r.status[0]) == 0 == o["collapsed"]
+    assert np.array_equal(r.X_hist[0].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+    np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
+    full = c_oracle.pf_run(1, Y, [4.0, 1.0, 1.0], False, .1, 1500, resampler=1, arith=1, seed=77, mu=[20], npop=[1000])
+    assert o["log_zetas"][-1] > full["log_zetas"][-1]                  # dropping a column from the min can only raise the weights
+    z, H, A = sem.particle_filter(Yh, sem.ModelType.SEIR, np.array([4.0, 1.0, 1.0]), False, .1, 1500, 1000, 20, seed=77)
+    assert H.shape == (T, 1500, 4) and np.allclose(np.log(z), o["log_zetas"], rtol=1e-11)
