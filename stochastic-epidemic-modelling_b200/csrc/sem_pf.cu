@@ -14,7 +14,9 @@
 // pf_step(0) initialises X_0 (given, or I_0 ~ Poisson(mu) per pmcmc.py:156-169) and weighs it against Y[0].
 // Timing convention of the reference is kept: step p weighs X[p-1] against Y[p-1]; the last state is
 // never weighed.
+#include <cooperative_groups.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "sem_common.cuh"
 #include "sem_host.h"
@@ -39,7 +41,7 @@ struct PfDev {
     double *pfx[2];      // [F][nb]  exclusive prefix of scale_b * s_b
     double *scale[2];    // [F][nb]
     double *total[2];    // [F]
-    double2 *part;       // [F][nb]  (m_b, s_b)
+    double2 *part;       // [2][F][nb]  (m_b, s_b), by step parity
     unsigned int *counter;  // [F]
     // particle-sharded filter (one shard of a larger filter, see sem_shard_*): global index of particle 0, the
     // pre-gathered children records [N][C+1] (state, global ancestor) and the (M, total) summary of the local weights
@@ -95,6 +97,52 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
     return lw == CUDART_INF ? 0.0 : lw;                      // nothing observed at this time: weight 1
 }
 
+// Weigh the CTA's particles against Y[p] and CTA-local scan: writes L[par] and the CTA partial (m_b, s_b).
+template <class Model>
+__device__ __forceinline__ void weigh_local(const PfDev &P, const int p, const int f, const int b, const int tid,
+                                            const bool active, const int j, const double *x, double *sm) {
+    const int N = P.N, par = p & 1;
+    double lw = -CUDART_INF;
+    if (active) {
+        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs);
+        if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in the combine
+    }
+    const int nwarps = (blockDim.x + 31) >> 5;
+    const double mb = block_max(lw, sm, tid, nwarps);
+    const double e = (active && mb > -CUDART_INF && mb < CUDART_INF) ? exp(lw - mb) : 0.0;
+    double sb;
+    const double incl = block_incl_scan(e, sm, tid, nwarps, &sb);
+    if (active) P.L[par][(size_t)f * N + j] = incl;
+    if (tid == 0) P.part[((size_t)par * P.n_filters + f) * P.nb + b] = make_double2(mb, sb);
+}
+
+// Combine the CTA partials of parity `par` into (M, total) and per-CTA (prefix, scale) written to pfx_out/scale_out
+// (shared or global memory).  Called by every thread of a CTA.
+__device__ __forceinline__ void combine_partials(const PfDev &P, const int f, const int par, const int tid, double *sm,
+                                                 double *pfx_out, double *scale_out, double &M_out, double &total_out) {
+    const int nwarps = (blockDim.x + 31) >> 5;
+    const double2 *part = P.part + ((size_t)par * P.n_filters + f) * P.nb;
+    double M = -CUDART_INF;
+    for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
+    M = block_max(M, sm, tid, nwarps);
+    double carry = 0.0;
+    const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
+    for (int i0 = 0; i0 < P.nb; i0 += blockDim.x) {
+        const int i = i0 + tid;
+        double sc = 0.0, val = 0.0;
+        if (i < P.nb && finiteM) {
+            const double mi = __ldcg(&part[i].x), si = __ldcg(&part[i].y);
+            sc = (mi > -CUDART_INF) ? exp(mi - M) : 0.0;
+            val = sc * si;
+        }
+        double chunk;
+        const double incl2 = block_incl_scan(val, sm, tid, nwarps, &chunk);
+        if (i < P.nb) { pfx_out[i] = carry + (incl2 - val); scale_out[i] = sc; }
+        carry += chunk;
+    }
+    M_out = M; total_out = carry;
+}
+
 // Weigh the CTA's particles against Y[p], CTA-local scan, and (last CTA to arrive) the step's global combine.
 template <class Model>
 __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p, const int f, const int b, const int tid,
@@ -113,7 +161,7 @@ __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p,
     double sb;
     const double incl = block_incl_scan(e, sm, tid, nwarps, &sb);
     if (active) P.L[par][(size_t)f * N + j] = incl;
-    if (tid == 0) P.part[(size_t)f * P.nb + b] = make_double2(mb, sb);
+    if (tid == 0) P.part[((size_t)par * P.n_filters + f) * P.nb + b] = make_double2(mb, sb);
 
     // ------------------------------------------------------------------------ last CTA finalizes the step
     __threadfence();
@@ -122,7 +170,7 @@ __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p,
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    const double2 *part = P.part + (size_t)f * P.nb;
+    const double2 *part = P.part + ((size_t)par * P.n_filters + f) * P.nb;
     double M = -CUDART_INF;
     for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
     M = block_max(M, sm, tid, nwarps);
@@ -194,6 +242,129 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
     if (P.T > 1) weigh_scan_finalize<Model>(P, 0, f, b, tid, active, j, x, sm, &is_last);
 }
 
+// Ancestor of slot j at step p (pmcmc.py:187-193): first particle whose cdf exceeds u_j * total, by a two-level
+// search: CTA prefixes (shared or global memory), then the CTA's local scan L of the previous step.
+template <bool REPLAY>
+__device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, const int f, const int j, const uint32_t fid,
+                                               const double *pfx, const double *scale, const double total) {
+    const int N = P.N, par = p & 1;
+    double u;
+    if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
+    else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
+        const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+        const double u0 = bits_to_d12(w.x, w.y) - 1.0;
+        u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
+    } else {
+        const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+        u = bits_to_d12(w.x, w.y) - 1.0;
+    }
+    const double v = __dmul_rn(u, total);
+    int lo = 0, hi = P.nb;                                  // last CTA index with pfx[b] <= v  (pfx[0] = 0)
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= v) lo = mid; else hi = mid; }
+    const int base = lo * P.ppb, len = min(P.ppb, N - base);
+    const double sc = scale[lo], pf = pfx[lo];
+    const double *L = P.L[par ^ 1] + (size_t)f * N + base;
+    int a = 0, e = len;                                      // first i with pf + sc*L[i] > v
+    while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, __ldcg(&L[mid]), pf) <= v) a = mid + 1; else e = mid; }
+    return base + min(a, len - 1);
+}
+
+// Whole filter in ONE cooperative launch (one CTA per SM, all co-resident): the resampling barrier of every step is
+// a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
+// waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
+template <class Model, int ARITH>
+__global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double s_dyn[];                        // pfx[nb], scale[nb] of the previous step
+    double *s_pfx = s_dyn, *s_scale = s_dyn + P.nb;
+    __shared__ double sm[32];
+    __shared__ double2 s_tab[128];
+    __shared__ unsigned long long s_pairs;
+    const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
+    const int N = P.N, j = b * P.ppb + tid;
+    const bool active = tid < P.ppb && j < N;
+    const uint32_t fid = P.filter_id0 + f;
+    int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
+    int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
+    if (ARITH != SEM_ARITH_REFERENCE) load_logtab(s_tab);
+    if (tid == 0) s_pairs = 0ull;
+    __syncthreads();
+    double x[Model::C];
+    // ------------------------------------------------------------------------ step 0: X_0 (pmcmc.py:156-170)
+    if (active) {
+        if (!P.init_poisson) {
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = (double)P.X0[(size_t)c * N + j];
+        } else {
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = 0.0;
+#pragma unroll
+            for (int g = 0; g < Model::G; g++) {
+                PairSource<false> src; src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)g, stream_word(DOM_INIT, fid));
+                const double i0 = poisson_draw(src, P.mu[g]);
+                constexpr bool seir = (Model::C == 4);
+                x[seir ? 2 : 3 * g + 1] = i0;
+                x[seir ? 0 : 3 * g] = P.npop[g] - i0;
+            }
+        }
+        Af[j] = 0;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) Xf[(size_t)c * N + j] = (int32_t)x[c];
+    }
+    if (P.T > 1) weigh_local<Model>(P, 0, f, b, tid, active, j, x, sm);
+    bool dead = false;
+    double lz = 0.0;
+    unsigned long long my_pairs = 0;
+    for (int p = 1; p < P.T; p++) {
+        __threadfence();
+        grid.sync();                                         // the resampling barrier
+        if (dead) continue;
+        const int par = p & 1;
+        const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
+        double M, total;
+        combine_partials(P, f, par ^ 1, tid, sm, s_pfx, s_scale, M, total);
+        const bool ok = (M > -CUDART_INF && M < CUDART_INF) && (total > 0.0);
+        if (b == 0 && tid == 0) {
+            double *lzp = P.log_zetas + (size_t)f * P.T;
+            if (!ok) {
+                P.status[f] = p;                             // np.random.choice raises at step p (pmcmc.py:191-192)
+                for (int q = p; q < P.T; q++) lzp[q] = -CUDART_INF;
+            } else {
+                lz = lz + M + log(total) - log((double)N);  // zetas[p] = zetas[p-1] * mean(w), pmcmc.py:183
+                lzp[p] = lz;
+            }
+        }
+        if (!ok) { dead = true; continue; }
+        __syncthreads();                                     // s_pfx / s_scale complete
+        long long pairs = 0;
+        if (active) {
+            const int a = select_ancestor<false>(P, p, f, j, fid, s_pfx, s_scale, total);
+            Af[(size_t)row * N + j] = a;
+            const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) x[c] = (double)__ldcg(&Xp[(size_t)c * N + a]);   // written by other CTAs: L2, not L1
+            Model m;
+            m.setup(P.theta + (size_t)f * P.ntheta, x);
+            PairSource<false> src;
+            src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
+            pairs = ssa_run<Model, ARITH, false, false>(m, x, P.dt, src, s_tab, NoRec());
+            int32_t *Xr = Xf + (size_t)row * Model::C * N;
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
+        }
+        my_pairs += (unsigned long long)pairs;
+        if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm);
+    }
+    if (P.n_events) {                                        // one global atomic per CTA for the whole filter
+#pragma unroll
+        for (int d = 16; d; d >>= 1) my_pairs += __shfl_xor_sync(0xffffffffu, my_pairs, d);
+        if ((tid & 31) == 0 && my_pairs) atomicAdd(&s_pairs, my_pairs);
+        __syncthreads();
+        if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
+    }
+}
+
 // Step p >= 1: resample, gather, propagate, store, weigh (see the file header).
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(ARITH == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads)
@@ -231,26 +402,7 @@ __maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, con
     }
     if (active && !P.sharded) {
         // -------------------------------------------------------------------- resample (pmcmc.py:187-193)
-        const double total = P.total[par ^ 1][f];
-        double u;
-        if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
-        else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
-            const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
-            const double u0 = bits_to_d12(w.x, w.y) - 1.0;
-            u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
-        } else {
-            const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
-            u = bits_to_d12(w.x, w.y) - 1.0;
-        }
-        const double v = __dmul_rn(u, total);
-        int lo = 0, hi = P.nb;                              // last CTA index with pfx[b] <= v  (pfx[0] = 0)
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (pfx[mid] <= v) lo = mid; else hi = mid; }
-        const int base = lo * P.ppb, len = min(P.ppb, N - base);
-        const double sc = P.scale[par ^ 1][(size_t)f * P.nb + lo], pf = pfx[lo];
-        const double *L = P.L[par ^ 1] + (size_t)f * N + base;
-        int a = 0, e = len;                                  // first i with pf + sc*L[i] > v
-        while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, L[mid], pf) <= v) a = mid + 1; else e = mid; }
-        a = base + min(a, len - 1);
+        const int a = select_ancestor<REPLAY>(P, p, f, j, fid, pfx, P.scale[par ^ 1] + (size_t)f * P.nb, P.total[par ^ 1][f]);
         Af[(size_t)row * N + j] = a;
         // -------------------------------------------------------------------- gather parent (pmcmc.py:195-199)
         const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
@@ -413,7 +565,7 @@ static WsLayout ws_layout(const sem_pf_config *c) {
     for (int i = 0; i < 2; i++) w.pfx[i] = take(F * w.nb * sizeof(double));
     for (int i = 0; i < 2; i++) w.scale[i] = take(F * w.nb * sizeof(double));
     for (int i = 0; i < 2; i++) w.total[i] = take(F * sizeof(double));
-    w.part = take(F * w.nb * sizeof(double2));
+    w.part = take(2 * F * w.nb * sizeof(double2));
     w.counter = take(F * sizeof(unsigned int));
     w.bytes = off;
     return w;
@@ -459,7 +611,7 @@ size_t sem_pf_hist_elems(const sem_pf_config *c) {
     return (size_t)c->n_filters * hist_rows(c) * model_cols(c->model, G) * c->n_particles;
 }
 size_t sem_pf_ancestry_elems(const sem_pf_config *c) { return validate(c) ? 0 : (size_t)c->n_filters * hist_rows(c) * c->n_particles; }
-int sem_pf_launch_count(const sem_pf_config *c) { return validate(c) ? 0 : c->n_obs; }
+int sem_pf_launch_count(const sem_pf_config *c);
 
 static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &P, WsLayout &w, bool &replay) {
     int rc = validate(cfg);
@@ -509,6 +661,50 @@ static void launch_step(const sem_pf_config *cfg, const PfDev &P, const WsLayout
     }
 }
 
+}  // extern "C"
+
+template <class Model>
+static const void *persistent_fn(int arith) {
+    return arith == SEM_ARITH_REFERENCE ? (const void *)pf_persistent<Model, SEM_ARITH_REFERENCE>
+                                        : (const void *)pf_persistent<Model, SEM_ARITH_FAST>;
+}
+static const void *persistent_kernel(const sem_pf_config *cfg) {
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    switch (cfg->model) {
+        case SEM_MODEL_SIR: return persistent_fn<SirModel>(cfg->arith);
+        case SEM_MODEL_SEIR: return persistent_fn<SeirModel>(cfg->arith);
+        default:
+            switch (G) {
+                case 1: return persistent_fn<SubModel<1>>(cfg->arith);
+                case 2: return persistent_fn<SubModel<2>>(cfg->arith);
+                case 3: return persistent_fn<SubModel<3>>(cfg->arith);
+                default: return persistent_fn<SubModel<4>>(cfg->arith);
+            }
+    }
+}
+
+// One cooperative launch for the whole filter when every CTA can be co-resident (SEM_NO_PERSISTENT=1 or
+// cfg->reserved = 1 forces the launch-per-step path; both give bit-identical results).
+static bool use_persistent(const sem_pf_config *cfg, const WsLayout &w, bool replay) {
+    if (replay || cfg->reserved == 1 || cfg->arith == SEM_ARITH_UNIFORMIZED || w.nb > 1024 || cfg->n_obs < 2) return false;
+    static int env_off = -1;
+    if (env_off < 0) { const char *e = getenv("SEM_NO_PERSISTENT"); env_off = (e && e[0] == '1') ? 1 : 0; }
+    if (env_off) return false;
+    int dev = 0, coop = 0, per_sm = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return false;
+    const int threads = (w.ppb + 31) / 32 * 32;
+    const size_t smem = 2 * (size_t)w.nb * sizeof(double);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel(cfg), threads, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+    return (long long)per_sm * sm_count() >= (long long)w.nb * cfg->n_filters;
+}
+
+extern "C" {
+
+int sem_pf_launch_count(const sem_pf_config *c) {
+    if (validate(c)) return 0;
+    return use_persistent(c, ws_layout(c), false) ? 1 : c->n_obs;
+}
+
 int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream) {
     PfDev P; WsLayout w; bool replay;
     int rc = fill_dev(cfg, buf, P, w, replay);
@@ -518,6 +714,12 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     SEM_CUDA(cudaMemsetAsync(P.status, 0, cfg->n_filters * sizeof(int32_t), s));
     SEM_CUDA(cudaMemsetAsync(P.log_zetas, 0, (size_t)cfg->n_filters * cfg->n_obs * sizeof(double), s));   // zetas[0] = 1 (pmcmc.py:154)
     if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
+    if (use_persistent(cfg, w, replay)) {
+        void *args[] = {(void *)&P};
+        const dim3 grid(w.nb, cfg->n_filters), block((w.ppb + 31) / 32 * 32);
+        SEM_CUDA(cudaLaunchCooperativeKernel(persistent_kernel(cfg), grid, block, args, 2 * (size_t)w.nb * sizeof(double), s));
+        return SEM_OK;
+    }
     for (int p = 0; p < cfg->n_obs; p++) launch_step(cfg, P, w, p, replay, s);
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;

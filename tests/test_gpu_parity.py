@@ -584,3 +584,25 @@ def test_seir_hidden_exposed_column(sem, c_oracle):
     assert o["log_zetas"][-1] > full["log_zetas"][-1]                  # dropping a column from the min can only raise the weights
     z, H, A = sem.particle_filter(Yh, sem.ModelType.SEIR, np.array([4.0, 1.0, 1.0]), False, .1, 1500, 1000, 20, seed=77)
     assert H.shape == (T, 1500, 4) and np.allclose(np.log(z), o["log_zetas"], rtol=1e-11)
+
+
+@pytest.mark.parametrize("model,G,theta,npop,mu,arith", [(0, 1, [2.0, 1.0], [1000], [20], 1), (0, 1, [2.0, 1.0], [1000], [20], 0),
+                                                          (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1)])
+def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, npop, mu, arith):
+    """The whole-filter cooperative kernel (grid.sync() as the resampling barrier) and the launch-per-step path are
+    bit-identical, including a multi-filter batch and the two-row (ping-pong) history."""
+    import torch
+    T = 7
+    Y = _truth_Y(model, T, 5, .1, False, G=G)
+    for F, N, hist in [(1, 3000, True), (3, 700, True), (1, 5000, False)]:
+        outs = []
+        for per_step in (False, True):
+            cfg = sem.engine.make_pf_config(model, N, T, G=G, n_filters=F, probs=.1, resampler=1, arith=arith, seed=6, filter_id0=2,
+                                            mu=mu, n_population=npop, store_history=hist, launch_per_step=per_step)
+            r = sem.engine.run_pf(cfg, Y, np.tile(np.array(theta, float), (F, 1)))
+            torch.cuda.synchronize()
+            outs.append((r.launches, r.X_hist.cpu().numpy(), r.ancestry.cpu().numpy(), r.log_zetas.cpu().numpy(), r.n_events.cpu().numpy(),
+                         r.status.cpu().numpy()))
+        assert outs[0][0] == 1 and outs[1][0] == T
+        for k in range(1, 6):
+            assert np.array_equal(outs[0][k], outs[1][k]), (F, N, hist, k)
