@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsem_b200.so")
+LIB_PATH = os.environ.get("SEM_LIB_PATH") or os.path.join(HERE, "libsem_b200.so")   # SEM_LIB_PATH: debug builds
 
 SEM_MAX_GROUPS = 4
 MODEL_SIR, MODEL_SEIR, MODEL_SIR_SUBGROUPS, MODEL_SIR_SUBGROUPS2 = 0, 1, 2, 3

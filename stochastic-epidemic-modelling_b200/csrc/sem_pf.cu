@@ -269,6 +269,13 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
     return base + min(a, len - 1);
 }
 
+#ifdef SEM_PHASES
+__device__ unsigned long long g_phase[8 * 256];
+#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_phase[p * 8 + (k)] = t_; } } while (0)
+#else
+#define PHASE(k)
+#endif
+
 // Whole filter in ONE cooperative launch (one CTA per SM, all co-resident): the resampling barrier of every step is
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
 // waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
@@ -317,8 +324,9 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
     double lz = 0.0;
     unsigned long long my_pairs = 0;
     for (int p = 1; p < P.T; p++) {
-        __threadfence();
-        grid.sync();                                         // the resampling barrier
+        PHASE(0);
+        grid.sync();                                         // the resampling barrier (grid-wide fence + barrier)
+        PHASE(1);
         if (dead) continue;
         const int par = p & 1;
         const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
@@ -337,6 +345,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
         }
         if (!ok) { dead = true; continue; }
         __syncthreads();                                     // s_pfx / s_scale complete
+        PHASE(2);
         long long pairs = 0;
         if (active) {
             const int a = select_ancestor<false>(P, p, f, j, fid, s_pfx, s_scale, total);
@@ -354,7 +363,11 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
             for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
         }
         my_pairs += (unsigned long long)pairs;
+        PHASE(3);
+        __syncthreads();                                     // keep the CTA in the SSA loop until its last warp is done: letting early
+        PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
         if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm);
+        PHASE(5);
     }
     if (P.n_events) {                                        // one global atomic per CTA for the whole filter
 #pragma unroll
@@ -780,6 +793,13 @@ int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, con
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }
+
+#ifdef SEM_PHASES
+int sem_debug_phases(unsigned long long *host_out) {
+    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 8 * 256));
+    return SEM_OK;
+}
+#endif
 
 int sem_path_sample(const int32_t *X_hist, const int32_t *ancestry, int32_t T, int32_t N, int32_t C, int32_t chosen,
                     int32_t exact, uint64_t seed, uint32_t filter_id, int32_t *traj, void *stream) {

@@ -604,5 +604,12 @@ def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, 
             outs.append((r.launches, r.X_hist.cpu().numpy(), r.ancestry.cpu().numpy(), r.log_zetas.cpu().numpy(), r.n_events.cpu().numpy(),
                          r.status.cpu().numpy()))
         assert outs[0][0] == 1 and outs[1][0] == T
-        for k in range(1, 6):
-            assert np.array_equal(outs[0][k], outs[1][k]), (F, N, hist, k)
+        assert np.array_equal(outs[0][5], outs[1][5])                          # status (0, or the step of the collapse)
+        for f in range(F):
+            upto = int(outs[0][5][f]) or T                                     # rows before a collapse are defined, later ones are not
+            rows = range(upto) if hist else ([] if outs[0][5][f] else range(2))
+            for r_ in rows:
+                assert np.array_equal(outs[0][1][f, r_], outs[1][1][f, r_]) and np.array_equal(outs[0][2][f, r_], outs[1][2][f, r_]), (F, N, hist, f, r_)
+            assert np.array_equal(outs[0][3][f], outs[1][3][f]), (F, N, hist, f)
+            if not outs[0][5][f]:
+                assert outs[0][4][f] == outs[1][4][f]

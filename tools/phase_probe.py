@@ -1,0 +1,35 @@
+"""Debug: per-step phase timestamps of CTA 0 in the cooperative kernel.  Builds a -DSEM_PHASES copy of the library into
+/tmp and loads it instead of the in-tree one."""
+import ctypes as C, os, sys, subprocess
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+pkg = os.path.join(ROOT, "stochastic-epidemic-modelling_b200")
+dbg = "/tmp/libsem_b200_phases.so"
+src = [os.path.join(pkg, "csrc", f) for f in ("sem_pf.cu", "sem_sim_abc.cu")]
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--fmad=false", "-DSEM_PHASES",
+                       "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", dbg] + src)
+import numpy as np, torch
+import sem_b200, workloads
+from sem_b200 import engine, _lib
+_lib.LIB_PATH = dbg
+_lib._lib = None
+L = _lib.load()
+Y = workloads.headline_Y()
+N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+cfg = engine.make_pf_config(0, N, 101, probs=.1, seed=1, mu=[20], n_population=[10000])
+out = engine.alloc_pf_outputs(cfg)
+for _ in range(3):
+    engine.run_pf(cfg, Y, np.array([.4, .2]), out=out)
+torch.cuda.synchronize()
+buf = np.zeros(8 * 256, dtype=np.uint64)
+assert L.sem_debug_phases(buf.ctypes.data_as(C.c_void_p)) == 0
+ph = buf.reshape(256, 8)[1:101].astype(np.int64)
+names = ["grid.sync", "combine", "search+SSA (own warp)", "wait CTA", "weigh+scan"]
+d = np.diff(ph[:, :6], axis=1) / 1e3
+print("per-step mean us (CTA 0, thread 0):")
+for k, nm in enumerate(names):
+    print(f"  {nm:24s} mean {d[:, k].mean():8.2f}  min {d[:, k].min():8.2f}  max {d[:, k].max():8.2f}")
+step = (ph[1:, 0] - ph[:-1, 0]) / 1e3
+print("  step-to-step            mean %.2f  total %.2f ms" % (step.mean(), step.sum() / 1e3))
+for p in (1, 10, 28, 60, 95):
+    print("  step", p + 1, np.round(d[p], 2))
