@@ -189,7 +189,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=None, help="override n_particles (not the headline then)")
     ap.add_argument("--resampler", default="systematic")
-    ap.add_argument("--arith", default="fast")
+    ap.add_argument("--arith", default="fast32")
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

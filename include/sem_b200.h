@@ -45,8 +45,10 @@ enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
  * UNIFORMIZED is exact too (same law of the state at the end of the interval) but draws no waiting times: the jump
  * chain is thinned from a rate-B Poisson stream of candidates whose NUMBER in the interval is drawn once; if a
  * fired event lifts the total propensity above B, that candidate's time is drawn from its order-statistic (Beta)
- * law and the rest of the interval restarts with a new bound. */
-enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2 };
+ * law and the rest of the interval restarts with a new bound.
+ * FAST32 is FAST with 32-bit uniforms: event k of a particle-step takes two words of Philox call k/2 (u1 = words 0/2,
+ * u2 = words 1/3), so one Philox4x32-10 call serves two events; all arithmetic stays fp64. */
+enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2, SEM_ARITH_FAST32 = 3 };
 
 enum {
     SEM_OK = 0,

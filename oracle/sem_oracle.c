@@ -44,7 +44,7 @@
 #define SO_MAX_R (SO_MAX_G * SO_MAX_G + SO_MAX_G)
 
 enum { M_SIR = 0, M_SEIR = 1, M_SUB = 2, M_SUB2 = 3 };
-enum { ARITH_REF = 0, ARITH_FAST = 1, ARITH_UNIF = 2 };
+enum { ARITH_REF = 0, ARITH_FAST = 1, ARITH_UNIF = 2, ARITH_FAST32 = 3 };
 enum { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7, DOM_AUX = 8 };
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
@@ -72,8 +72,12 @@ static inline double u52(uint32_t lo, uint32_t hi) {
     return d - 1.0;
 }
 
+/* one 32-bit word -> double in [0,1) with 32 random bits (the SSA streams of ARITH_FAST32) */
+static inline double u32d(uint32_t w) { return (double)w * (1.0 / 4294967296.0); }
+
 typedef struct {
     int philox;            /* 0 = replay buffer, 1 = philox */
+    int bits32;            /* philox only: event k takes words (2(k&1), 2(k&1)+1) of call k>>1 (ARITH_FAST32) */
     const double *u;       /* replay: next doubles */
     int64_t pos, len;      /* replay cursor / limit */
     int overrun;           /* replay buffer exhausted */
@@ -84,7 +88,13 @@ typedef struct {
 
 /* one pair of uniforms = one SSA event's draws */
 static inline void stream_pair(so_stream *s, double *u1, double *u2) {
-    if (s->philox) {
+    if (s->philox && s->bits32) {
+        uint32_t ctr[4] = {s->k >> 1, s->c1, s->c2, s->c3}, w[4];
+        so_philox4x32(ctr, s->key, w);
+        *u1 = u32d(w[2 * (s->k & 1)]);
+        *u2 = u32d(w[2 * (s->k & 1) + 1]);
+        s->k++;
+    } else if (s->philox) {
         uint32_t ctr[4] = {s->k++, s->c1, s->c2, s->c3}, w[4];
         so_philox4x32(ctr, s->key, w);
         *u1 = u52(w[0], w[1]);
@@ -183,6 +193,7 @@ static int64_t ssa_run(const so_model *m, double *x, double max_time, int arith,
                        double *times, double *states, int64_t max_rec, int64_t *n_rec) {
     if (arith == ARITH_UNIF && s->philox && !times) return ssa_run_unif(m, x, max_time, s);
     if (arith == ARITH_UNIF) arith = ARITH_FAST;
+    if (arith == ARITH_FAST32) { arith = ARITH_FAST; s->bits32 = s->philox; }   /* same arithmetic, 32-bit streams */
     double r[SO_MAX_R], cdf[SO_MAX_R];
     const int R = m->R, C = m->C;
     double N = model_popsize(m, x), invN = 1.0 / N;
@@ -577,6 +588,7 @@ int so_abc_trials(const so_abc_cfg *cfg, const double *obs, int64_t n_trials, ui
             gamma = cfg->prior[2] + (cfg->prior[3] - cfg->prior[2]) * u2;     /* :37 */
             for (int c = 0; c < 3; c++) x[c] = poisson_draw(&ps, (double)(int64_t)obs[c]);   /* :39-40 */
             philox_stream(&s, cfg->seed, (uint32_t)id, (uint32_t)(id >> 32), DOM_ABC_SSA, 0);
+            s.bits32 = (cfg->arith == ARITH_FAST32);
         } else {
             beta = theta_in[2 * i]; gamma = theta_in[2 * i + 1];
             for (int c = 0; c < 3; c++) x[c] = (double)n_start_in[3 * i + c];

@@ -44,7 +44,7 @@ def _device_trajectories(obs, ids, threshold, prior4, seed, arith):
     return out["traj"].cpu().numpy()
 
 
-def abc_rejection(observed_data, no_of_samples, threshold, priors, *, seed=None, batch=None, arith="fast",
+def abc_rejection(observed_data, no_of_samples, threshold, priors, *, seed=None, batch=None, arith="fast32",
                   early_reject=True, max_trials=None, run_batch=None, run_traj=None, stats=None):
     """Engine behind abc_algo.  run_batch / run_traj are injectable (tests drive the sharding logic with a CPU
     executor); by default they launch the CUDA kernels."""
@@ -94,7 +94,7 @@ def abc_rejection(observed_data, no_of_samples, threshold, priors, *, seed=None,
     return theta, traj
 
 
-def abc_algo(observed_data, no_of_samples, threshold, priors, *, seed=None, batch=None, arith="fast",
+def abc_algo(observed_data, no_of_samples, threshold, priors, *, seed=None, batch=None, arith="fast32",
              early_reject=True, max_trials=None, stats=None):
     """ABC rejection sampler (abc_algo.py:17-109).  observed_data (T,3) [S,I,R]; priors {'beta':[lo,hi],'gamma':[lo,hi]}."""
     theta, traj = abc_rejection(observed_data, no_of_samples, threshold, priors, seed=seed, batch=batch, arith=arith,

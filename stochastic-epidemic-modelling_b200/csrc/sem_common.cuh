@@ -40,6 +40,11 @@ __device__ __forceinline__ double bits_to_d12(uint32_t lo, uint32_t hi) {
     return __hiloint2double((int)(0x3FF00000u | (hi >> 12)), (int)((hi << 20) | (lo >> 12)));
 }
 
+// one word -> double in [1,2) carrying 32 random bits (the 32-bit streams of SEM_ARITH_FAST32)
+__device__ __forceinline__ double word_to_d12(uint32_t w) {
+    return __hiloint2double((int)(0x3FF00000u | (w >> 12)), (int)(w << 20));
+}
+
 __host__ __device__ __forceinline__ uint32_t stream_word(uint32_t domain, uint32_t fid) { return (domain << 24) | (fid & 0xFFFFFFu); }
 
 // A sequential source of (u1,u2) pairs: one Philox call, or two doubles of a replay buffer.
@@ -59,47 +64,46 @@ struct PairSource<false> {
 };
 
 // ------------------------------------------------------------------------------------------ fast fp64 helpers
-// -log(x) for x in (0,1] without a division: x = z * 2^k with z in [0.6875, 1.375); a 128-entry table gives
-// (1/c, log c) for the mantissa-bit subinterval of z; r = z/c - 1 (one FMA, |r| < 2^-8) and
-// log1p(r) = r - r^2/2 + ... - r^6/6 (truncation < 3e-18).  Absolute error ~1e-16 + 1e-16*|log x| (checked against
-// libm on the GPU by tests/test_gpu_parity.py::test_fast_math).  The table lives in shared memory.
+// -log(x) for x in (0,1] without a division: x = z * 2^k with z in [0.6875, 1.375); a 1024-entry table gives
+// (1/c, log c) for the mantissa-bit subinterval of z; r = z/c - 1 (one FMA, |r| < 2^-11) and
+// log1p(r) = r - r^2/2 + r^3/3 - r^4/4 (truncation r^5/5 < 6e-18).  Absolute error ~1e-16 + 1e-16*|log x| (checked
+// against libm on the GPU by tests/test_gpu_parity.py::test_fast_math).  The table (16 KB) lives in shared memory.
 // (global memory, not __constant__: the copy into shared memory indexes it by thread id, which the constant cache
 // would serialise)
-static __device__ const double2 kLogTab[128] = {
+constexpr int kLogTabBits = 10, kLogTabSize = 1 << kLogTabBits;
+static __device__ const double2 kLogTab[kLogTabSize] = {
 #include "sem_logtab.inc"
 };
 
 __device__ __forceinline__ void load_logtab(double2 *smem_tab) {
-    for (int i = threadIdx.x; i < 128; i += blockDim.x) smem_tab[i] = kLogTab[i];
+    for (int i = threadIdx.x; i < kLogTabSize; i += blockDim.x) smem_tab[i] = kLogTab[i];
 }
 
-static __constant__ double kLogPoly[6] = {-1.0 / 6, 1.0 / 5, -1.0 / 4, 1.0 / 3, -1.0 / 2, 0x1.62e42fefa39efp-1 /* ln 2 */};
+static __constant__ double kLogPoly[4] = {-1.0 / 4, 1.0 / 3, -1.0 / 2, 0x1.62e42fefa39efp-1 /* ln 2 */};
 
 __device__ __forceinline__ double neg_log_fast(double x, const double2 *tab) {
     const int hi = __double2hiint(x), lo = __double2loint(x);
     const int tmp = hi - 0x3fe60000;
-    const int i = (tmp >> 13) & 127;
+    const int i = (tmp >> (20 - kLogTabBits)) & (kLogTabSize - 1);
     const int k = tmp >> 20;                                   // arithmetic shift: floor exponent offset (<= 0 here)
     const double z = __hiloint2double(hi - (tmp & 0xfff00000), lo);
     const double2 tc = tab[i];
     const double r = __fma_rn(z, tc.x, -1.0);
-    const double w = __fma_rn((double)k, kLogPoly[5], tc.y);
+    const double w = __fma_rn((double)k, kLogPoly[3], tc.y);
     const double r2 = __dmul_rn(r, r);
     double p = __fma_rn(r, kLogPoly[0], kLogPoly[1]);
     p = __fma_rn(r, p, kLogPoly[2]);
-    p = __fma_rn(r, p, kLogPoly[3]);
-    p = __fma_rn(r, p, kLogPoly[4]);
     return -__fma_rn(r2, p, __dadd_rn(w, r));
 }
 
-// 1/a for normal positive a, no IEEE fix-up path: hardware seed y0 (rcp.approx.ftz.f64, rel. error e ~ 2^-20 or
-// better), then 1/a = y0 (1 + e + e^2 + e^3 + ...) cut after e^3 (a 4th-order step, 2^-80) and rounded: <= 1 ulp.
+// 1/a for normal positive a, no IEEE fix-up path: hardware seed y0 (rcp.approx.ftz.f64 looks at the high word only,
+// rel. error e <~ 2^-20), then 1/a = y0 (1 + e + e^2 + ...) cut after e^2 (a 3rd-order step, 2^-60) and rounded:
+// <= 1 ulp.  a = 0 gives NaN (0 * inf), which the SSA loops use as "no event".
 __device__ __forceinline__ double rcp_nr(double a) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double e = __fma_rn(-a, y, 1.0);
-    const double e2 = __dmul_rn(e, e);
-    const double q = __fma_rn(e2, e, __dadd_rn(e2, e));     // e + e^2 + e^3
+    const double q = __fma_rn(e, e, e);                      // e + e^2
     return __fma_rn(y, q, y);
 }
 
@@ -217,10 +221,10 @@ struct SirModel {
     // TRACK_R = false leaves the removed count to fix_removed() (R = N - S - I): one fp64 op less per event
     template <bool TRACK_R = true>
     __device__ __forceinline__ void apply(double *x, int j) const {                                     // :43-46
-        const bool inf = (j == 0);
-        x[0] = inf ? x[0] - 1.0 : x[0];
-        x[1] = inf ? x[1] + 1.0 : x[1] - 1.0;
-        if (TRACK_R) x[2] = inf ? x[2] : x[2] + 1.0;
+        const bool inf = (j == 0);                                       // +-1 / 0 are exact: one add per compartment
+        x[0] = x[0] + (inf ? -1.0 : 0.0);
+        x[1] = x[1] + (inf ? 1.0 : -1.0);
+        if (TRACK_R) x[2] = x[2] + (inf ? 0.0 : 1.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[2] = N - x[0] - x[1]; }
 };
@@ -243,10 +247,10 @@ struct SeirModel {
     }
     template <bool TRACK_R = true>
     __device__ __forceinline__ void apply(double *x, int j) const {                                     // :113-117
-        x[0] = (j == 0) ? x[0] - 1.0 : x[0];
-        x[1] = (j == 0) ? x[1] + 1.0 : ((j == 1) ? x[1] - 1.0 : x[1]);
-        x[2] = (j == 1) ? x[2] + 1.0 : ((j == 2) ? x[2] - 1.0 : x[2]);
-        if (TRACK_R) x[3] = (j == 2) ? x[3] + 1.0 : x[3];
+        x[0] = x[0] + ((j == 0) ? -1.0 : 0.0);
+        x[1] = x[1] + ((j == 0) ? 1.0 : ((j == 1) ? -1.0 : 0.0));
+        x[2] = x[2] + ((j == 1) ? 1.0 : ((j == 2) ? -1.0 : 0.0));
+        if (TRACK_R) x[3] = x[3] + ((j == 2) ? 1.0 : 0.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[3] = N - x[0] - x[1] - x[2]; }
 };
@@ -412,6 +416,92 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
     return pairs;
 }
 
+// FAST order, Philox only: the same arithmetic as ssa_run_fast event by event (bit-identical states and draw counts),
+// executed U events at a time.  Only the reaction choice feeds back into the state (rates -> a0 -> u2*a0 -> compare ->
+// +-1); the reciprocal / logarithm / waiting-time chain is feed-forward, and the interval end is decided by the running
+// time alone.  So a block advances the state speculatively through U events (a short dependent chain), evaluates the U
+// waiting times with U-fold instruction-level parallelism, and tests the interval end ONCE (times are non-decreasing,
+// and a non-positive a0 -- an extinct or frozen state -- makes its time NaN, which poisons every later sum).  The
+// block in which the interval ends rolls back to the last event that fired; the Philox draws after it are simply unused
+// (streams restart at counter 0 every particle-step, so nothing downstream shifts).
+// BITS32 (SEM_ARITH_FAST32): event k takes words (2(k&1), 2(k&1)+1) of Philox call k>>1 -- u1 and u2 carry 32 random
+// bits each, one call serves two events.  The 32x32->64 multiplies of Philox are the most expensive instructions of
+// the loop on sm_100a (IMAD.WIDE issues once per ~4 cycles, tools/micro/pipes2.cu), so this halves its largest cost.
+template <class Model, int U, bool BITS32, bool TRACK_R, class Rec>
+__device__ __forceinline__ long long ssa_run_spec(const Model &m, double *x, double max_time, PairSource<false> &src,
+                                                  const double2 *tab, Rec rec) {
+    static_assert(!BITS32 || U % 2 == 0, "32-bit streams serve two events per call");
+    if (!m.alive(x)) { if (!TRACK_R) m.fix_removed(x); return 0; }
+    double t = 0.0;
+    int pairs = 0;
+    PairSource<false> loc = src;
+    double xs[U + 1][Model::C];
+#pragma unroll
+    for (int c = 0; c < Model::C; c++) xs[0][c] = x[c];
+    for (;;) {
+        double d1[U], d2[U], a0[U], tn[U];
+        if constexpr (BITS32) {
+#pragma unroll
+            for (int i = 0; i < U; i += 2) {
+                const uint4 w = loc.raw();
+                d1[i] = word_to_d12(w.x); d2[i] = word_to_d12(w.y); d1[i + 1] = word_to_d12(w.z); d2[i + 1] = word_to_d12(w.w);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < U; i++) { const uint4 w = loc.raw(); d1[i] = bits_to_d12(w.x, w.y); d2[i] = bits_to_d12(w.z, w.w); }
+        }
+#pragma unroll
+        for (int i = 0; i < U; i++) {                                      // state chain (speculative)
+            double r[Model::R];
+            a0[i] = ssa_total<Model, SEM_ARITH_FAST>(m, xs[i], r);
+            const double v = __fma_rn(d2[i], a0[i], -a0[i]);
+            double acc = r[0];
+            int j = (acc <= v) ? 1 : 0;
+#pragma unroll
+            for (int k = 1; k < Model::R - 1; k++) { acc = __dadd_rn(acc, r[k]); j += (acc <= v) ? 1 : 0; }
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) xs[i + 1][c] = xs[i][c];
+            m.template apply<TRACK_R>(xs[i + 1], j);
+        }
+        double tt = t;
+#pragma unroll
+        for (int i = 0; i < U; i++) {                                      // waiting times (feed-forward, independent)
+            const double E = neg_log_fast(__dsub_rn(2.0, d1[i]), tab);
+            tt = __dadd_rn(tt, __dmul_rn(E, rcp_nr(a0[i])));
+            tn[i] = tt;
+        }
+        if (tn[U - 1] <= max_time) {                                       // all U events fired (gillespie_algo.py:65)
+            pairs += U;
+            t = tt;
+#pragma unroll
+            for (int i = 0; i < U; i++) rec(tn[i], xs[i + 1]);
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) xs[0][c] = xs[U][c];
+            continue;
+        }
+        int nf = 0;                                                        // the interval ends inside this block
+#pragma unroll
+        for (int i = 0; i < U; i++) nf += (tn[i] <= max_time) ? 1 : 0;
+#pragma unroll
+        for (int i = 0; i < U - 1; i++) if (i < nf) rec(tn[i], xs[i + 1]);
+        double a_stop = a0[0];
+#pragma unroll
+        for (int i = 1; i < U; i++) a_stop = (nf == i) ? a0[i] : a_stop;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) {
+            double v = xs[0][c];
+#pragma unroll
+            for (int i = 1; i < U; i++) v = (nf == i) ? xs[i][c] : v;
+            x[c] = v;
+        }
+        pairs += nf + ((a_stop > 0) ? 1 : 0);                              // the discarded draw counts when one was made
+        break;
+    }
+    src.k = loc.k;
+    if (!TRACK_R) m.fix_removed(x);
+    return pairs;
+}
+
 // ------------------------------------------------------------------------------------------ uniformized interval
 // Exact simulation of the state at the end of an interval WITHOUT waiting times (Jensen's uniformization with a
 // restart rule).  While the total propensity a0(x) stays <= B, the jump process is a rate-B Poisson stream of
@@ -508,10 +598,19 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
     return total_fired;
 }
 
+// events per speculative block of the production loops (measured, tools/micro/ssa_loop.cu): 4 with 32-bit uniforms
+// (two Philox calls in flight), 2 with 52-bit uniforms (4 spills under the 80-register cap); models with many
+// compartments keep fewer speculative states in registers (0 = the one-event-per-iteration loop)
+template <class Model> struct SpecBlock { static constexpr int bits32 = Model::C <= 4 ? 4 : 2, bits52 = Model::C <= 6 ? 2 : 0; };
+
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,
                                              const double2 *tab, Rec rec) {
-    if constexpr (ARITH == SEM_ARITH_FAST && !REPLAY) return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, rec);
+    if constexpr (ARITH == SEM_ARITH_FAST && !REPLAY) {
+        if constexpr (SpecBlock<Model>::bits52 > 0) return ssa_run_spec<Model, SpecBlock<Model>::bits52, false, TRACK_R>(m, x, max_time, src, tab, rec);
+        else return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, rec);
+    }
+    else if constexpr (ARITH == SEM_ARITH_FAST32 && !REPLAY) return ssa_run_spec<Model, SpecBlock<Model>::bits32, true, TRACK_R>(m, x, max_time, src, tab, rec);
     else if constexpr (ARITH == SEM_ARITH_UNIFORMIZED && !REPLAY) {
         PairSource<false> aux; aux.init(src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
         return ssa_run_unif<Model, TRACK_R>(m, x, max_time, src, aux, tab);

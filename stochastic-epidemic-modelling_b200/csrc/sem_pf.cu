@@ -286,7 +286,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
     extern __shared__ double s_dyn[];                        // pfx[nb], scale[nb] of the previous step
     double *s_pfx = s_dyn, *s_scale = s_dyn + P.nb;
     __shared__ double sm[32];
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[kLogTabSize];
     __shared__ unsigned long long s_pairs;
     const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
     const int N = P.N, j = b * P.ppb + tid;
@@ -384,7 +384,7 @@ __global__ void __launch_bounds__(ARITH == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUn
 __maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, const int p) {
     extern __shared__ double s_pfx[];                        // previous step's CTA prefixes (when they fit)
     __shared__ double sm[32];
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[kLogTabSize];
     __shared__ unsigned long long s_pairs;
     __shared__ bool is_last;
     const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
@@ -591,6 +591,7 @@ static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 gri
     else if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_UNIFORMIZED) pf_step<Model, SEM_ARITH_UNIFORMIZED, false><<<grid, threads, smem, s>>>(P, p);
+    else if (arith == SEM_ARITH_FAST32) pf_step<Model, SEM_ARITH_FAST32, false><<<grid, threads, smem, s>>>(P, p);
     else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, smem, s>>>(P, p);
 }
 
@@ -679,6 +680,7 @@ static void launch_step(const sem_pf_config *cfg, const PfDev &P, const WsLayout
 template <class Model>
 static const void *persistent_fn(int arith) {
     return arith == SEM_ARITH_REFERENCE ? (const void *)pf_persistent<Model, SEM_ARITH_REFERENCE>
+           : arith == SEM_ARITH_FAST32  ? (const void *)pf_persistent<Model, SEM_ARITH_FAST32>
                                         : (const void *)pf_persistent<Model, SEM_ARITH_FAST>;
 }
 static const void *persistent_kernel(const sem_pf_config *cfg) {

@@ -63,7 +63,7 @@ struct EventLogRef { EventLog<C> *l; __device__ __forceinline__ void operator()(
 
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[kLogTabSize];
     if (ARITH != SEM_ARITH_REFERENCE && !REPLAY) load_logtab(s_tab);
     __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,6 +107,7 @@ static void launch_sim(const SimDev &P, int arith, bool replay, cudaStream_t s) 
     else if (arith == SEM_ARITH_REFERENCE) sim_kernel<Model, SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
     else if (arith == SEM_ARITH_UNIFORMIZED && P.cap == 0 && P.daily == 0)      // no event times exist to log
         sim_kernel<Model, SEM_ARITH_UNIFORMIZED, false><<<blocks, threads, 0, s>>>(P);
+    else if (arith == SEM_ARITH_FAST32) sim_kernel<Model, SEM_ARITH_FAST32, false><<<blocks, threads, 0, s>>>(P);
     else sim_kernel<Model, SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);
 }
 
@@ -131,8 +132,9 @@ constexpr int kAbcMaxDays = 128;
 template <int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
     __shared__ double s_obs[kAbcMaxDays * 2];                            // (I_obs, R_obs) per day
-    __shared__ double2 s_tab[128];
-    constexpr bool FAST = (ARITH == SEM_ARITH_FAST) && !REPLAY;
+    __shared__ double2 s_tab[kLogTabSize];
+    constexpr bool FAST = (ARITH == SEM_ARITH_FAST || ARITH == SEM_ARITH_FAST32) && !REPLAY;
+    constexpr bool BITS32 = FAST && ARITH == SEM_ARITH_FAST32;           // two events per Philox call
     if (FAST) load_logtab(s_tab);
     for (int i = threadIdx.x; i < P.T; i += blockDim.x) { s_obs[2 * i] = P.obs[3 * i + 1]; s_obs[2 * i + 1] = P.obs[3 * i + 2]; }
     __syncthreads();
@@ -146,6 +148,8 @@ __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
     long long slot = 0;
     double x[3] = {0, 0, 0}, t = 0, sI = 0, sR = 0;
     int day = 0;
+    uint32_t ev_k = 0;                                                   // event index of the trial (32-bit streams)
+    uint4 wq = make_uint4(0, 0, 0, 0);
     SirModel m;
     PairSource<REPLAY> src;
 
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
                 P.theta_out[2 * slot] = beta; P.theta_out[2 * slot + 1] = gamma;
                 const double th[2] = {beta, gamma};
                 m.setup(th, x);
-                t = 0; sI = 0; sR = 0; day = 0;
+                t = 0; sI = 0; sR = 0; day = 0; ev_k = 0;
                 record_day();                                             // row 0 = the perturbed start
                 have = true;
             }
@@ -195,13 +199,24 @@ __global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
             bool done = !(m.alive(x) && day < T);
             bool rejected = false, dry = false;
             if (!done) {
-                double r[2], u1, u2, tau; int j;
+                double r[2], u1 = 0.5, u2 = 0.5, tau; int j;
                 const double a0 = ssa_total<SirModel, FAST ? SEM_ARITH_FAST : SEM_ARITH_REFERENCE>(m, x, r);
-                if (!(a0 > 0)) done = true;
-                else if (!src.next(u1, u2)) { done = true; dry = true; }
+                bool drew = a0 > 0;
+                if constexpr (BITS32) {
+                    if (drew) {
+                        if (!(ev_k & 1)) wq = src.raw();
+                        u1 = word_to_d12((ev_k & 1) ? wq.z : wq.x); u2 = word_to_d12((ev_k & 1) ? wq.w : wq.y);   // in [1,2)
+                        ev_k++;
+                    }
+                } else if (drew) {
+                    drew = src.next(u1, u2);
+                    dry = !drew;
+                    if constexpr (FAST) { u1 += 1.0; u2 += 1.0; }         // u+1 exact (52-bit u)
+                }
+                if (!drew) done = true;
                 else {
                     my_events++;
-                    if constexpr (FAST) ssa_pick_fast<SirModel>(r, a0, u1 + 1.0, u2 + 1.0, s_tab, tau, j);   // u+1 exact (52-bit u)
+                    if constexpr (FAST) ssa_pick_fast<SirModel>(r, a0, u1, u2, s_tab, tau, j);
                     else ssa_pick_ref<SirModel>(r, a0, u1, u2, tau, j);
                     const double tn = __dadd_rn(t, tau);
                     if (tn > t_stop) done = true;
@@ -289,6 +304,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     const int blocks = (int)(want < cap ? want : cap);
     if (replay) abc_kernel<SEM_ARITH_REFERENCE, true><<<blocks, threads, 0, s>>>(P);
     else if (cfg->arith == SEM_ARITH_REFERENCE) abc_kernel<SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
+    else if (cfg->arith == SEM_ARITH_FAST32) abc_kernel<SEM_ARITH_FAST32, false><<<blocks, threads, 0, s>>>(P);
     else abc_kernel<SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);     // (UNIFORMIZED: the ABC loop needs event times)
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
@@ -315,7 +331,7 @@ __global__ void k_poisson(double mu, PhiloxKey key, uint32_t domain, uint32_t c2
 }
 
 __global__ void k_fast_math(const double *x, const double *a, double *nl, double *rc, long long cnt) {
-    __shared__ double2 s_tab[128];
+    __shared__ double2 s_tab[kLogTabSize];
     load_logtab(s_tab);
     __syncthreads();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;

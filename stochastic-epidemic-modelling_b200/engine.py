@@ -14,7 +14,7 @@ from . import _lib
 
 MODEL_NAMES = {"sir": 0, "seir": 1, "sir_subgroups": 2, "sir_subgroups2": 3}
 RESAMPLERS = {"multinomial": 0, "systematic": 1}
-ARITH = {"reference": 0, "fast": 1, "uniformized": 2}
+ARITH = {"reference": 0, "fast": 1, "uniformized": 2, "fast32": 3}
 
 
 def require_cuda(device=None):
@@ -83,7 +83,7 @@ class PfResult:
         return traj
 
 
-def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="fast",
+def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="fast32",
                    seed=0, filter_id0=0, mu=None, n_population=None, dt=1.0, store_history=True, block_particles=0,
                    launch_per_step=False):
     Cn, P, Cobs = model_dims(model, G)
@@ -159,7 +159,7 @@ def alloc_pf_outputs(cfg, device=None):
             torch.empty((L.sem_pf_workspace_bytes(C.byref(cfg)),), dtype=torch.uint8, device=dev))
 
 
-def simulate(model, x0, theta, max_time, G=1, arith="fast", seed=0, sim_index0=0, record_capacity=0, replay=None,
+def simulate(model, x0, theta, max_time, G=1, arith="fast32", seed=0, sim_index0=0, record_capacity=0, replay=None,
              n_sims=None, daily_rows=0, device=None):
     """Batch of independent SSA runs (sem_ssa_simulate).  x0 (n,C) or (C,), theta (n,P) or (P,).
     Returns dict(x (n,C) int32, n_rows (n,), times (n,cap), states (n,cap,C)) as device tensors."""
@@ -200,7 +200,7 @@ def simulate(model, x0, theta, max_time, G=1, arith="fast", seed=0, sim_index0=0
         return dict(x=x_out, n_rows=n_rows, times=times, states=states, _keep=[x0t, tht, ru, ro])
 
 
-def abc_trials(obs, n_trials, threshold, priors, seed=0, trial0=0, trial_ids=None, arith="fast", early_reject=False,
+def abc_trials(obs, n_trials, threshold, priors, seed=0, trial0=0, trial_ids=None, arith="fast32", early_reject=False,
                want_traj=False, replay=None, device=None):
     """Run n_trials ABC trials (sem_abc_run).  Returns dict(theta (n,2), distance (n,), traj (n,T,3)|None, n_events)."""
     L = _lib.load()

@@ -44,21 +44,21 @@ def _run_one(model, G, x0, theta, max_time, last_values_only, names, seed, arith
     return cond
 
 
-def sir_simulate(population, theta_proposal, max_time, last_values_only, *, seed=None, arith="fast", replay_u=None):
+def sir_simulate(population, theta_proposal, max_time, last_values_only, *, seed=None, arith="fast32", replay_u=None):
     """gillespie_algo.py:10-75.  population [S,I,R]; theta_proposal array [beta,gamma].
     Returns (S,I,R) at max_time, or the dict of event-by-event lists {"s","i","r","time"}."""
     r = _run_one(0, 1, population, theta_proposal, max_time, last_values_only, ["s", "i", "r"], seed, arith, replay_u)
     return tuple(r) if last_values_only else r
 
 
-def seir_simulate(population, theta_proposal, max_time, last_values_only, *, seed=None, arith="fast", replay_u=None):
+def seir_simulate(population, theta_proposal, max_time, last_values_only, *, seed=None, arith="fast32", replay_u=None):
     """gillespie_algo.py:78-146.  population [S,E,I,R]; theta_proposal [beta,alpha,gamma] (:92)."""
     r = _run_one(1, 1, population, theta_proposal, max_time, last_values_only, ["s", "e", "i", "r"], seed, arith, replay_u)
     return tuple(r) if last_values_only else r
 
 
 def sir_subgroups_simulate(population, betas_proposal, gamma_proposal, max_time, last_values_only, *, seed=None,
-                           arith="fast", replay_u=None):
+                           arith="fast32", replay_u=None):
     """gillespie_algo.py:148-233.  population (G,3); betas (G,G) with betas[a,b] = infector group a ->
     susceptible group b (:182-183).  Returns list of G [S,I,R] lists (:224-231) or the dict of lists keyed
     "s_g","i_g","r_g","time" (:169-174)."""
@@ -72,7 +72,7 @@ def sir_subgroups_simulate(population, betas_proposal, gamma_proposal, max_time,
     return r
 
 
-def simulate_batch(model, populations, thetas, max_time, *, n_groups=1, seed=None, arith="fast", n_sims=None):
+def simulate_batch(model, populations, thetas, max_time, *, n_groups=1, seed=None, arith="fast32", n_sims=None):
     """Many independent SSA runs at once: populations (n,C) or (C,), thetas (n,P) or (P,) -> (n,C) int32 CUDA
     tensor of final states.  model: 'sir' | 'seir' | 'sir_subgroups'."""
     seed = engine.new_seed() if seed is None else seed
@@ -81,7 +81,7 @@ def simulate_batch(model, populations, thetas, max_time, *, n_groups=1, seed=Non
     return out["x"]
 
 
-def predict_forward(model, thetas, last_states, horizon, *, n_groups=1, seed=None, arith="fast"):
+def predict_forward(model, thetas, last_states, horizon, *, n_groups=1, seed=None, arith="fast32"):
     """Forward-prediction fan-out of tests/pred_tmps.py:55-73: from every posterior sample's last
     state simulate `horizon` more days with its own theta; returns (n, horizon, C) int32 CUDA tensor whose row d is
     the state at integer time d+1 (the state the reference extracts as "last event with floor(time) == d",

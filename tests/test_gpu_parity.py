@@ -193,6 +193,9 @@ def _truth_Y(model, T, seed, probs, normal, dying=False, G=2):
         base = np.stack([900 - 40 * t, 10 * t, 20 + 15 * t, 15 * t], 1)       # E_0 = 0 (pmcmc.py:163)
     elif model == 2 and G == 3:
         base = np.stack([190 - 8 * t, 5 + 3 * t, 5 * t, 280 - 12 * t, 8 + 5 * t, 7 * t, 140 - 6 * t, 4 + 3 * t, 3 * t], 1)
+    elif model == 2 and G == 4:
+        base = np.stack([190 - 8 * t, 5 + 3 * t, 5 * t, 280 - 12 * t, 8 + 5 * t, 7 * t, 140 - 6 * t, 4 + 3 * t, 3 * t,
+                         240 - 9 * t, 6 + 4 * t, 5 * t], 1)
     elif model == 2:
         base = np.stack([400 - 20 * t, 15 + 8 * t, 12 * t, 600 - 30 * t, 20 + 12 * t, 18 * t], 1)
     elif model == 3:
@@ -217,6 +220,17 @@ PHILOX_CASES = [
     (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 0, 1, 32),
     (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1000, 7, True, .1, 1, 0, 0),
     (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 1, 0),
+    # 32-bit streams (arith 3, the production default): two events per Philox call, same fp64 arithmetic
+    (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 3, 0),
+    (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 0, 3, 96),
+    (0, 1, [0.5, 3.0], [300], [3], 777, 8, False, .5, 0, 3, 0),          # many extinctions
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, False, .1, 1, 3, 0),
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, True, .2, 0, 3, 128),
+    (2, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 1, 3, 0),
+    (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 0, 3, 32),
+    (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 3, 0),
+    (2, 4, [3, 1, .5, .2, .3, 2, 1, 1, .7, .2, 4, .8, .1, .6, .9, 2.5, .8], [200, 300, 150, 250], [5, 8, 4, 6], 500, 6, False, .2, 1, 3, 0),
+    (2, 4, [3, 1, .5, .2, .3, 2, 1, 1, .7, .2, 4, .8, .1, .6, .9, 2.5, .8], [200, 300, 150, 250], [5, 8, 4, 6], 500, 6, False, .2, 1, 1, 0),
     # uniformized intervals (arith 2): exact law without waiting times, bit-checked against the oracle's statement
     (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 2, 0),
     (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 0, 2, 96),
@@ -347,7 +361,7 @@ def test_abc_replay_vs_reference(sem):
     assert np.array_equal(tr[acc], g["trajectories"][:, :, 1:].astype(np.int32))
 
 
-@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("arith", [0, 1, 3])
 def test_abc_philox_vs_oracle(sem, c_oracle, arith):
     g = golden("abc_sir_small")
     obs = g["observed"]
@@ -373,7 +387,7 @@ def test_abc_algo_dropin(sem, c_oracle):
     assert sorted(post) == ["beta", "gamma"] and len(post["beta"]) == 5 and traj.shape == (5, obs.shape[0], 4)
     assert np.array_equal(traj[0, :, 0], np.arange(obs.shape[0]))
     # same accepted trials as the oracle's sequential acceptance over trial ids 0,1,2,...
-    ref = c_oracle.abc_trials(obs, 4096, 45.0, (0, 5, 0, 5), arith=1, seed=7, trial0=0)
+    ref = c_oracle.abc_trials(obs, 4096, 45.0, (0, 5, 0, 5), arith=3, seed=7, trial0=0)     # fast32 is the default
     acc = np.nonzero(ref["distance"] <= 45.0)[0][:5]
     assert np.array_equal(st["accepted_ids"], acc)
     assert np.array_equal(np.array(post["beta"]), ref["theta"][acc, 0])
@@ -434,12 +448,12 @@ def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta,
     assert out["collapsed"] == 0
     X = torch.cat([sh.X_hist for sh in out["shards"]], dim=2).permute(0, 2, 1).cpu().numpy()       # (T,N,C)
     A = torch.cat([sh.ancestry for sh in out["shards"]], dim=1).cpu().numpy()
-    ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=1, seed=4242, filter_id=5, mu=mu, npop=npop)
+    ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=3, seed=4242, filter_id=5, mu=mu, npop=npop)
     assert np.array_equal(A, ref["ancestry"])
     assert np.array_equal(X, ref["X_hist"])
     np.testing.assert_allclose(out["log_zetas"], ref["log_zetas"], rtol=1e-11)
     assert sum(sh.n_events for sh in out["shards"]) == ref["n_events"]
-    cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=1, seed=4242, filter_id0=5, mu=mu,
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=3, seed=4242, filter_id0=5, mu=mu,
                                     n_population=npop)
     one = sem.engine.run_pf(cfg, Y, np.array(theta, float))
     assert np.array_equal(one.X_hist[0].permute(0, 2, 1).cpu().numpy(), X)
@@ -456,7 +470,7 @@ def test_predict_forward_daily_states(sem, c_oracle):
     out = sem.gillespie_algo.predict_forward("sir", thetas, last, H, seed=17).cpu().numpy()
     assert out.shape == (n, H, 3)
     for i in range(0, n, 7):
-        ref = c_oracle.ssa(0, 1, last[i], thetas[i], float(H), arith=1, seed=17, sim_index=i, max_rec=4000)
+        ref = c_oracle.ssa(0, 1, last[i], thetas[i], float(H), arith=3, seed=17, sim_index=i, max_rec=4000)
         for d in range(1, H + 1):
             k = np.searchsorted(ref["times"], d, side="right") - 1          # last event with time <= d
             assert np.array_equal(out[i, d - 1], ref["states"][k].astype(np.int32)), (i, d)
@@ -582,12 +596,14 @@ def test_seir_hidden_exposed_column(sem, c_oracle):
     np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
     full = c_oracle.pf_run(1, Y, [4.0, 1.0, 1.0], False, .1, 1500, resampler=1, arith=1, seed=77, mu=[20], npop=[1000])
     assert o["log_zetas"][-1] > full["log_zetas"][-1]                  # dropping a column from the min can only raise the weights
-    z, H, A = sem.particle_filter(Yh, sem.ModelType.SEIR, np.array([4.0, 1.0, 1.0]), False, .1, 1500, 1000, 20, seed=77)
+    z, H, A = sem.particle_filter(Yh, sem.ModelType.SEIR, np.array([4.0, 1.0, 1.0]), False, .1, 1500, 1000, 20, seed=77, arith="fast")
     assert H.shape == (T, 1500, 4) and np.allclose(np.log(z), o["log_zetas"], rtol=1e-11)
 
 
 @pytest.mark.parametrize("model,G,theta,npop,mu,arith", [(0, 1, [2.0, 1.0], [1000], [20], 1), (0, 1, [2.0, 1.0], [1000], [20], 0),
-                                                          (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1)])
+                                                          (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1),
+                                                          (0, 1, [2.0, 1.0], [1000], [20], 3), (1, 1, [4.0, 1.0, 1.0], [1000], [20], 3),
+                                                          (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 3)])
 def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, npop, mu, arith):
     """The whole-filter cooperative kernel (grid.sync() as the resampling barrier) and the launch-per-step path are
     bit-identical, including a multi-filter batch and the two-row (ping-pong) history."""
