@@ -29,7 +29,7 @@ def main():
     out = sharded.run_distributed(Y, 0, np.array([2.0, 1.0]), N, probs=.1, seed=777, filter_id=2, mu=[20], n_population=[pop])
     assert out["collapsed"] == 0
     sh = out["shard"]
-    cfg = sem_b200.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=1, seed=777, filter_id0=2, mu=[20], n_population=[pop])
+    cfg = sem_b200.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=3, seed=777, filter_id0=2, mu=[20], n_population=[pop])
     one = sem_b200.engine.run_pf(cfg, Y, np.array([2.0, 1.0]))
     torch.cuda.synchronize()
     lo, cnt = sh.j0, sh.n_local
@@ -41,7 +41,7 @@ def main():
     assert int(ev) == int(one.n_events[0])
     if rank == 0:
         from oracle import c_oracle as co
-        ref = co.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=1, seed=777, filter_id=2, mu=[20], npop=[pop])
+        ref = co.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=3, seed=777, filter_id=2, mu=[20], npop=[pop])
         assert np.array_equal(one.ancestry[0].cpu().numpy(), ref["ancestry"])
         print(f"sharded filter over {world} GPUs == single GPU == oracle: OK  logZ={out['log_zetas'][-1]:.6f}")
     # ABC across ranks
@@ -50,7 +50,7 @@ def main():
     post, traj = sem_b200.abc_algo.abc_algo(obs, 6, 45.0, {"beta": [0, 5], "gamma": [0, 5]}, seed=11, batch=8192, stats=st)
     if rank == 0:
         from oracle import c_oracle as co
-        ref = co.abc_trials(obs, st["trials"], 45.0, (0, 5, 0, 5), arith=1, seed=11, trial0=0, want_traj=False)
+        ref = co.abc_trials(obs, st["trials"], 45.0, (0, 5, 0, 5), arith=3, seed=11, trial0=0, want_traj=False)
         acc = np.nonzero(ref["distance"] <= 45.0)[0][:6]
         assert np.array_equal(st["accepted_ids"], acc) and np.array_equal(np.array(post["beta"]), ref["theta"][acc, 0])
         print(f"ABC sharded over {world} GPUs: accepted ids {list(acc)} OK")
