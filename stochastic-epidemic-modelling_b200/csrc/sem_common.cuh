@@ -19,18 +19,26 @@ namespace sem {
 enum : uint32_t { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7, DOM_AUX = 8 };
 
 // ------------------------------------------------------------------------------------------ Philox4x32-10
-struct PhiloxKey { uint32_t k0, k1; };
+// The key travels as its expanded round-key schedule (rk[2r] = k0 + r*W0, rk[2r+1] = k1 + r*W1), filled on the host:
+// as part of a kernel parameter it sits in the constant bank, where LOP3 reads it as a direct operand -- no
+// registers and no per-call key arithmetic (the Weyl additions cost 18 integer adds per call otherwise).
+struct PhiloxKey { uint32_t rk[20]; };
 
-__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, PhiloxKey key) {
-    uint32_t k0 = key.k0, k1 = key.k1;
+__host__ __device__ inline PhiloxKey make_philox_key(uint32_t k0, uint32_t k1) {
+    PhiloxKey key;
+    for (int r = 0; r < 10; r++) { key.rk[2 * r] = k0 + (uint32_t)r * 0x9E3779B9u; key.rk[2 * r + 1] = k1 + (uint32_t)r * 0xBB67AE85u; }
+    return key;
+}
+__host__ __device__ inline PhiloxKey make_philox_key(uint64_t seed) { return make_philox_key((uint32_t)seed, (uint32_t)(seed >> 32)); }
+
+__device__ __forceinline__ uint4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key) {
 #pragma unroll
     for (int r = 0; r < 10; r++) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;     // IMAD.WIDE.U32
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0; // LOP3
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ key.rk[2 * r];     // LOP3 with a constant-bank operand
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ key.rk[2 * r + 1];
         c1 = (uint32_t)p1; c3 = (uint32_t)p0; c0 = n0; c2 = n2;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     return make_uint4(c0, c1, c2, c3);
 }
@@ -53,9 +61,9 @@ struct PairSource;
 
 template <>
 struct PairSource<false> {
-    PhiloxKey key; uint32_t k, c1, c2, c3;
-    __device__ __forceinline__ void init(PhiloxKey key_, uint32_t c1_, uint32_t c2_, uint32_t c3_) { key = key_; k = 0; c1 = c1_; c2 = c2_; c3 = c3_; }
-    __device__ __forceinline__ uint4 raw() { return philox4x32_10(k++, c1, c2, c3, key); }
+    const PhiloxKey *key; uint32_t k, c1, c2, c3;         // key points into the kernel parameters (constant bank)
+    __device__ __forceinline__ void init(const PhiloxKey &key_, uint32_t c1_, uint32_t c2_, uint32_t c3_) { key = &key_; k = 0; c1 = c1_; c2 = c2_; c3 = c3_; }
+    __device__ __forceinline__ uint4 raw() { return philox4x32_10(k++, c1, c2, c3, *key); }
     __device__ __forceinline__ bool next(double &u1, double &u2) {
         const uint4 w = raw();
         u1 = bits_to_d12(w.x, w.y) - 1.0; u2 = bits_to_d12(w.z, w.w) - 1.0;
@@ -612,7 +620,7 @@ __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double m
     }
     else if constexpr (ARITH == SEM_ARITH_FAST32 && !REPLAY) return ssa_run_spec<Model, SpecBlock<Model>::bits32, true, TRACK_R>(m, x, max_time, src, tab, rec);
     else if constexpr (ARITH == SEM_ARITH_UNIFORMIZED && !REPLAY) {
-        PairSource<false> aux; aux.init(src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
+        PairSource<false> aux; aux.init(*src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
         return ssa_run_unif<Model, TRACK_R>(m, x, max_time, src, aux, tab);
     }
     else return ssa_run_ref<Model, REPLAY>(m, x, max_time, src, rec);

@@ -521,7 +521,7 @@ __global__ void i32_to_f64_kernel(const int32_t *in, size_t n, double *out) {
 
 // particle_path_sampler (pmcmc.py:236-248): one thread chases the genealogy backwards.
 __global__ void path_sample_kernel(const int32_t *X, const int32_t *A, int T, int N, int C, int chosen, int exact,
-                                   PhiloxKey key, uint32_t fid, int32_t *traj) {
+                                   const PhiloxKey key, uint32_t fid, int32_t *traj) {
     if (blockIdx.x || threadIdx.x) return;
     if (chosen < 0) {                                          // np.random.randint(0, N) (pmcmc.py:241)
         const uint4 w = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, fid), key);
@@ -643,7 +643,7 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
     P.ntheta = model_ntheta(cfg->model, G); P.init_poisson = buf->X0 == nullptr;
     P.pfx_in_smem = w.nb <= 4096;                           // 32 KB of dynamic shared memory at most
     P.probs = cfg->probs; P.dt = cfg->dt;
-    P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32); P.filter_id0 = cfg->filter_id0;
+    P.key = make_philox_key(cfg->seed); P.filter_id0 = cfg->filter_id0;
     for (int g = 0; g < SEM_MAX_GROUPS; g++) { P.mu[g] = cfg->mu[g]; P.npop[g] = cfg->n_population[g]; }
     P.Y = buf->Y; P.theta = buf->theta; P.X0 = buf->X0;
     P.res_u = buf->replay_resample_u; P.ssa_u = buf->replay_ssa_u; P.ssa_off = (const long long *)buf->replay_ssa_off;
@@ -806,7 +806,7 @@ int sem_debug_phases(unsigned long long *host_out) {
 int sem_path_sample(const int32_t *X_hist, const int32_t *ancestry, int32_t T, int32_t N, int32_t C, int32_t chosen,
                     int32_t exact, uint64_t seed, uint32_t filter_id, int32_t *traj, void *stream) {
     if (!X_hist || !ancestry || !traj || T < 1 || N < 1 || chosen >= N) { set_error("bad path_sample args"); return SEM_ERR_INVALID; }
-    PhiloxKey key{(uint32_t)seed, (uint32_t)(seed >> 32)};
+    const PhiloxKey key = make_philox_key(seed);
     path_sample_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(X_hist, ancestry, T, N, C, chosen, exact, key, filter_id, traj);
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;

@@ -258,7 +258,7 @@ int sem_ssa_simulate(const sem_sim_config *cfg, const int32_t *x0, const double 
     SimDev P;
     P.n_sims = cfg->n_sims; P.shared_theta = cfg->shared_theta; P.shared_x0 = cfg->shared_x0;
     P.ntheta = model_ntheta(cfg->model, G); P.cap = cfg->record_capacity; P.max_time = cfg->max_time; P.daily = cfg->daily_rows;
-    P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32); P.sim0 = cfg->sim_index0;
+    P.key = make_philox_key(cfg->seed); P.sim0 = cfg->sim_index0;
     P.x0 = x0; P.theta = theta; P.replay_u = replay_u; P.replay_off = (const long long *)replay_off;
     P.x_out = x_out; P.states = states; P.n_rows = (long long *)n_rows; P.times = times;
     const bool replay = replay_u != nullptr;
@@ -290,7 +290,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     P.T = cfg->n_days; P.early_reject = cfg->early_reject; P.n_trials = cfg->n_trials; P.trial0 = cfg->trial0;
     P.threshold = cfg->threshold;
     for (int i = 0; i < 4; i++) P.prior[i] = cfg->prior[i];
-    P.key.k0 = (uint32_t)cfg->seed; P.key.k1 = (uint32_t)(cfg->seed >> 32);
+    P.key = make_philox_key(cfg->seed);
     P.obs = obs; P.trial_ids = (const unsigned long long *)trial_ids; P.theta_in = theta_in; P.replay_u = replay_u;
     P.n_start_in = (const long long *)n_start_in; P.replay_off = (const long long *)replay_off;
     P.theta_out = theta_out; P.distance = distance; P.traj = traj;
@@ -313,7 +313,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------ test hooks
-__global__ void k_philox(uint4 c, PhiloxKey k, uint32_t *out) {
+__global__ void k_philox(uint4 c, const PhiloxKey k, uint32_t *out) {
     const uint4 w = philox4x32_10(c.x, c.y, c.z, c.w, k);
     out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
 }
@@ -325,7 +325,7 @@ __global__ void k_norm(const double *y, const double *x, const double *pr, doubl
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < cnt) out[i] = norm_logpdf(y[i], x[i], pr[i]);
 }
-__global__ void k_poisson(double mu, PhiloxKey key, uint32_t domain, uint32_t c2, double *out, long long cnt) {
+__global__ void k_poisson(double mu, const PhiloxKey key, uint32_t domain, uint32_t c2, double *out, long long cnt) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < cnt) { PairSource<false> s; s.init(key, (uint32_t)i, c2, stream_word(domain, 0)); out[i] = poisson_draw(s, mu); }
 }
@@ -356,7 +356,7 @@ extern "C" {
 int sem_test_philox(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t *d = nullptr;
     SEM_CUDA(cudaMalloc(&d, 16));
-    k_philox<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), PhiloxKey{key[0], key[1]}, d);
+    k_philox<<<1, 1>>>(make_uint4(ctr[0], ctr[1], ctr[2], ctr[3]), make_philox_key(key[0], key[1]), d);
     cudaError_t e = cudaMemcpy(out, d, 16, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { set_error("philox test: %s", cudaGetErrorString(e)); return SEM_ERR_CUDA; }
@@ -382,7 +382,7 @@ int sem_test_fast_math(const double *x, const double *a, double *neglog_out, dou
 int sem_test_poisson(double mu, uint64_t seed, uint32_t domain, uint32_t c2, double *out, int64_t count) {
     double *d = nullptr;
     SEM_CUDA(cudaMalloc(&d, (size_t)count * 8));
-    k_poisson<<<(unsigned)((count + 127) / 128), 128>>>(mu, PhiloxKey{(uint32_t)seed, (uint32_t)(seed >> 32)}, domain, c2, d, count);
+    k_poisson<<<(unsigned)((count + 127) / 128), 128>>>(mu, make_philox_key(seed), domain, c2, d, count);
     cudaError_t e = cudaMemcpy(out, d, count * 8, cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) { set_error("poisson test: %s", cudaGetErrorString(e)); return SEM_ERR_CUDA; }

@@ -16,7 +16,7 @@ using namespace sem;
 // variant 0: one event per iteration (ssa_run_fast); 1,2: speculative blocks of 2,4 events, 52-bit uniforms;
 // 3,4,5: blocks of 2,4,6 events with 32-bit uniforms (one Philox call per two events)
 template <int V>
-__global__ void __launch_bounds__(768) k_loop(const double *theta, const int32_t *X0, int n, double dt, uint64_t seed, int32_t *Xout,
+__global__ void __launch_bounds__(768) k_loop(const double *theta, const int32_t *X0, int n, double dt, const PhiloxKey key, int32_t *Xout,
                                               unsigned long long *events, int reps) {
     __shared__ double2 s_tab[kLogTabSize];
     load_logtab(s_tab);
@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(768) k_loop(const double *theta, const int32_t
         SirModel m;
         m.setup(theta, x);
         PairSource<false> src;
-        src.init(PhiloxKey{(uint32_t)seed, (uint32_t)(seed >> 32)}, (uint32_t)j, (uint32_t)rep, stream_word(DOM_SSA, 0));
+        src.init(key, (uint32_t)j, (uint32_t)rep, stream_word(DOM_SSA, 0));
         long long pairs;
         if constexpr (V == 0) pairs = ssa_run_fast<SirModel, false>(m, x, dt, src, s_tab, NoRec());
         else if constexpr (V == 1) pairs = ssa_run_spec<SirModel, 2, false, false>(m, x, dt, src, s_tab, NoRec());
@@ -58,7 +58,7 @@ static void run(int warps_per_smsp, const double *d_theta, const int32_t *d_X0, 
     for (int it = 0; it < 4; it++) {
         cudaMemset(d_ev, 0, 8);
         cudaEventRecord(a);
-        k_loop<V><<<blocks, threads>>>(d_theta, d_X0, n, 1.0, 1234, d_out, d_ev, reps);
+        k_loop<V><<<blocks, threads>>>(d_theta, d_X0, n, 1.0, make_philox_key(1234ull), d_out, d_ev, reps);
         cudaEventRecord(b);
         cudaEventSynchronize(b);
         float ms;
