@@ -156,26 +156,57 @@ __device__ __forceinline__ double bd0(double x, double np) {
     return x * log(x / np) + np - x;
 }
 
+// Division-free, libm-free variants for the observation weights (every particle, every step): quotients through the
+// Newton reciprocal, logarithms through the shared-memory table.  Each agrees with the IEEE / libm statement above to a
+// few ulp; the weights agree with scipy / Boost to ~1e-12 (tests/test_gpu_parity.py::test_weights_vs_scipy_golden).
+__device__ __forceinline__ double log_tab(double x, const double2 *tab) { return -neg_log_fast(x, tab); }   // x > 0, normal
+
+__device__ __forceinline__ double stirlerr_w(double n) {
+    const double S0 = 1.0 / 12, S1 = 1.0 / 360, S2 = 1.0 / 1260, S3 = 1.0 / 1680, S4 = 1.0 / 1188;
+    if (n < 16) return kSfe[(int)n];
+    const double inv = rcp_nr(n), i2 = inv * inv;
+    if (n > 500) return (S0 - S1 * i2) * inv;
+    if (n > 80) return (S0 - (S1 - S2 * i2) * i2) * inv;
+    if (n > 35) return (S0 - (S1 - (S2 - S3 * i2) * i2) * i2) * inv;
+    return (S0 - (S1 - (S2 - (S3 - S4 * i2) * i2) * i2) * i2) * inv;
+}
+
+__device__ __forceinline__ double bd0_w(double x, double np, const double2 *tab) {
+    const double d = x - np, s = x + np;
+    if (fabs(d) < 0.1 * s) {
+        const double v = d * rcp_nr(s), v2 = v * v;
+        double q = 1.0 / 17;
+        q = q * v2 + 1.0 / 15; q = q * v2 + 1.0 / 13; q = q * v2 + 1.0 / 11; q = q * v2 + 1.0 / 9;
+        q = q * v2 + 1.0 / 7; q = q * v2 + 1.0 / 5; q = q * v2 + 1.0 / 3;
+        return d * v + (2 * x * v) * (v2 * q);
+    }
+    return x * log_tab(x * rcp_nr(np), tab) + np - x;
+}
+
 // log binom.pmf(k | n, p) with scipy's support rules (pmcmc.py:179): k<0, k>n, non-integer k -> -inf
-static __device__ __noinline__ double binom_logpmf(double k, double n, double p) {
+static __device__ __noinline__ double binom_logpmf(double k, double n, double p, const double2 *tab) {
     if (!(k >= 0) || k > n || k != floor(k)) return -CUDART_INF;
     const double q = 1 - p;
     if (p == 0) return k == 0 ? 0.0 : -CUDART_INF;
     if (q == 0) return k == n ? 0.0 : -CUDART_INF;
     if (k == 0) {
         if (n == 0) return 0.0;
-        return p < 0.1 ? -bd0(n, n * q) - n * p : n * log(q);
+        return p < 0.1 ? -bd0_w(n, n * q, tab) - n * p : n * log(q);
     }
-    if (k == n) return q < 0.1 ? -bd0(n, n * p) - n * q : n * log(p);
-    const double lc = stirlerr(n) - stirlerr(k) - stirlerr(n - k) - bd0(k, n * p) - bd0(n - k, n * q);
-    const double lf = 1.8378770664093453 + log(k) + log1p(-k / n);
+    if (k == n) return q < 0.1 ? -bd0_w(n, n * p, tab) - n * q : n * log(p);
+    const double nk = n - k;
+    const double lc = stirlerr_w(n) - stirlerr_w(k) - stirlerr_w(nk) - bd0_w(k, n * p, tab) - bd0_w(nk, n * q, tab);
+    // 0.5 log(2 pi k (n-k)/n): log k + log1p(-k/n), the second as the log of the exactly known ratio (n-k)/n
+    const double lf = 1.8378770664093453 + log_tab(k, tab) + log_tab(nk * rcp_nr(n), tab);
     return lc - 0.5 * lf;
 }
 
 // log norm.pdf(y | loc = x, scale = probs*x + 1e-4)  (pmcmc.py:181)
-__device__ __forceinline__ double norm_logpdf(double y, double x, double probs) {
-    const double sd = probs * x + .0001, z = (y - x) / sd;
-    return -0.5 * z * z - log(sd) - 0.9189385332046727;
+__device__ __forceinline__ double norm_logpdf(double y, double x, double probs, const double2 *tab) {
+    const double sd = probs * x + .0001;
+    if (!(sd > 0)) { const double z = (y - x) / sd; return -0.5 * z * z - log(sd) - 0.9189385332046727; }   // scipy's nan / inf rules
+    const double z = (y - x) * rcp_nr(sd);
+    return -0.5 * z * z - log_tab(sd, tab) - 0.9189385332046727;
 }
 
 __device__ __forceinline__ double log_factorial(double k) {

@@ -77,7 +77,7 @@ __device__ __forceinline__ double block_incl_scan(double v, double *sm, int tid,
 }
 
 template <class Model>
-__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow) {
+__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double2 *tab) {
     double lw = CUDART_INF;
 #pragma unroll
     for (int c = 0; c < Model::C; c++) {
@@ -90,7 +90,7 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
             }
             const double y = Yrow[c];
             if (y != y) continue;                            // extension: a NaN entry of Y marks an unobserved column
-            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf(y, xc, P.probs) : norm_logpdf(y, xc, P.probs);
+            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf(y, xc, P.probs, tab) : norm_logpdf(y, xc, P.probs, tab);
             lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
         }
     }
@@ -100,11 +100,12 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
 // Weigh the CTA's particles against Y[p] and CTA-local scan: writes L[par] and the CTA partial (m_b, s_b).
 template <class Model>
 __device__ __forceinline__ void weigh_local(const PfDev &P, const int p, const int f, const int b, const int tid,
-                                            const bool active, const int j, const double *x, double *sm) {
+                                            const bool active, const int j, const double *x, double *sm,
+                                            const double2 *tab) {
     const int N = P.N, par = p & 1;
     double lw = -CUDART_INF;
     if (active) {
-        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs);
+        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, tab);
         if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in the combine
     }
     const int nwarps = (blockDim.x + 31) >> 5;
@@ -147,21 +148,9 @@ __device__ __forceinline__ void combine_partials(const PfDev &P, const int f, co
 template <class Model>
 __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p, const int f, const int b, const int tid,
                                                     const bool active, const int j, const double *x, double *sm,
-                                                    bool *is_last) {
+                                                    const double2 *tab, bool *is_last) {
     const int N = P.N, par = p & 1;
-    // ------------------------------------------------------------------------ weigh against Y[p] (pmcmc.py:178-181)
-    double lw = -CUDART_INF;
-    if (active) {
-        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs);
-        if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in finalize
-    }
-    const int nwarps = (blockDim.x + 31) >> 5;
-    const double mb = block_max(lw, sm, tid, nwarps);
-    const double e = (active && mb > -CUDART_INF && mb < CUDART_INF) ? exp(lw - mb) : 0.0;
-    double sb;
-    const double incl = block_incl_scan(e, sm, tid, nwarps, &sb);
-    if (active) P.L[par][(size_t)f * N + j] = incl;
-    if (tid == 0) P.part[((size_t)par * P.n_filters + f) * P.nb + b] = make_double2(mb, sb);
+    weigh_local<Model>(P, p, f, b, tid, active, j, x, sm, tab);          // weigh against Y[p] (pmcmc.py:178-181) + CTA scan
 
     // ------------------------------------------------------------------------ last CTA finalizes the step
     __threadfence();
@@ -170,26 +159,9 @@ __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p,
     __syncthreads();
     if (!*is_last) return;
     __threadfence();
-    const double2 *part = P.part + ((size_t)par * P.n_filters + f) * P.nb;
-    double M = -CUDART_INF;
-    for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
-    M = block_max(M, sm, tid, nwarps);
-    double carry = 0.0;
-    double *pfx = P.pfx[par] + (size_t)f * P.nb, *scale = P.scale[par] + (size_t)f * P.nb;
+    double M, carry;
+    combine_partials(P, f, par, tid, sm, P.pfx[par] + (size_t)f * P.nb, P.scale[par] + (size_t)f * P.nb, M, carry);
     const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
-    for (int i0 = 0; i0 < P.nb; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        double sc = 0.0, val = 0.0;
-        if (i < P.nb && finiteM) {
-            const double mi = __ldcg(&part[i].x), si = __ldcg(&part[i].y);
-            sc = (mi > -CUDART_INF) ? exp(mi - M) : 0.0;
-            val = sc * si;
-        }
-        double chunk;
-        const double incl2 = block_incl_scan(val, sm, tid, nwarps, &chunk);
-        if (i < P.nb) { pfx[i] = carry + (incl2 - val); scale[i] = sc; }
-        carry += chunk;
-    }
     if (tid == 0) {
         P.total[par][f] = carry;
         if (P.sharded) {                                     // the host combines the shards' (M, total) summaries
@@ -210,13 +182,15 @@ __device__ __forceinline__ void weigh_scan_finalize(const PfDev &P, const int p,
 
 // Step 0: X_0 (pmcmc.py:156-170), given or I_0 ~ Poisson(mu), then weigh against Y[0].
 template <class Model>
-__global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
+__global__ void __launch_bounds__(kMaxThreads) pf_init(const __grid_constant__ PfDev P) {
     __shared__ double sm[32];
+    __shared__ double2 s_tab[kLogTabSize];
     __shared__ bool is_last;
     const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
     const int N = P.N, j = b * P.ppb + tid;
     const bool active = tid < P.ppb && j < N;
     const uint32_t fid = P.filter_id0 + f;
+    load_logtab(s_tab);                                      // the weights' logarithms (made visible by the barriers of the scan)
     double x[Model::C];
     if (active) {
         if (!P.init_poisson) {
@@ -239,7 +213,8 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const PfDev P) {
 #pragma unroll
         for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
     }
-    if (P.T > 1) weigh_scan_finalize<Model>(P, 0, f, b, tid, active, j, x, sm, &is_last);
+    __syncthreads();                                         // s_tab complete
+    if (P.T > 1) weigh_scan_finalize<Model>(P, 0, f, b, tid, active, j, x, sm, s_tab, &is_last);
 }
 
 // Ancestor of slot j at step p (pmcmc.py:187-193): first particle whose cdf exceeds u_j * total, by a two-level
@@ -280,7 +255,7 @@ __device__ unsigned long long g_phase[8 * 256];
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
 // waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
 template <class Model, int ARITH>
-__global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
+__global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_constant__ PfDev P) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double s_dyn[];                        // pfx[nb], scale[nb] of the previous step
@@ -294,7 +269,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
     const uint32_t fid = P.filter_id0 + f;
     int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
-    if (ARITH != SEM_ARITH_REFERENCE) load_logtab(s_tab);
+    load_logtab(s_tab);
     if (tid == 0) s_pairs = 0ull;
     __syncthreads();
     double x[Model::C];
@@ -319,7 +294,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
 #pragma unroll
         for (int c = 0; c < Model::C; c++) Xf[(size_t)c * N + j] = (int32_t)x[c];
     }
-    if (P.T > 1) weigh_local<Model>(P, 0, f, b, tid, active, j, x, sm);
+    if (P.T > 1) weigh_local<Model>(P, 0, f, b, tid, active, j, x, sm, s_tab);
     bool dead = false;
     double lz = 0.0;
     unsigned long long my_pairs = 0;
@@ -366,7 +341,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
         PHASE(3);
         __syncthreads();                                     // keep the CTA in the SSA loop until its last warp is done: letting early
         PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
-        if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm);
+        if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm, s_tab);
         PHASE(5);
     }
     if (P.n_events) {                                        // one global atomic per CTA for the whole filter
@@ -381,7 +356,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const PfDev P) {
 // Step p >= 1: resample, gather, propagate, store, weigh (see the file header).
 template <class Model, int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(ARITH == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads)
-__maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, const int p) {
+__maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const __grid_constant__ PfDev P, const int p) {
     extern __shared__ double s_pfx[];                        // previous step's CTA prefixes (when they fit)
     __shared__ double sm[32];
     __shared__ double2 s_tab[kLogTabSize];
@@ -394,7 +369,7 @@ __maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, con
     const int par = p & 1;
     const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
     const double *pfx_g = P.pfx[par ^ 1] + (size_t)f * P.nb;
-    if (ARITH != SEM_ARITH_REFERENCE && !REPLAY) load_logtab(s_tab);
+    load_logtab(s_tab);
     if (P.pfx_in_smem && !P.sharded) for (int i = tid; i < P.nb; i += blockDim.x) s_pfx[i] = pfx_g[i];
     if (tid == 0) s_pairs = 0ull;
     __syncthreads();
@@ -450,7 +425,7 @@ __maxnreg__(ARITH == SEM_ARITH_UNIFORMIZED ? 88 : 80) pf_step(const PfDev P, con
         if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
     }
     if (p >= P.T - 1) return;                                // the final state is never weighed
-    weigh_scan_finalize<Model>(P, p, f, b, tid, active, j, x, sm, &is_last);
+    weigh_scan_finalize<Model>(P, p, f, b, tid, active, j, x, sm, s_tab, &is_last);
 }
 
 // ---------------------------------------------------------------------------------------------- sharded filter
@@ -521,7 +496,7 @@ __global__ void i32_to_f64_kernel(const int32_t *in, size_t n, double *out) {
 
 // particle_path_sampler (pmcmc.py:236-248): one thread chases the genealogy backwards.
 __global__ void path_sample_kernel(const int32_t *X, const int32_t *A, int T, int N, int C, int chosen, int exact,
-                                   const PhiloxKey key, uint32_t fid, int32_t *traj) {
+                                   const __grid_constant__ PhiloxKey key, uint32_t fid, int32_t *traj) {
     if (blockIdx.x || threadIdx.x) return;
     if (chosen < 0) {                                          // np.random.randint(0, N) (pmcmc.py:241)
         const uint4 w = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, fid), key);

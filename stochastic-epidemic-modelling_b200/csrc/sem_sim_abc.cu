@@ -62,7 +62,7 @@ template <int C>
 struct EventLogRef { EventLog<C> *l; __device__ __forceinline__ void operator()(double t, const double *x) const { (*l)(t, x); } };
 
 template <class Model, int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(128) sim_kernel(const SimDev P) {
+__global__ void __launch_bounds__(128) sim_kernel(const __grid_constant__ SimDev P) {
     __shared__ double2 s_tab[kLogTabSize];
     if (ARITH != SEM_ARITH_REFERENCE && !REPLAY) load_logtab(s_tab);
     __syncthreads();
@@ -130,7 +130,7 @@ struct AbcDev {
 constexpr int kAbcMaxDays = 128;
 
 template <int ARITH, bool REPLAY>
-__global__ void __launch_bounds__(128) abc_kernel(const AbcDev P) {
+__global__ void __launch_bounds__(128) abc_kernel(const __grid_constant__ AbcDev P) {
     __shared__ double s_obs[kAbcMaxDays * 2];                            // (I_obs, R_obs) per day
     __shared__ double2 s_tab[kLogTabSize];
     constexpr bool FAST = (ARITH == SEM_ARITH_FAST || ARITH == SEM_ARITH_FAST32) && !REPLAY;
@@ -313,19 +313,25 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------ test hooks
-__global__ void k_philox(uint4 c, const PhiloxKey k, uint32_t *out) {
+__global__ void k_philox(uint4 c, const __grid_constant__ PhiloxKey k, uint32_t *out) {
     const uint4 w = philox4x32_10(c.x, c.y, c.z, c.w, k);
     out[0] = w.x; out[1] = w.y; out[2] = w.z; out[3] = w.w;
 }
 __global__ void k_binom(const double *k, const double *n, const double *p, double *out, long long cnt) {
+    __shared__ double2 s_tab[kLogTabSize];
+    load_logtab(s_tab);
+    __syncthreads();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < cnt) out[i] = binom_logpmf(k[i], n[i], p[i]);
+    if (i < cnt) out[i] = binom_logpmf(k[i], n[i], p[i], s_tab);
 }
 __global__ void k_norm(const double *y, const double *x, const double *pr, double *out, long long cnt) {
+    __shared__ double2 s_tab[kLogTabSize];
+    load_logtab(s_tab);
+    __syncthreads();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < cnt) out[i] = norm_logpdf(y[i], x[i], pr[i]);
+    if (i < cnt) out[i] = norm_logpdf(y[i], x[i], pr[i], s_tab);
 }
-__global__ void k_poisson(double mu, const PhiloxKey key, uint32_t domain, uint32_t c2, double *out, long long cnt) {
+__global__ void k_poisson(double mu, const __grid_constant__ PhiloxKey key, uint32_t domain, uint32_t c2, double *out, long long cnt) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i < cnt) { PairSource<false> s; s.init(key, (uint32_t)i, c2, stream_word(domain, 0)); out[i] = poisson_draw(s, mu); }
 }
