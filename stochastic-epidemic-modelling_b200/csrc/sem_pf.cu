@@ -53,14 +53,14 @@ struct PfDev {
 constexpr int kMaxThreads = 768;
 constexpr int kMaxThreadsUnif = 352;      // the uniformized step keeps more live state: two 352-thread CTAs per SM, <= 93 registers
 
+// CTA-wide max / inclusive scan: warp shuffles, one shared-memory slot per warp, and a second shuffle pass over the
+// (at most 32) warp results done redundantly by every warp -- no serial loop over the warps.
 __device__ __forceinline__ double block_max(double v, double *sm, int tid, int nwarps) {
     v = warp_max_d(v);
     __syncthreads();
     if ((tid & 31) == 0) sm[tid >> 5] = v;
     __syncthreads();
-    double r = sm[0];
-    for (int w = 1; w < nwarps; w++) r = fmax(r, sm[w]);
-    return r;
+    return warp_max_d((tid & 31) < nwarps ? sm[tid & 31] : -CUDART_INF);
 }
 
 // inclusive scan over the CTA; returns this thread's inclusive value, *total = CTA sum
@@ -70,10 +70,10 @@ __device__ __forceinline__ double block_incl_scan(double v, double *sm, int tid,
     __syncthreads();
     if (lane == 31) sm[w] = v;
     __syncthreads();
-    double off = 0.0, tot = 0.0;
-    for (int i = 0; i < nwarps; i++) { const double s = sm[i]; if (i < w) off += s; tot += s; }
-    *total = tot;
-    return v + off;
+    const double ws = warp_incl_scan_d(lane < nwarps ? sm[lane] : 0.0, lane);   // inclusive scan of the warp totals
+    *total = __shfl_sync(0xffffffffu, ws, nwarps - 1);
+    const double off = __shfl_sync(0xffffffffu, ws, w > 0 ? w - 1 : 0);
+    return w > 0 ? v + off : v;
 }
 
 template <class Model>
@@ -123,6 +123,18 @@ __device__ __forceinline__ void combine_partials(const PfDev &P, const int f, co
                                                  double *pfx_out, double *scale_out, double &M_out, double &total_out) {
     const int nwarps = (blockDim.x + 31) >> 5;
     const double2 *part = P.part + ((size_t)par * P.n_filters + f) * P.nb;
+    if (P.nb <= (int)blockDim.x) {                           // one partial per thread: a single L2 round trip
+        double2 ps = make_double2(-CUDART_INF, 0.0);
+        if (tid < P.nb) ps = __ldcg(&part[tid]);
+        const double M = block_max(ps.x, sm, tid, nwarps);
+        const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
+        const double sc = (tid < P.nb && finiteM && ps.x > -CUDART_INF) ? exp(ps.x - M) : 0.0, val = sc * ps.y;
+        double tot;
+        const double incl = block_incl_scan(val, sm, tid, nwarps, &tot);
+        if (tid < P.nb) { pfx_out[tid] = 0.0 + (incl - val); scale_out[tid] = sc; }
+        M_out = M; total_out = 0.0 + tot;
+        return;
+    }
     double M = -CUDART_INF;
     for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
     M = block_max(M, sm, tid, nwarps);
@@ -246,7 +258,7 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
 
 #ifdef SEM_PHASES
 __device__ unsigned long long g_phase[8 * 256];
-#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { unsigned long long t_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)); g_phase[p * 8 + (k)] = t_; } } while (0)
+#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 8 + (k)] = (unsigned long long)clock64(); } } while (0)
 #else
 #define PHASE(k)
 #endif
@@ -324,6 +336,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         long long pairs = 0;
         if (active) {
             const int a = select_ancestor<false>(P, p, f, j, fid, s_pfx, s_scale, total);
+            PHASE(6);
             Af[(size_t)row * N + j] = a;
             const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
 #pragma unroll
@@ -332,6 +345,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
             m.setup(P.theta + (size_t)f * P.ntheta, x);
             PairSource<false> src;
             src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
+            PHASE(7);
             pairs = ssa_run<Model, ARITH, false, false>(m, x, P.dt, src, s_tab, NoRec());
             int32_t *Xr = Xf + (size_t)row * Model::C * N;
 #pragma unroll
@@ -339,7 +353,9 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         }
         my_pairs += (unsigned long long)pairs;
         PHASE(3);
+#ifndef SEM_NO_SSA_BARRIER
         __syncthreads();                                     // keep the CTA in the SSA loop until its last warp is done: letting early
+#endif
         PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
         if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm, s_tab);
         PHASE(5);

@@ -24,12 +24,16 @@ torch.cuda.synchronize()
 buf = np.zeros(8 * 256, dtype=np.uint64)
 assert L.sem_debug_phases(buf.ctypes.data_as(C.c_void_p)) == 0
 ph = buf.reshape(256, 8)[1:101].astype(np.int64)
-names = ["grid.sync", "combine", "search+SSA (own warp)", "wait CTA", "weigh+scan"]
-d = np.diff(ph[:, :6], axis=1) / 1e3
+# slots: 0 before grid.sync, 1 after, 2 after combine, 6 after ancestor search, 7 after gather+setup, 3 after SSA+store (own warp),
+# 4 after the CTA barrier, 5 after weigh+scan.  SM cycle counter of CTA 0's SM (1.965 GHz).
+order = [0, 1, 2, 6, 7, 3, 4, 5]
+names = ["grid.sync", "combine", "ancestor search", "gather+setup", "SSA+store (warp 0)", "wait CTA", "weigh+scan"]
+t = ph[:, order] / 1965.0
+d = np.diff(t, axis=1)
 print("per-step mean us (CTA 0, thread 0):")
 for k, nm in enumerate(names):
     print(f"  {nm:24s} mean {d[:, k].mean():8.2f}  min {d[:, k].min():8.2f}  max {d[:, k].max():8.2f}")
-step = (ph[1:, 0] - ph[:-1, 0]) / 1e3
+step = (t[1:, 0] - t[:-1, 0])
 print("  step-to-step            mean %.2f  total %.2f ms" % (step.mean(), step.sum() / 1e3))
 for p in (1, 10, 28, 60, 95):
     print("  step", p + 1, np.round(d[p], 2))
