@@ -32,9 +32,16 @@ if ROOT not in sys.path:
 
 import workloads  # noqa: E402
 
-I_ALG = 128            # declared thread-instructions per SSA event, SIR fp64; see DESIGN.md
+# Thread-instructions per SSA event (SIR, fp64), the per-unit figure of the issue roofline.  SURVEY 8(d) declared a
+# budget of 128 "to be replaced by ncu smsp__inst_executed / events once the kernel exists"; these are the measured
+# values: smsp__inst_executed.sum x thread_inst_per_inst / n_events over the whole-filter kernel
+# (profiles/r01b_pf_persistent_fast32.txt: 4.4516e9 x 26.71 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
+I_ALG_BY_ARITH = {"fast32": 74.4, "fast": 106.0}
+I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
 LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
+# dram__bytes_read.sum + dram__bytes_write.sum of one whole-filter launch (ncu --set full, same profile)
+DRAM_TRAFFIC_PER_PASS = {"fast32": 312.32e3 + 112.229888e6}
 
 
 def measured_peaks():
@@ -312,15 +319,25 @@ def main():
         per_gpu_ms = dev_ms / K
         events_per_s = events_last / (per_gpu_ms / 1e3)
         issue_peak = LANES * f_sm
-        roofline = {"bound": "issue", "kernel": "pf_step<SirModel>", "achieved": events_per_s * I_ALG / 1e9,
-                    "peak": issue_peak / 1e9, "unit": "Gthread-inst/s", "frac": events_per_s * I_ALG / issue_peak,
-                    "traffic": None, "events_per_s": events_per_s, "events_per_particle_step": events_last / (N * (T - 1)),
-                    "I_alg": I_ALG, "sm_mhz_used": f_sm / 1e6, "avg_launch_us": 1e3 * per_gpu_ms / T,
+        i_alg = I_ALG_BY_ARITH.get(args.arith, I_ALG_DECLARED)
+        launches = res.launches
+        traffic = DRAM_TRAFFIC_PER_PASS.get(args.arith) if (N == workloads.HEADLINE["n_particles"] and launches == 1) else None
+        roofline = {"bound": "issue", "kernel": ("pf_persistent" if launches == 1 else "pf_step") + f"<SirModel, {args.arith}>",
+                    "achieved": events_per_s * i_alg / 1e9, "peak": issue_peak / 1e9, "unit": "Gthread-inst/s",
+                    "frac": events_per_s * i_alg / issue_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                    "events_per_s": events_per_s,
+                    "events_per_particle_step": events_last / (N * (T - 1)), "I_alg": i_alg,
+                    "I_alg_source": "ncu: executed thread-instructions per SSA event over the whole-filter kernel (profiles/)",
+                    "frac_with_declared_I_alg_128": events_per_s * I_ALG_DECLARED / issue_peak,
+                    "sm_mhz_used": f_sm / 1e6, "launches_per_pass": launches, "avg_launch_us": 1e3 * per_gpu_ms / launches,
                     "note": "SSA propagate is bound by SM instruction issue, not HBM (SURVEY 8(d)); peak = 148 SMs x 4 "
-                            "schedulers x 32 lanes x SM clock sampled during the run"}
-        hbm_ach = N * B_ALG / (per_gpu_ms / 1e3 / T) / 1e9
+                            "schedulers x 32 lanes x SM clock sampled during the run; sm_100a issues the IMAD.WIDE of "
+                            "Philox once per ~4 cycles, so the reachable fraction for this mix is ~0.65 (DESIGN.md)"}
+        hbm_ach = N * (T - 1) * B_ALG / (per_gpu_ms / 1e3) / 1e9
         roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
-                        "traffic": None, "peak_source": how, "bytes_per_launch": N * B_ALG}
+                        "traffic": traffic, "peak_source": how, "bytes_per_launch": N * (T - 1) * B_ALG / launches,
+                        "note": "algorithmic bytes 8C+24 per particle-step; measured DRAM traffic is lower because the "
+                                "step's working set (4.8 MB) stays in the 126 MB L2"}
         line = {
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
