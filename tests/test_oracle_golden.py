@@ -184,3 +184,38 @@ def test_oracle_philox_logz_distribution_vs_reference(c_oracle):
         se = np.sqrt(ref.var() / ref.size + z.var() / z.size)
         assert abs(z.mean() - ref.mean()) < 4 * se, (arith, z.mean(), ref.mean(), se)      # unbiased for the same Z
         assert stats.ks_2samp(np.log(z), np.log(ref)).pvalue > 1e-3, arith             # same N, multinomial => same law
+
+
+def test_fast32_stream_layout(c_oracle):
+    """arith 3 (fast32): event k of a simulation takes words (2(k&1), 2(k&1)+1) of Philox call k>>1 as 32-bit uniforms
+    u = w / 2^32; everything else is the FAST arithmetic.  Restated here in plain Python from the raw Philox words."""
+    import math
+    seed, sim = 0xFEEDFACE12345, 7
+    x0, theta, tmax = [480.0, 20.0, 0.0], [2.0, 1.0], 0.75
+    out = c_oracle.ssa(0, 1, x0, theta, tmax, arith=3, seed=seed, sim_index=sim, max_rec=4000)
+    key = [seed & 0xFFFFFFFF, seed >> 32]
+    S, I, R = x0
+    N = S + I + R
+    bN = theta[0] * (1.0 / N)
+    t, k, times, states = 0.0, 0, [0.0], [[S, I, R]]
+    while I > 0:
+        w = c_oracle.philox4x32([k >> 1, sim, 0, (7 << 24)], key)          # DOM_SIM = 7, filter id 0
+        u1, u2 = w[2 * (k & 1)] / 2.0**32, w[2 * (k & 1) + 1] / 2.0**32
+        k += 1
+        r0, r1 = bN * S * I, theta[1] * I
+        a0 = r0 + r1
+        tau = -math.log(1.0 - u1) / a0
+        if t + tau > tmax:
+            break
+        t += tau
+        if r0 <= u2 * a0:
+            I -= 1; R += 1
+        else:
+            S -= 1; I += 1
+        times.append(t); states.append([S, I, R])
+    assert out["pairs"] == k and out["n_rec"] == len(times)
+    assert np.array_equal(out["states"], np.array(states))
+    np.testing.assert_allclose(out["times"], times, rtol=1e-15)
+    # and the 52-bit stream of arith 1 is a different stream over the same law: one call per event
+    out52 = c_oracle.ssa(0, 1, x0, theta, tmax, arith=1, seed=seed, sim_index=sim, max_rec=4000)
+    assert out52["pairs"] != out["pairs"] or not np.array_equal(out52["states"], out["states"])
