@@ -466,10 +466,49 @@ __device__ __forceinline__ long long ssa_run_fast(const Model &m, double *x, dou
 // BITS32 (SEM_ARITH_FAST32): event k takes words (2(k&1), 2(k&1)+1) of Philox call k>>1 -- u1 and u2 carry 32 random
 // bits each, one call serves two events.  The 32x32->64 multiplies of Philox are the most expensive instructions of
 // the loop on sm_100a (IMAD.WIDE issues once per ~4 cycles, tools/micro/pipes2.cu), so this halves its largest cost.
+// One speculative block: from state xs[0] at time t, the states xs[1..U] after each of the next U events (whether or
+// not they fit in the interval), their firing times tn[0..U) (non-decreasing; NaN from the first event whose total
+// propensity is not positive) and the propensities a0[0..U).  Event i fires iff tn[i] <= max_time.
+template <class Model, int U, bool BITS32, bool TRACK_R>
+__device__ __forceinline__ void ssa_block(const Model &m, double (&xs)[U + 1][Model::C], const double t, PairSource<false> &src,
+                                          const double2 *tab, double (&tn)[U], double (&a0)[U]) {
+    static_assert(!BITS32 || U % 2 == 0, "32-bit streams serve two events per call");
+    double d1[U], d2[U];
+    if constexpr (BITS32) {
+#pragma unroll
+        for (int i = 0; i < U; i += 2) {
+            const uint4 w = src.raw();
+            d1[i] = word_to_d12(w.x); d2[i] = word_to_d12(w.y); d1[i + 1] = word_to_d12(w.z); d2[i + 1] = word_to_d12(w.w);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < U; i++) { const uint4 w = src.raw(); d1[i] = bits_to_d12(w.x, w.y); d2[i] = bits_to_d12(w.z, w.w); }
+    }
+#pragma unroll
+    for (int i = 0; i < U; i++) {                                          // state chain (speculative)
+        double r[Model::R];
+        a0[i] = ssa_total<Model, SEM_ARITH_FAST>(m, xs[i], r);
+        const double v = __fma_rn(d2[i], a0[i], -a0[i]);
+        double acc = r[0];
+        int j = (acc <= v) ? 1 : 0;
+#pragma unroll
+        for (int k = 1; k < Model::R - 1; k++) { acc = __dadd_rn(acc, r[k]); j += (acc <= v) ? 1 : 0; }
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) xs[i + 1][c] = xs[i][c];
+        m.template apply<TRACK_R>(xs[i + 1], j);
+    }
+    double tt = t;
+#pragma unroll
+    for (int i = 0; i < U; i++) {                                          // waiting times (feed-forward, independent)
+        const double E = neg_log_fast(__dsub_rn(2.0, d1[i]), tab);
+        tt = __dadd_rn(tt, __dmul_rn(E, rcp_nr(a0[i])));
+        tn[i] = tt;
+    }
+}
+
 template <class Model, int U, bool BITS32, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run_spec(const Model &m, double *x, double max_time, PairSource<false> &src,
                                                   const double2 *tab, Rec rec) {
-    static_assert(!BITS32 || U % 2 == 0, "32-bit streams serve two events per call");
     if (!m.alive(x)) { if (!TRACK_R) m.fix_removed(x); return 0; }
     double t = 0.0;
     int pairs = 0;
@@ -478,40 +517,11 @@ __device__ __forceinline__ long long ssa_run_spec(const Model &m, double *x, dou
 #pragma unroll
     for (int c = 0; c < Model::C; c++) xs[0][c] = x[c];
     for (;;) {
-        double d1[U], d2[U], a0[U], tn[U];
-        if constexpr (BITS32) {
-#pragma unroll
-            for (int i = 0; i < U; i += 2) {
-                const uint4 w = loc.raw();
-                d1[i] = word_to_d12(w.x); d2[i] = word_to_d12(w.y); d1[i + 1] = word_to_d12(w.z); d2[i + 1] = word_to_d12(w.w);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < U; i++) { const uint4 w = loc.raw(); d1[i] = bits_to_d12(w.x, w.y); d2[i] = bits_to_d12(w.z, w.w); }
-        }
-#pragma unroll
-        for (int i = 0; i < U; i++) {                                      // state chain (speculative)
-            double r[Model::R];
-            a0[i] = ssa_total<Model, SEM_ARITH_FAST>(m, xs[i], r);
-            const double v = __fma_rn(d2[i], a0[i], -a0[i]);
-            double acc = r[0];
-            int j = (acc <= v) ? 1 : 0;
-#pragma unroll
-            for (int k = 1; k < Model::R - 1; k++) { acc = __dadd_rn(acc, r[k]); j += (acc <= v) ? 1 : 0; }
-#pragma unroll
-            for (int c = 0; c < Model::C; c++) xs[i + 1][c] = xs[i][c];
-            m.template apply<TRACK_R>(xs[i + 1], j);
-        }
-        double tt = t;
-#pragma unroll
-        for (int i = 0; i < U; i++) {                                      // waiting times (feed-forward, independent)
-            const double E = neg_log_fast(__dsub_rn(2.0, d1[i]), tab);
-            tt = __dadd_rn(tt, __dmul_rn(E, rcp_nr(a0[i])));
-            tn[i] = tt;
-        }
+        double a0[U], tn[U];
+        ssa_block<Model, U, BITS32, TRACK_R>(m, xs, t, loc, tab, tn, a0);
         if (tn[U - 1] <= max_time) {                                       // all U events fired (gillespie_algo.py:65)
             pairs += U;
-            t = tt;
+            t = tn[U - 1];
 #pragma unroll
             for (int i = 0; i < U; i++) rec(tn[i], xs[i + 1]);
 #pragma unroll

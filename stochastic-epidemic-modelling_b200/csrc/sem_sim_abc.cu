@@ -148,8 +148,6 @@ __global__ void __launch_bounds__(128) abc_kernel(const __grid_constant__ AbcDev
     long long slot = 0;
     double x[3] = {0, 0, 0}, t = 0, sI = 0, sR = 0;
     int day = 0;
-    uint32_t ev_k = 0;                                                   // event index of the trial (32-bit streams)
-    uint4 wq = make_uint4(0, 0, 0, 0);
     SirModel m;
     PairSource<REPLAY> src;
 
@@ -188,36 +186,71 @@ __global__ void __launch_bounds__(128) abc_kernel(const __grid_constant__ AbcDev
                 P.theta_out[2 * slot] = beta; P.theta_out[2 * slot + 1] = gamma;
                 const double th[2] = {beta, gamma};
                 m.setup(th, x);
-                t = 0; sI = 0; sR = 0; day = 0; ev_k = 0;
+                t = 0; sI = 0; sR = 0; day = 0;
                 record_day();                                             // row 0 = the perturbed start
                 have = true;
             }
         }
         if (__all_sync(0xffffffffu, exhausted && !have)) break;
-        if (have) {
+        if constexpr (FAST) {
+            // ------------------------------------------------------------ one speculative block of events (ssa_block):
+            // the events that fit before t_stop fire in order; a day boundary strictly before an event's time keeps the
+            // pre-event state (abc_algo.py:58-84)
+            if (have) {
+                constexpr int U = BITS32 ? 4 : 2;
+                bool done = !(m.alive(x) && day < T);
+                bool rejected = false;
+                if (!done) {
+                    double xs[U + 1][3], tn[U], a0[U];
+#pragma unroll
+                    for (int c = 0; c < 3; c++) xs[0][c] = x[c];
+                    ssa_block<SirModel, U, BITS32, true>(m, xs, t, src, s_tab, tn, a0);
+                    int nf = 0;
+#pragma unroll
+                    for (int i = 0; i < U; i++) {
+                        if (tn[i] <= t_stop) {                            // times are non-decreasing, NaN once a0 <= 0
+                            nf++;
+                            t = tn[i];
+                            while (day < T && (double)day < t) {
+#pragma unroll
+                                for (int c = 0; c < 3; c++) x[c] = xs[i][c];
+                                record_day();
+                            }
+                        }
+                    }
+                    double a_stop = a0[0];
+#pragma unroll
+                    for (int i = 1; i < U; i++) a_stop = (nf == i) ? a0[i] : a_stop;
+#pragma unroll
+                    for (int c = 0; c < 3; c++) {
+                        double v = xs[0][c];
+#pragma unroll
+                        for (int i = 1; i <= U; i++) v = (nf == i) ? xs[i][c] : v;
+                        x[c] = v;
+                    }
+                    my_events += (unsigned long long)(nf + ((nf < U && a_stop > 0) ? 1 : 0));
+                    if (nf < U) done = true;                              // overshoot of t_stop, extinction or a0 = 0
+                    else if (P.early_reject && sI + sR > reject_at) { done = true; rejected = true; }
+                }
+                if (done) {
+                    if (!rejected) while (day < T) record_day();          // forward fill (abc_algo.py:85-91)
+                    P.distance[slot] = rejected ? CUDART_INF : (sI / T + sR / T) / 2;   // distance_function (abc_algo.py:10-13)
+                    have = false;
+                }
+            }
+        } else if (have) {
             // ------------------------------------------------------------ one SSA event (gillespie_algo.py:48-70)
             bool done = !(m.alive(x) && day < T);
             bool rejected = false, dry = false;
             if (!done) {
                 double r[2], u1 = 0.5, u2 = 0.5, tau; int j;
-                const double a0 = ssa_total<SirModel, FAST ? SEM_ARITH_FAST : SEM_ARITH_REFERENCE>(m, x, r);
+                const double a0 = ssa_total<SirModel, SEM_ARITH_REFERENCE>(m, x, r);
                 bool drew = a0 > 0;
-                if constexpr (BITS32) {
-                    if (drew) {
-                        if (!(ev_k & 1)) wq = src.raw();
-                        u1 = word_to_d12((ev_k & 1) ? wq.z : wq.x); u2 = word_to_d12((ev_k & 1) ? wq.w : wq.y);   // in [1,2)
-                        ev_k++;
-                    }
-                } else if (drew) {
-                    drew = src.next(u1, u2);
-                    dry = !drew;
-                    if constexpr (FAST) { u1 += 1.0; u2 += 1.0; }         // u+1 exact (52-bit u)
-                }
+                if (drew) { drew = src.next(u1, u2); dry = !drew; }
                 if (!drew) done = true;
                 else {
                     my_events++;
-                    if constexpr (FAST) ssa_pick_fast<SirModel>(r, a0, u1, u2, s_tab, tau, j);
-                    else ssa_pick_ref<SirModel>(r, a0, u1, u2, tau, j);
+                    ssa_pick_ref<SirModel>(r, a0, u1, u2, tau, j);
                     const double tn = __dadd_rn(t, tau);
                     if (tn > t_stop) done = true;
                     else {
@@ -299,13 +332,17 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     SEM_CUDA(cudaMemsetAsync(work_counter, 0, sizeof(uint64_t), s));
     if (n_events) SEM_CUDA(cudaMemsetAsync(n_events, 0, sizeof(uint64_t), s));
     const int threads = 128;
-    long long want = (cfg->n_trials + threads - 1) / threads;
-    const long long cap = (long long)sm_count() * 8;                      // persistent: 8 CTAs of 4 warps per SM
+    const void *fn = replay ? (const void *)abc_kernel<SEM_ARITH_REFERENCE, true>
+                     : cfg->arith == SEM_ARITH_REFERENCE ? (const void *)abc_kernel<SEM_ARITH_REFERENCE, false>
+                     : cfg->arith == SEM_ARITH_FAST32 ? (const void *)abc_kernel<SEM_ARITH_FAST32, false>
+                                                      : (const void *)abc_kernel<SEM_ARITH_FAST, false>;   // (UNIFORMIZED: the ABC loop needs event times)
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    const long long want = (cfg->n_trials + threads - 1) / threads;
+    const long long cap = (long long)sm_count() * per_sm;                // persistent lanes: every CTA resident, no second wave
     const int blocks = (int)(want < cap ? want : cap);
-    if (replay) abc_kernel<SEM_ARITH_REFERENCE, true><<<blocks, threads, 0, s>>>(P);
-    else if (cfg->arith == SEM_ARITH_REFERENCE) abc_kernel<SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
-    else if (cfg->arith == SEM_ARITH_FAST32) abc_kernel<SEM_ARITH_FAST32, false><<<blocks, threads, 0, s>>>(P);
-    else abc_kernel<SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);     // (UNIFORMIZED: the ABC loop needs event times)
+    void *args[] = {(void *)&P};
+    SEM_CUDA(cudaLaunchKernel(fn, dim3(blocks), dim3(threads), args, 0, s));
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }
