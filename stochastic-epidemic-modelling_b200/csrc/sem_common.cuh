@@ -201,6 +201,46 @@ static __device__ __noinline__ double binom_logpmf(double k, double n, double p,
     return lc - 0.5 * lf;
 }
 
+// The filter's hot form of the same function: the observed count k (one per column and step) is shared by all
+// particles, so its terms are prepared once (BinomObs), and the common case 1 <= k < n, 0 < p < 1 runs straight-line:
+// 4 Newton reciprocals, two 5-term Stirling tails, two bd0 (series near the mode) and one table logarithm.  Everything
+// else (k = 0, k = n, k > n, non-integer k, p in {0,1}) goes to the general function above.
+struct BinomObs { double k, sk, lk; bool regular; };
+
+static __device__ const double kSfeG[16] = {0.0, 0.08106146679532726, 0.04134069595540929, 0.02767792568499834,
+    0.02079067210376509, 0.01664469118982119, 0.01387612882307075, 0.01189670994589177,
+    0.01041126526197209, 0.009255462182712733, 0.008330563433362871, 0.007573675487951841,
+    0.006942840107209530, 0.006408994188004207, 0.005951370112758848, 0.005554733551962801};
+
+// stirlerr(n) from inv = 1/n: the full 5-term tail for every n >= 16 (the extra terms of the shorter forms used for
+// large n are below 1e-17), the exact table below 16
+__device__ __forceinline__ double stirlerr_inv(double n, double inv) {
+    const double S0 = 1.0 / 12, S1 = 1.0 / 360, S2 = 1.0 / 1260, S3 = 1.0 / 1680, S4 = 1.0 / 1188;
+    const double i2 = inv * inv;
+    const double tail = (S0 - (S1 - (S2 - (S3 - S4 * i2) * i2) * i2) * i2) * inv;
+    return n < 16 ? kSfeG[(int)n] : tail;
+}
+
+__device__ __forceinline__ BinomObs binom_obs(double k, const double2 *tab) {
+    BinomObs o;
+    o.k = k;
+    o.regular = (k >= 1.0) && (k == floor(k)) && (k < 4.0e15);
+    const double kk = o.regular ? k : 1.0;
+    o.sk = stirlerr_inv(kk, rcp_nr(kk));
+    o.lk = log_tab(kk, tab);
+    return o;
+}
+
+__device__ __forceinline__ double binom_logpmf_obs(const BinomObs &o, double n, double p, const double2 *tab) {
+    const double q = 1 - p;
+    if (!(o.regular && n > o.k && p > 0 && q > 0)) return binom_logpmf(o.k, n, p, tab);
+    const double k = o.k, nk = n - k;
+    const double rn = rcp_nr(n), rnk = rcp_nr(nk);
+    const double lc = stirlerr_inv(n, rn) - o.sk - stirlerr_inv(nk, rnk) - bd0_w(k, n * p, tab) - bd0_w(nk, n * q, tab);
+    const double lf = 1.8378770664093453 + o.lk + log_tab(nk * rn, tab);
+    return lc - 0.5 * lf;
+}
+
 // log norm.pdf(y | loc = x, scale = probs*x + 1e-4)  (pmcmc.py:181)
 __device__ __forceinline__ double norm_logpdf(double y, double x, double probs, const double2 *tab) {
     const double sd = probs * x + .0001;

@@ -90,12 +90,20 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
             }
             const double y = Yrow[c];
             if (y != y) continue;                            // extension: a NaN entry of Y marks an unobserved column
-            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf(y, xc, P.probs, tab) : norm_logpdf(y, xc, P.probs, tab);
+            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf_obs(binom_obs(y, tab), xc, P.probs, tab)
+                                                              : norm_logpdf(y, xc, P.probs, tab);
             lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
         }
     }
     return lw == CUDART_INF ? 0.0 : lw;                      // nothing observed at this time: weight 1
 }
+
+#ifdef SEM_PHASES
+__device__ unsigned long long g_phase[16 * 256];
+#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 16 + (k)] = (unsigned long long)clock64(); } } while (0)
+#else
+#define PHASE(k)
+#endif
 
 // Weigh the CTA's particles against Y[p] and CTA-local scan: writes L[par] and the CTA partial (m_b, s_b).
 template <class Model>
@@ -108,11 +116,14 @@ __device__ __forceinline__ void weigh_local(const PfDev &P, const int p, const i
         lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, tab);
         if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in the combine
     }
+    PHASE(8);
     const int nwarps = (blockDim.x + 31) >> 5;
     const double mb = block_max(lw, sm, tid, nwarps);
+    PHASE(9);
     const double e = (active && mb > -CUDART_INF && mb < CUDART_INF) ? exp(lw - mb) : 0.0;
     double sb;
     const double incl = block_incl_scan(e, sm, tid, nwarps, &sb);
+    PHASE(10);
     if (active) P.L[par][(size_t)f * N + j] = incl;
     if (tid == 0) P.part[((size_t)par * P.n_filters + f) * P.nb + b] = make_double2(mb, sb);
 }
@@ -255,13 +266,6 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
     while (a < e) { const int mid = (a + e) >> 1; if (__fma_rn(sc, __ldcg(&L[mid]), pf) <= v) a = mid + 1; else e = mid; }
     return base + min(a, len - 1);
 }
-
-#ifdef SEM_PHASES
-__device__ unsigned long long g_phase[8 * 256];
-#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 8 + (k)] = (unsigned long long)clock64(); } } while (0)
-#else
-#define PHASE(k)
-#endif
 
 // Whole filter in ONE cooperative launch (one CTA per SM, all co-resident): the resampling barrier of every step is
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
@@ -789,7 +793,7 @@ int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, con
 
 #ifdef SEM_PHASES
 int sem_debug_phases(unsigned long long *host_out) {
-    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 8 * 256));
+    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 16 * 256));
     return SEM_OK;
 }
 #endif

@@ -359,7 +359,7 @@ __global__ void k_binom(const double *k, const double *n, const double *p, doubl
     load_logtab(s_tab);
     __syncthreads();
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (i < cnt) out[i] = binom_logpmf(k[i], n[i], p[i], s_tab);
+    if (i < cnt) out[i] = binom_logpmf_obs(binom_obs(k[i], s_tab), n[i], p[i], s_tab);      // the filter's entry point
 }
 __global__ void k_norm(const double *y, const double *x, const double *pr, double *out, long long cnt) {
     __shared__ double2 s_tab[kLogTabSize];

@@ -21,13 +21,14 @@ out = engine.alloc_pf_outputs(cfg)
 for _ in range(3):
     engine.run_pf(cfg, Y, np.array([.4, .2]), out=out)
 torch.cuda.synchronize()
-buf = np.zeros(8 * 256, dtype=np.uint64)
+buf = np.zeros(16 * 256, dtype=np.uint64)
 assert L.sem_debug_phases(buf.ctypes.data_as(C.c_void_p)) == 0
-ph = buf.reshape(256, 8)[1:101].astype(np.int64)
+ph = buf.reshape(256, 16)[1:100].astype(np.int64)
 # slots: 0 before grid.sync, 1 after, 2 after combine, 6 after ancestor search, 7 after gather+setup, 3 after SSA+store (own warp),
-# 4 after the CTA barrier, 5 after weigh+scan.  SM cycle counter of CTA 0's SM (1.965 GHz).
-order = [0, 1, 2, 6, 7, 3, 4, 5]
-names = ["grid.sync", "combine", "ancestor search", "gather+setup", "SSA+store (warp 0)", "wait CTA", "weigh+scan"]
+# 4 after the CTA barrier, 8 after the thread's log-weight, 9 after the CTA max, 10 after exp + CTA scan, 5 after the stores.  SM cycle counter of CTA 0's SM (1.965 GHz).
+order = [0, 1, 2, 6, 7, 3, 4, 8, 9, 10, 5]
+names = ["grid.sync", "combine", "ancestor search", "gather+setup", "SSA+store (warp 0)", "wait CTA", "weights (warp 0)", "CTA max", "exp + CTA scan",
+         "store L, partial"]
 t = ph[:, order] / 1965.0
 d = np.diff(t, axis=1)
 print("per-step mean us (CTA 0, thread 0):")
