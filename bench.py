@@ -188,6 +188,57 @@ def run_abc(args):
         dist.destroy_process_group()
 
 
+def run_sharded(args):
+    """Extra measurement (not the driver's headline): ONE filter sharded over all ranks (BASELINE config 5 shape:
+    2-subgroup SIR, group-summed binomial observations, global systematic resampling, particle migration by
+    all-to-all-v).  Weak scaling: N_global = ranks x --particles (default 1e5); population scaled to --population
+    (default 1e5: config 5's 1e6 would take ~10 s per pass).  Wall clock with device syncs, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from sem_b200 import sharded
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev, init_method=None if "MASTER_ADDR" in os.environ else "tcp://127.0.0.1:29533",
+                            rank=rank, world_size=world)
+    pop = args.population
+    npop = [int(.4 * pop), pop - int(.4 * pop)]
+    mu = [max(1, npop[0] // 66), max(1, npop[1] // 75)]
+    theta = np.array([5, 2, 1, 3, .5])
+    T = 15
+    y0 = [(npop[0] - mu[0], mu[0], 0), (npop[1] - mu[1], mu[1], 0)]
+    truth = workloads.subgroups_truth(y0, T, theta[:4].reshape(2, 2), theta[4]).reshape(T, 2, 3).sum(1)
+    Y = workloads.observe_binomial(truth, .1, seed=0)
+    n_local = args.particles or 100_000
+    n_global = n_local * world
+    K, W = args.steps, max(min(args.warmup, 3), 1)
+    times, events = [], 0
+    for i in range(W + K):
+        torch.cuda.synchronize(); dist.barrier()
+        t0 = time.perf_counter()
+        out = sharded.run_distributed(Y, 3, theta, n_global, G=2, probs=.1, seed=4242, filter_id=i, mu=mu, n_population=npop,
+                                      arith=args.arith, store_history=False)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert out["collapsed"] == 0, "sharded filter collapsed"
+        if i >= W:
+            times.append(float(dt.cpu()[0]))
+            ev = torch.tensor([out["shard"].n_events], dtype=torch.int64, device=dev)
+            dist.all_reduce(ev)
+            events = int(ev.cpu()[0])
+    if rank == 0:
+        s_pass = sum(times) / K
+        print(json.dumps({"metric": "particle-steps/s", "value": n_global * (T - 1) / s_pass, "unit": "particle-steps/s", "n_gpus": world,
+                          "steps": K, "warmup": W, "ms_per_step": 1e3 * s_pass, "higher_is_better": True, "scaling": "weak", "dtype": "f64",
+                          "data": "synthetic",
+                          "config": {"workload": f"sharded_pf_sub2_pop{pop}_Nlocal{n_local}_T15", "n_global": n_global, "arith": args.arith,
+                                     "exchange": "all_gather(2 doubles/rank) + all_to_all_v(int32 records) per step, host-planned"},
+                          "events_per_s": events / s_pass, "events_per_particle_step": events / (n_global * (T - 1)),
+                          "log_likelihood": float(out["log_zetas"][-1])}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -200,8 +251,10 @@ def main():
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="pf", choices=["pf", "abc"],
-                    help="pf = the BASELINE metric workload (default); abc = ABC rejection trials (config 2), extra measurement")
+    ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded"],
+                    help="pf = the BASELINE metric workload (default); abc = ABC rejection trials (config 2); sharded = one "
+                         "particle-sharded filter over all ranks (config 5 shape); the last two are extra measurements")
+    ap.add_argument("--population", type=int, default=100_000, help="total population of the sharded workload")
     ap.add_argument("--trials", type=int, default=1 << 20, help="ABC trials per step per GPU")
     ap.add_argument("--early-reject", action="store_true")
     args = ap.parse_args()
@@ -209,6 +262,8 @@ def main():
         return run_reference_arm(args)
     if args.workload == "abc":
         return run_abc(args)
+    if args.workload == "sharded":
+        return run_sharded(args)
 
     import torch
     import torch.distributed as dist
