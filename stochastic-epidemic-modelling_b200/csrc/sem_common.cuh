@@ -591,6 +591,76 @@ __device__ __forceinline__ long long ssa_run_spec(const Model &m, double *x, dou
     return pairs;
 }
 
+// events per speculative block of the production loops (measured, tools/micro/ssa_loop.cu): 4 with 32-bit uniforms
+// (two Philox calls in flight), 2 with 52-bit uniforms (4 spills under the 80-register cap); models with many
+// compartments keep fewer speculative states in registers (0 = the one-event-per-iteration loop)
+template <class Model> struct SpecBlock { static constexpr int bits32 = Model::C <= 4 ? 4 : 2, bits52 = Model::C <= 6 ? 2 : 0; };
+
+// The same loop in two legs, for a particle whose interval is shared by two warps (pf_persistent's scheduler
+// balancing): it runs from time t (0 on the first leg) until the interval ends (finished = true) or -- at a block
+// boundary -- until t >= handoff, and returns the continuation (state, t, stream counter).  The blocks stay aligned to
+// the same stream counters as in ssa_run_spec, so two legs reproduce the single run bit for bit.
+template <class Model, int U, bool BITS32>
+__device__ __forceinline__ long long ssa_run_spec_leg(const Model &m, double *x, double &t, const double handoff, const double max_time,
+                                                      PairSource<false> &src, const double2 *tab, bool &finished) {
+    finished = true;
+    if (!m.alive(x)) { m.fix_removed(x); return 0; }
+    int pairs = 0;
+    PairSource<false> loc = src;
+    double xs[U + 1][Model::C];
+#pragma unroll
+    for (int c = 0; c < Model::C; c++) xs[0][c] = x[c];
+    for (;;) {
+        double a0[U], tn[U];
+        ssa_block<Model, U, BITS32, false>(m, xs, t, loc, tab, tn, a0);
+        if (tn[U - 1] <= max_time) {
+            pairs += U;
+            t = tn[U - 1];
+#pragma unroll
+            for (int c = 0; c < Model::C; c++) xs[0][c] = xs[U][c];
+            if (t >= handoff) {                                            // pass the particle on
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) x[c] = xs[0][c];
+                finished = false;
+                break;
+            }
+            continue;
+        }
+        int nf = 0;
+#pragma unroll
+        for (int i = 0; i < U; i++) nf += (tn[i] <= max_time) ? 1 : 0;
+        double a_stop = a0[0];
+#pragma unroll
+        for (int i = 1; i < U; i++) a_stop = (nf == i) ? a0[i] : a_stop;
+#pragma unroll
+        for (int c = 0; c < Model::C; c++) {
+            double v = xs[0][c];
+#pragma unroll
+            for (int i = 1; i < U; i++) v = (nf == i) ? xs[i][c] : v;
+            x[c] = v;
+        }
+        pairs += nf + ((a_stop > 0) ? 1 : 0);
+        break;
+    }
+    src.k = loc.k;
+    m.fix_removed(x);                                                      // keeps S + I + R = N for the next leg's setup
+    return pairs;
+}
+
+// out-of-line entry (keeps the legs' registers out of the callers' main loop)
+template <class Model, int U, bool BITS32>
+__device__ __noinline__ long long ssa_run_spec_leg_call(const Model &m, double *x, double &t, const double handoff, const double max_time,
+                                                        PairSource<false> &src, const double2 *tab, bool &finished) {
+    return ssa_run_spec_leg<Model, U, BITS32>(m, x, t, handoff, max_time, src, tab, finished);
+}
+
+template <class Model, int ARITH>
+struct LegLoop {                                                           // which (block size, stream width) ssa_run<ARITH> uses
+    static constexpr bool available = (ARITH == SEM_ARITH_FAST32) || (ARITH == SEM_ARITH_FAST && SpecBlock<Model>::bits52 > 0);
+    static constexpr bool bits32 = ARITH == SEM_ARITH_FAST32;
+    static constexpr int U = bits32 ? SpecBlock<Model>::bits32 : (SpecBlock<Model>::bits52 > 0 ? SpecBlock<Model>::bits52 : 2);
+};
+
 // ------------------------------------------------------------------------------------------ uniformized interval
 // Exact simulation of the state at the end of an interval WITHOUT waiting times (Jensen's uniformization with a
 // restart rule).  While the total propensity a0(x) stays <= B, the jump process is a rate-B Poisson stream of
@@ -686,11 +756,6 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
     if (!TRACK_R) m.fix_removed(x);
     return total_fired;
 }
-
-// events per speculative block of the production loops (measured, tools/micro/ssa_loop.cu): 4 with 32-bit uniforms
-// (two Philox calls in flight), 2 with 52-bit uniforms (4 spills under the 80-register cap); models with many
-// compartments keep fewer speculative states in registers (0 = the one-event-per-iteration loop)
-template <class Model> struct SpecBlock { static constexpr int bits32 = Model::C <= 4 ? 4 : 2, bits52 = Model::C <= 6 ? 2 : 0; };
 
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,

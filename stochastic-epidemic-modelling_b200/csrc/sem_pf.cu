@@ -46,6 +46,7 @@ struct PfDev {
     // particle-sharded filter (one shard of a larger filter, see sem_shard_*): global index of particle 0, the
     // pre-gathered children records [N][C+1] (state, global ancestor) and the (M, total) summary of the local weights
     int j0, sharded;
+    int split_main;      // pf_persistent: > 0 = particles [split_main, ppb) of a CTA are shared by two warps each (see there)
     const int32_t *X_in;
     double *summary;
 };
@@ -280,8 +281,25 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
     __shared__ double2 s_tab[kLogTabSize];
     __shared__ unsigned long long s_pairs;
     const int f = blockIdx.y, b = blockIdx.x, tid = threadIdx.x;
-    const int N = P.N, j = b * P.ppb + tid;
-    const bool active = tid < P.ppb && j < N;
+    // Thread -> particle.  Plain: thread t owns particle t of the CTA.  Balanced (P.split_main = 128 W > 0): the CTA holds
+    // 128 W + e particles, e <= 64, i.e. W full warps per scheduler plus up to two more warps' worth -- which would make
+    // two of the four schedulers run W + 1 full rounds while the others idle.  Instead the extra particles are split in
+    // TIME between two helper warps on different schedulers: warp 4W + g runs group g (32 particles) until t >= dt / 2,
+    // hands the continuation (state, time, stream counter) over through shared memory, and warp 4W + 2 + g finishes the
+    // interval and owns the particle in the weights / scan.  Every scheduler then carries W + 1/2 rounds.  The legs
+    // reproduce the single run bit for bit (ssa_run_spec_leg).
+    constexpr bool kLegs = LegLoop<Model, ARITH>::available;
+    const int N = P.N, warp = tid >> 5, lane = tid & 31;
+    const int main_n = (kLegs && P.split_main > 0) ? P.split_main : (int)blockDim.x;
+    const int helper = tid < main_n ? -1 : warp - (main_n >> 5);          // -1 main; 0,1 first leg of group 0,1; 2,3 second leg
+    const int pidx = helper < 0 ? tid : main_n + 32 * (helper & 1) + lane;
+    const int j = b * P.ppb + pidx;
+    const bool has = pidx < P.ppb && j < N;
+    const bool starts = has && helper < 2;                   // resamples, gathers and starts the interval
+    const bool active = has && (helper < 0 || helper >= 2);  // owns the particle at the observation time (store, weigh, scan)
+    __shared__ double s_cx[kLegs ? 2 : 1][32][Model::C], s_ct[kLegs ? 2 : 1][32];
+    __shared__ uint32_t s_ck[kLegs ? 2 : 1][32];
+    __shared__ int s_cfin[kLegs ? 2 : 1][32];
     const uint32_t fid = P.filter_id0 + f;
     int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
@@ -338,20 +356,54 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         __syncthreads();                                     // s_pfx / s_scale complete
         PHASE(2);
         long long pairs = 0;
-        if (active) {
+        int32_t *Xr = Xf + (size_t)row * Model::C * N;
+        Model m;
+        PairSource<false> src;
+        if (starts) {
             const int a = select_ancestor<false>(P, p, f, j, fid, s_pfx, s_scale, total);
             PHASE(6);
             Af[(size_t)row * N + j] = a;
             const int32_t *Xp = Xf + (size_t)prow * Model::C * N;
 #pragma unroll
             for (int c = 0; c < Model::C; c++) x[c] = (double)__ldcg(&Xp[(size_t)c * N + a]);   // written by other CTAs: L2, not L1
-            Model m;
             m.setup(P.theta + (size_t)f * P.ntheta, x);
-            PairSource<false> src;
             src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
             PHASE(7);
-            pairs = ssa_run<Model, ARITH, false, false>(m, x, P.dt, src, s_tab, NoRec());
-            int32_t *Xr = Xf + (size_t)row * Model::C * N;
+        }
+        if constexpr (kLegs) {
+            // ONE call site of the event loop for every role: warps that ran different copies of the loop side by side
+            // on a scheduler cost 14 % (instruction cache), measured
+            const int g = helper & 1;
+            bool run = starts, fin = true;
+            double t = 0.0;
+            const double handoff = (helper == 0 || helper == 1) ? 0.5 * P.dt : CUDART_INF;
+            if (helper >= 2) {                               // second leg: wait for the continuation
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+                run = false;
+                if (has) {
+#pragma unroll
+                    for (int c = 0; c < Model::C; c++) x[c] = s_cx[g][lane][c];
+                    if (!s_cfin[g][lane]) {
+                        run = true;
+                        t = s_ct[g][lane];
+                        m.setup(P.theta + (size_t)f * P.ntheta, x);
+                        src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
+                        src.k = s_ck[g][lane];
+                    }
+                }
+            }
+            if (run) pairs = ssa_run_spec_leg<Model, LegLoop<Model, ARITH>::U, LegLoop<Model, ARITH>::bits32>(m, x, t, handoff, P.dt, src, s_tab, fin);
+            if (helper == 0 || helper == 1) {                // first leg: hand over
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) s_cx[g][lane][c] = x[c];
+                s_ct[g][lane] = t; s_ck[g][lane] = src.k; s_cfin[g][lane] = fin ? 1 : 0;
+                __threadfence_block();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+            }
+        } else {
+            if (starts) pairs = ssa_run<Model, ARITH, false, false>(m, x, P.dt, src, s_tab, NoRec());
+        }
+        if (active) {
 #pragma unroll
             for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
         }
@@ -649,7 +701,7 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
         P.scale[i] = (double *)(ws + w.scale[i]); P.total[i] = (double *)(ws + w.total[i]);
     }
     P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
-    P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr;
+    P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr; P.split_main = 0;
     return SEM_OK;
 }
 
@@ -693,6 +745,20 @@ static const void *persistent_kernel(const sem_pf_config *cfg) {
     }
 }
 
+// Threads per CTA of the whole-filter kernel and the balanced layout's main-thread count (0 = plain layout): when a
+// CTA's ppb particles are W full warps per scheduler plus at most two more warps' worth, those extra particles are
+// time-split between four helper warps (see pf_persistent).  SEM_NO_SPLIT=1 keeps the plain layout.
+static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *split_main) {
+    *split_main = 0;
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
+    const bool legs = cfg->arith == SEM_ARITH_FAST32 || (cfg->arith == SEM_ARITH_FAST && C <= 6);
+    const int e = w.ppb % 128, main_n = w.ppb - e;
+    static int env_off = -1;
+    if (env_off < 0) { const char *s = getenv("SEM_NO_SPLIT"); env_off = (s && s[0] == '1') ? 1 : 0; }
+    if (legs && !env_off && main_n >= 128 && e > 0 && e <= 64 && main_n + 128 <= kMaxThreads) { *split_main = main_n; return main_n + 128; }
+    return (w.ppb + 31) / 32 * 32;
+}
+
 // One cooperative launch for the whole filter when every CTA can be co-resident (SEM_NO_PERSISTENT=1 or
 // cfg->reserved = 1 forces the launch-per-step path; both give bit-identical results).
 static bool use_persistent(const sem_pf_config *cfg, const WsLayout &w, bool replay) {
@@ -702,7 +768,8 @@ static bool use_persistent(const sem_pf_config *cfg, const WsLayout &w, bool rep
     if (env_off) return false;
     int dev = 0, coop = 0, per_sm = 0;
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return false;
-    const int threads = (w.ppb + 31) / 32 * 32;
+    int split_main;
+    const int threads = persistent_threads(cfg, w, &split_main);
     const size_t smem = 2 * (size_t)w.nb * sizeof(double);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel(cfg), threads, smem) != cudaSuccess) { cudaGetLastError(); return false; }
     return (long long)per_sm * sm_count() >= (long long)w.nb * cfg->n_filters;
@@ -726,7 +793,7 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
     if (use_persistent(cfg, w, replay)) {
         void *args[] = {(void *)&P};
-        const dim3 grid(w.nb, cfg->n_filters), block((w.ppb + 31) / 32 * 32);
+        const dim3 grid(w.nb, cfg->n_filters), block(persistent_threads(cfg, w, &P.split_main));
         SEM_CUDA(cudaLaunchCooperativeKernel(persistent_kernel(cfg), grid, block, args, 2 * (size_t)w.nb * sizeof(double), s));
         return SEM_OK;
     }
