@@ -509,7 +509,7 @@ def test_logz_distribution_vs_reference(sem):
     N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
     ref = g["zetas_last"]
     runs = 1200
-    for resampler, arith in [(0, 1), (0, 0), (1, 1), (0, 2)]:
+    for resampler, arith in [(0, 3), (1, 3), (0, 1), (0, 0), (1, 1), (0, 2)]:       # 3 = fast32, the production default
         cfg = sem.engine.make_pf_config(0, N, len(g["Y"]), n_filters=runs, probs=float(g["probs"]), resampler=resampler,
                                         arith=arith, seed=2024 + 7 * resampler + arith, mu=[mu], n_population=[npop])
         res = sem.engine.run_pf(cfg, g["Y"], np.tile(g["theta"], (runs, 1)))
