@@ -233,6 +233,8 @@ __device__ __forceinline__ BinomObs binom_obs(double k, const double2 *tab) {
 
 __device__ __forceinline__ double binom_logpmf_obs(const BinomObs &o, double n, double p, const double2 *tab) {
     const double q = 1 - p;
+    if (o.k == 0.0 && n >= 1.0 && p > 0 && q > 0)            // nothing observed: q^n (frequent: a compartment that is still / again empty)
+        return p < 0.1 ? -bd0_w(n, n * q, tab) - n * p : n * log_tab(q, tab);
     if (!(o.regular && n > o.k && p > 0 && q > 0)) return binom_logpmf(o.k, n, p, tab);
     const double k = o.k, nk = n - k;
     const double rn = rcp_nr(n), rnk = rcp_nr(nk);
