@@ -354,7 +354,7 @@ def main():
         e2e_s = float(te.cpu()[0])
         runs = st["filter_runs"]
         e2e = {"value": world * runs * N * (T - 1) / e2e_s, "unit": "particle-steps/s",
-               "h2d_bytes_per_step": int(theta.nbytes + Y.nbytes / runs), "d2h_bytes_per_step": int(8 + 4 + T * 3 * 4),
+               "h2d_bytes_per_step": int(theta.nbytes + Y.nbytes / runs), "d2h_bytes_per_step": int(8 * (4 + T * 3)),
                "api": "sem_b200.particle_mcmc (drop-in for pmcmc.py:251): host numpy in, host numpy out, one filter pass + "
                       "path sample per MH iteration", "iterations": runs, "pmcmc_iters_per_s": world * runs / e2e_s}
         # the other public call: particle_filter returning the reference's full (T,N,C)+(T,N) float64 history on the host

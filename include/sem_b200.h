@@ -87,7 +87,8 @@ typedef struct sem_pf_config {
     double dt;              /* observation interval, the reference uses 1 (pmcmc.py:205) */
     uint64_t seed;          /* Philox key */
     uint32_t filter_id0;    /* stream id of filter 0; filter f uses filter_id0 + f */
-    uint32_t reserved2;
+    uint32_t path_exact;    /* iteration_result only: 0 = the reference's off-by-one ancestry indexing (pmcmc.py:244-246),
+                               1 = true genealogy */
     double mu[SEM_MAX_GROUPS];           /* Poisson mean of I_0 per group (pmcmc.py:157,161,167) */
     double n_population[SEM_MAX_GROUPS]; /* population per group (pmcmc.py:158,162,168) */
 } sem_pf_config;
@@ -108,7 +109,13 @@ typedef struct sem_pf_buffers {
     int32_t *status;            /* device [n_filters]: 0 ok, p>0 collapsed at step p, -3 replay exhausted */
     uint64_t *n_events;         /* device [n_filters] total SSA events drawn (incl. discarded overshoots) or NULL */
     void *workspace;            /* device, sem_pf_workspace_bytes() */
+    /* One PMCMC iteration in one call (pmcmc.py:354-371: particle_filter + particle_path_sampler): when not NULL
+     * (needs store_history = 1) the run ends by sampling a path (final particle ~ Philox(seed, domain 4, filter id),
+     * ancestry chased backwards) and packs, per filter, device double[SEM_ITER_HEADER + T*C] =
+     * { log_zetas[T-1], status, n_events, chosen final particle, trajectory[T][C] } for a single D2H copy. */
+    double *iteration_result;
 } sem_pf_buffers;
+#define SEM_ITER_HEADER 4
 
 size_t sem_pf_workspace_bytes(const sem_pf_config *cfg);
 /* number of int32 in X_hist / ancestry and doubles in log_zetas the caller must provide */

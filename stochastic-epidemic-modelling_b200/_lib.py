@@ -30,7 +30,7 @@ class PfConfig(C.Structure):
         ("n_particles", C.c_int32), ("n_obs", C.c_int32), ("n_groups", C.c_int32), ("n_obs_cols", C.c_int32),
         ("n_filters", C.c_int32), ("block_particles", C.c_int32), ("store_history", C.c_int32), ("reserved", C.c_int32),
         ("probs", C.c_double), ("dt", C.c_double), ("seed", C.c_uint64), ("filter_id0", C.c_uint32),
-        ("reserved2", C.c_uint32), ("mu", C.c_double * SEM_MAX_GROUPS), ("n_population", C.c_double * SEM_MAX_GROUPS),
+        ("path_exact", C.c_uint32), ("mu", C.c_double * SEM_MAX_GROUPS), ("n_population", C.c_double * SEM_MAX_GROUPS),
     ]
 
 
@@ -39,7 +39,7 @@ class PfBuffers(C.Structure):
         ("Y", C.c_void_p), ("theta", C.c_void_p), ("X0", C.c_void_p),
         ("replay_resample_u", C.c_void_p), ("replay_ssa_u", C.c_void_p), ("replay_ssa_off", C.c_void_p),
         ("X_hist", C.c_void_p), ("ancestry", C.c_void_p), ("log_zetas", C.c_void_p), ("status", C.c_void_p),
-        ("n_events", C.c_void_p), ("workspace", C.c_void_p),
+        ("n_events", C.c_void_p), ("workspace", C.c_void_p), ("iteration_result", C.c_void_p),
     ]
 
 

@@ -46,6 +46,8 @@ struct PfDev {
     // particle-sharded filter (one shard of a larger filter, see sem_shard_*): global index of particle 0, the
     // pre-gathered children records [N][C+1] (state, global ancestor) and the (M, total) summary of the local weights
     int j0, sharded;
+    int path_exact;
+    double *iter_out;    // [F][SEM_ITER_HEADER + T*C] packed result of one PMCMC iteration, or null
     int split_main;      // pf_persistent: > 0 = particles [split_main, ppb) of a CTA are shared by two warps each (see there)
     const int32_t *X_in;
     double *summary;
@@ -268,6 +270,37 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
     return base + min(a, len - 1);
 }
 
+// End of one PMCMC iteration (pmcmc.py:371 particle_path_sampler + the three small results the MH loop reads), by one
+// thread per filter after everything else of the filter is globally visible.  Same draw and indexing as
+// path_sample_kernel.
+template <int C>
+__device__ void iteration_epilogue(const PfDev &P, const int f) {
+    const int T = P.T, N = P.N;
+    double *out = P.iter_out + (size_t)f * (SEM_ITER_HEADER + (size_t)T * C);
+    const int status = *(volatile int32_t *)&P.status[f];
+    out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
+    out[1] = (double)status;
+    out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
+    if (status != 0) { out[3] = -1.0; return; }
+    const int32_t *X = P.X_hist + (size_t)f * P.hist_rows * C * N, *A = P.ancestry + (size_t)f * P.hist_rows * N;
+    const uint4 w = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, P.filter_id0 + f), P.key);
+    int chosen = min((int)((bits_to_d12(w.x, w.y) - 1.0) * (double)N), N - 1);          // np.random.randint(0, N) (pmcmc.py:241)
+    out[3] = (double)chosen;
+    double *traj = out + SEM_ITER_HEADER;
+#pragma unroll
+    for (int c = 0; c < C; c++) traj[(size_t)(T - 1) * C + c] = (double)__ldcg(&X[((size_t)(T - 1) * C + c) * N + chosen]);
+    for (int p = T - 2; p >= 0; p--) {
+        chosen = __ldcg(&A[(size_t)(P.path_exact ? p + 1 : p) * N + chosen]);           // reference indexes row p
+#pragma unroll
+        for (int c = 0; c < C; c++) traj[(size_t)p * C + c] = (double)__ldcg(&X[((size_t)p * C + c) * N + chosen]);
+    }
+}
+
+template <int C>
+__global__ void iteration_epilogue_kernel(const __grid_constant__ PfDev P) {
+    if (threadIdx.x == 0) iteration_epilogue<C>(P, blockIdx.x);
+}
+
 // Whole filter in ONE cooperative launch (one CTA per SM, all co-resident): the resampling barrier of every step is
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
 // waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
@@ -305,6 +338,11 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
     load_logtab(s_tab);
     if (tid == 0) s_pairs = 0ull;
+    if (b == 0 && tid == 0) {                                // the launch needs no memsets: the first grid.sync orders these
+        P.status[f] = 0;                                     // before any other CTA's write
+        P.log_zetas[(size_t)f * P.T] = 0.0;                  // zetas[0] = 1 (pmcmc.py:154)
+        if (P.n_events) P.n_events[f] = 0ull;
+    }
     __syncthreads();
     double x[Model::C];
     // ------------------------------------------------------------------------ step 0: X_0 (pmcmc.py:156-170)
@@ -422,6 +460,10 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         if ((tid & 31) == 0 && my_pairs) atomicAdd(&s_pairs, my_pairs);
         __syncthreads();
         if (tid == 0 && s_pairs) atomicAdd(&P.n_events[f], s_pairs);
+    }
+    if (P.iter_out) {                                        // path sample + packed result of the MH iteration
+        grid.sync();
+        if (b == 0 && tid == 0) iteration_epilogue<Model::C>(P, f);
     }
 }
 
@@ -702,6 +744,8 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
     }
     P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
     P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr; P.split_main = 0;
+    P.iter_out = buf->iteration_result; P.path_exact = (int)cfg->path_exact;
+    if (P.iter_out && !cfg->store_history) { set_error("iteration_result needs store_history = 1"); return SEM_ERR_INVALID; }
     return SEM_OK;
 }
 
@@ -787,17 +831,27 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     int rc = fill_dev(cfg, buf, P, w, replay);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    SEM_CUDA(cudaMemsetAsync(P.counter, 0, cfg->n_filters * sizeof(unsigned int), s));
-    SEM_CUDA(cudaMemsetAsync(P.status, 0, cfg->n_filters * sizeof(int32_t), s));
-    SEM_CUDA(cudaMemsetAsync(P.log_zetas, 0, (size_t)cfg->n_filters * cfg->n_obs * sizeof(double), s));   // zetas[0] = 1 (pmcmc.py:154)
-    if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
-    if (use_persistent(cfg, w, replay)) {
+    if (use_persistent(cfg, w, replay)) {                    // one launch, nothing else (the kernel initialises its outputs)
         void *args[] = {(void *)&P};
         const dim3 grid(w.nb, cfg->n_filters), block(persistent_threads(cfg, w, &P.split_main));
         SEM_CUDA(cudaLaunchCooperativeKernel(persistent_kernel(cfg), grid, block, args, 2 * (size_t)w.nb * sizeof(double), s));
         return SEM_OK;
     }
+    SEM_CUDA(cudaMemsetAsync(P.counter, 0, cfg->n_filters * sizeof(unsigned int), s));
+    SEM_CUDA(cudaMemsetAsync(P.status, 0, cfg->n_filters * sizeof(int32_t), s));
+    SEM_CUDA(cudaMemsetAsync(P.log_zetas, 0, (size_t)cfg->n_filters * cfg->n_obs * sizeof(double), s));   // zetas[0] = 1 (pmcmc.py:154)
+    if (P.n_events) SEM_CUDA(cudaMemsetAsync(P.n_events, 0, cfg->n_filters * sizeof(unsigned long long), s));
     for (int p = 0; p < cfg->n_obs; p++) launch_step(cfg, P, w, p, replay, s);
+    if (P.iter_out) {
+        const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+        switch (model_cols(cfg->model, G)) {
+            case 3: iteration_epilogue_kernel<3><<<cfg->n_filters, 32, 0, s>>>(P); break;
+            case 4: iteration_epilogue_kernel<4><<<cfg->n_filters, 32, 0, s>>>(P); break;
+            case 6: iteration_epilogue_kernel<6><<<cfg->n_filters, 32, 0, s>>>(P); break;
+            case 9: iteration_epilogue_kernel<9><<<cfg->n_filters, 32, 0, s>>>(P); break;
+            default: iteration_epilogue_kernel<12><<<cfg->n_filters, 32, 0, s>>>(P); break;
+        }
+    }
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }

@@ -85,13 +85,13 @@ class PfResult:
 
 def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="fast32",
                    seed=0, filter_id0=0, mu=None, n_population=None, dt=1.0, store_history=True, block_particles=0,
-                   launch_per_step=False):
+                   launch_per_step=False, path_exact=False):
     Cn, P, Cobs = model_dims(model, G)
     cfg = _lib.PfConfig(model=model, obs_kind=int(bool(observations)), resampler=RESAMPLERS.get(resampler, resampler),
                         arith=ARITH.get(arith, arith), n_particles=int(N), n_obs=int(T), n_groups=int(G),
                         n_obs_cols=Cobs, n_filters=int(n_filters), block_particles=int(block_particles),
                         store_history=int(bool(store_history)), reserved=int(bool(launch_per_step)), probs=float(probs),
-                        dt=float(dt),
+                        dt=float(dt), path_exact=int(bool(path_exact)),
                         seed=int(seed) & (2**64 - 1), filter_id0=int(filter_id0) & 0xFFFFFF)
     if mu is not None:
         mu = np.asarray(mu, dtype=np.float64).reshape(-1)
@@ -101,8 +101,14 @@ def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, 
     return cfg
 
 
-def run_pf(cfg, Y, theta, X0=None, replay=None, device=None, out=None):
+ITER_HEADER = 4      # SEM_ITER_HEADER: log_zetas[T-1], status, n_events, chosen final particle
+
+
+def run_pf(cfg, Y, theta, X0=None, replay=None, device=None, out=None, iter_out=None):
     """Enqueue one particle-filter pass (all T steps) on the current stream.  Returns PfResult (device tensors).
+
+    iter_out: optional CUDA float64 tensor [F, ITER_HEADER + T*C]; the pass then ends with the path sample of
+    particle_path_sampler and packs the results one MH iteration reads (sem_b200.h: iteration_result).
 
     Y (T,Cobs), theta (F,P) or (P,), X0 (N,C) or None (Poisson init on device), replay = dict(res_u (T-1,N),
     ssa_u flat, ssa_off CSR) for the bit-exact replay mode.
@@ -130,7 +136,8 @@ def run_pf(cfg, Y, theta, X0=None, replay=None, device=None, out=None):
         else:
             X_hist, anc, logz, status, nev, ws = out
         buf = _lib.PfBuffers(Y=_ptr(Yd), theta=_ptr(thd), X0=_ptr(X0d), X_hist=_ptr(X_hist), ancestry=_ptr(anc),
-                             log_zetas=_ptr(logz), status=_ptr(status), n_events=_ptr(nev), workspace=_ptr(ws))
+                             log_zetas=_ptr(logz), status=_ptr(status), n_events=_ptr(nev), workspace=_ptr(ws),
+                             iteration_result=_ptr(iter_out))
         keep = [Yd, thd, X0d, ws]
         if replay is not None:
             ru = _dev_f64(replay["res_u"], dev); su = _dev_f64(replay["ssa_u"], dev)

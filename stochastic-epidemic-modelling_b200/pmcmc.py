@@ -155,30 +155,34 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     seed = engine.new_seed() if seed is None else seed
     counters = dict(filter_runs=0, acceptances=1, launches=0)
 
-    # reusable device buffers + pinned staging for the three small results of one iteration
+    # One iteration = ONE launch (the filter, the path sample of pmcmc.py:371 and the packing of the results happen in
+    # the whole-filter kernel) + one small H2D (theta) + one small D2H (log-likelihood, status, sampled trajectory).
     cfg0, _, _ = _setup(Y, type_model, _split(model, G, np.asarray(parameters, dtype=float), probs)[0], observations,
                         .5, n_particles, n_population, mu, resampler, seed, arith, 0)
     out = engine.alloc_pf_outputs(cfg0, dev)
     Yd = torch.from_numpy(Y).to(dev)
-    pin_lz = torch.empty((1,), dtype=torch.float64).pin_memory()
-    pin_st = torch.empty((1,), dtype=torch.int32).pin_memory()
-    pin_tr = torch.empty((T, Cn), dtype=torch.int32).pin_memory()
+    n_theta = engine.model_dims(model, G)[1]
+    pin_th = torch.empty((n_theta,), dtype=torch.float64).pin_memory()
+    dev_th = torch.empty((n_theta,), dtype=torch.float64, device=dev)
+    dev_it = torch.empty((1, engine.ITER_HEADER + T * Cn), dtype=torch.float64, device=dev)
+    pin_it = torch.empty((1, engine.ITER_HEADER + T * Cn), dtype=torch.float64).pin_memory()
 
     def run_filter(theta_vec, it):
         theta2, probs2 = _split(model, G, theta_vec, probs)
         cfg, _, th = _setup(Y, type_model, theta2, observations, probs2, n_particles, n_population, mu, resampler, seed,
                             arith, it)
-        res = engine.run_pf(cfg, Yd, th, out=out)
-        traj = res.path_sample(0, exact=exact_genealogy, seed=seed, filter_id=it)
-        pin_lz.copy_(res.log_zetas[0, -1:], non_blocking=True)
-        pin_st.copy_(res.status, non_blocking=True)
-        pin_tr.copy_(traj, non_blocking=True)
+        cfg.path_exact = int(bool(exact_genealogy))
+        pin_th.numpy()[:] = th
+        dev_th.copy_(pin_th, non_blocking=True)
+        res = engine.run_pf(cfg, Yd, dev_th, out=out, iter_out=dev_it)
+        pin_it.copy_(dev_it, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         counters["filter_runs"] += 1
-        counters["launches"] += res.launches + 1
-        if int(pin_st[0]) != 0:
+        counters["launches"] += res.launches + (0 if res.launches == 1 else 1)
+        r = pin_it.numpy()[0]
+        if int(r[1]) != 0:
             return None, None
-        return float(pin_lz[0]), pin_tr.numpy().astype(np.float64)
+        return float(r[0]), r[engine.ITER_HEADER:].reshape(T, Cn).copy()
 
     def finish_theta(theta_vec):
         if probs is None:                                                         # :313-314,373-374: stored p_obs is clipped

@@ -629,3 +629,32 @@ def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, 
             assert np.array_equal(outs[0][3][f], outs[1][3][f]), (F, N, hist, f)
             if not outs[0][5][f]:
                 assert outs[0][4][f] == outs[1][4][f]
+
+
+@pytest.mark.parametrize("exact", [False, True])
+def test_iteration_result_equals_separate_calls(sem, exact):
+    """One PMCMC iteration in one call (sem_b200.h: iteration_result): the packed log-likelihood / status / event count /
+    sampled trajectory equal the separate particle_filter + particle_path_sampler calls, on the whole-filter kernel and on
+    the launch-per-step path, for one and for several filters."""
+    import torch
+    T, seed = 9, 0xABCDEF
+    Y = _truth_Y(0, T, 5, .1, False)
+    for F, N, per_step in [(1, 3000, False), (1, 3000, True), (3, 700, False)]:
+        cfg = sem.engine.make_pf_config(0, N, T, n_filters=F, probs=.1, resampler=1, arith=3, seed=seed, filter_id0=17, mu=[20],
+                                        n_population=[1000], launch_per_step=per_step, path_exact=exact)
+        it = torch.full((F, sem.engine.ITER_HEADER + T * 3), -7.0, dtype=torch.float64, device="cuda")
+        res = sem.engine.run_pf(cfg, Y, np.tile(np.array([2.0, 1.0]), (F, 1)), iter_out=it)
+        torch.cuda.synchronize()
+        r = it.cpu().numpy()
+        for f in range(F):
+            assert r[f, 0] == float(res.log_zetas[f, -1]) and r[f, 1] == float(res.status[f]) == 0 and r[f, 2] == float(res.n_events[f])
+            traj = res.path_sample(f, exact=exact, seed=seed, filter_id=17 + f).cpu().numpy()
+            assert np.array_equal(r[f, sem.engine.ITER_HEADER:].reshape(T, 3), traj.astype(float))
+            assert 0 <= r[f, 3] < N and np.array_equal(traj[-1], res.X_hist[f, -1, :, int(r[f, 3])].cpu().numpy())
+    # a collapsing filter reports its status and no trajectory
+    Yc = Y.copy(); Yc[3] = [5000.0, 5000.0, 5000.0]
+    cfg = sem.engine.make_pf_config(0, 500, T, probs=.1, resampler=1, arith=3, seed=seed, mu=[20], n_population=[1000])
+    it = torch.zeros((1, sem.engine.ITER_HEADER + T * 3), dtype=torch.float64, device="cuda")
+    res = sem.engine.run_pf(cfg, Yc, np.array([2.0, 1.0]), iter_out=it)
+    torch.cuda.synchronize()
+    assert int(res.status[0]) == 4 and it[0, 1].item() == 4.0 and it[0, 3].item() == -1.0 and it[0, 0].item() == float("-inf")
