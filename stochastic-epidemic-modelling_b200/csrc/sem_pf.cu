@@ -47,6 +47,8 @@ struct PfDev {
     // pre-gathered children records [N][C+1] (state, global ancestor) and the (M, total) summary of the local weights
     int j0, sharded;
     int path_exact;
+    double *wtab;        // [T-1][Cobs][wt_n + 1] log-weight of a compartment count, or null (see weight_table_fill)
+    int wt_n;
     double *iter_out;    // [F][SEM_ITER_HEADER + T*C] packed result of one PMCMC iteration, or null
     int split_main;      // pf_persistent: > 0 = particles [split_main, ppb) of a CTA are shared by two warps each (see there)
     const int32_t *X_in;
@@ -79,8 +81,33 @@ __device__ __forceinline__ double block_incl_scan(double v, double *sm, int tid,
     return w > 0 ? v + off : v;
 }
 
+// log-weight of one observed column given the compartment count (pmcmc.py:179,181)
+__device__ __forceinline__ double column_logw(const PfDev &P, double y, double xc, const double2 *tab) {
+    return (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf_obs(binom_obs(y, tab), xc, P.probs, tab) : norm_logpdf(y, xc, P.probs, tab);
+}
+
+// The weight of a column depends on the particle only through an integer count in [0, total population], and Y is
+// known up front: all (T-1) x Cobs x (pop+1) values are tabulated once per launch (weight_table_fill; 3*10^6 evaluations
+// for the headline instead of 3*10^7 per pass) and the per-particle weight becomes Cobs L2-resident loads.  Same
+// function, same values: results are bit-identical to the direct evaluation.
+__device__ __forceinline__ void weight_table_fill(const PfDev &P, size_t first, size_t stride, const double2 *tab) {
+    const size_t per_col = (size_t)P.wt_n + 1, total = (size_t)(P.T - 1) * P.Cobs * per_col;
+    for (size_t i = first; i < total; i += stride) {
+        const size_t pc = i / per_col;
+        const double y = P.Y[pc];                            // Y[p][c], p = pc / Cobs
+        P.wtab[i] = (y != y) ? 0.0 : column_logw(P, y, (double)(i - pc * per_col), tab);
+    }
+}
+
+__global__ void __launch_bounds__(256) weight_table_kernel(const __grid_constant__ PfDev P) {
+    __shared__ double2 s_tab[kLogTabSize];
+    load_logtab(s_tab);
+    __syncthreads();
+    weight_table_fill(P, blockIdx.x * (size_t)blockDim.x + threadIdx.x, (size_t)gridDim.x * blockDim.x, s_tab);
+}
+
 template <class Model>
-__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double2 *tab) {
+__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double *wrow, const double2 *tab) {
     double lw = CUDART_INF;
 #pragma unroll
     for (int c = 0; c < Model::C; c++) {
@@ -93,8 +120,9 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
             }
             const double y = Yrow[c];
             if (y != y) continue;                            // extension: a NaN entry of Y marks an unobserved column
-            const double l = (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf_obs(binom_obs(y, tab), xc, P.probs, tab)
-                                                              : norm_logpdf(y, xc, P.probs, tab);
+            double l;
+            if (wrow && xc >= 0.0 && xc <= (double)P.wt_n) l = wrow[(size_t)c * (P.wt_n + 1) + (int)xc];
+            else l = column_logw(P, y, xc, tab);
             lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
         }
     }
@@ -116,7 +144,7 @@ __device__ __forceinline__ void weigh_local(const PfDev &P, const int p, const i
     const int N = P.N, par = p & 1;
     double lw = -CUDART_INF;
     if (active) {
-        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, tab);
+        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, P.wtab ? P.wtab + (size_t)p * P.Cobs * (P.wt_n + 1) : nullptr, tab);
         if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in the combine
     }
     PHASE(8);
@@ -344,6 +372,11 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         if (P.n_events) P.n_events[f] = 0ull;
     }
     __syncthreads();
+    if (P.wtab) {                                            // tabulate the observation weights (all CTAs, once per launch)
+        const size_t nthr = (size_t)gridDim.x * gridDim.y * blockDim.x;
+        weight_table_fill(P, ((size_t)f * gridDim.x + b) * blockDim.x + tid, nthr, s_tab);
+        grid.sync();
+    }
     double x[Model::C];
     // ------------------------------------------------------------------------ step 0: X_0 (pmcmc.py:156-170)
     if (active) {
@@ -655,7 +688,19 @@ static int validate(const sem_pf_config *c) {
     return SEM_OK;
 }
 
-struct WsLayout { size_t L[2], pfx[2], scale[2], total[2], part, counter, bytes; int nb, ppb; };
+struct WsLayout { size_t L[2], pfx[2], scale[2], total[2], part, counter, wtab, bytes; int nb, ppb, wt_n; };
+
+// total population = the largest count a compartment (or a group sum) can hold; 0 = no table (unknown, or > 1 GiB)
+static int weight_table_n(const sem_pf_config *c) {
+    const int G = c->model >= SEM_MODEL_SIR_SUBGROUPS ? c->n_groups : 1;
+    double tot = 0;
+    for (int g = 0; g < G; g++) tot += c->n_population[g];
+    static int env_off = -1;
+    if (env_off < 0) { const char *e = getenv("SEM_NO_WEIGHT_TABLE"); env_off = (e && e[0] == '1') ? 1 : 0; }
+    if (env_off || c->obs_kind != SEM_OBS_BINOMIAL || !(tot >= 1) || tot != (double)(long long)tot || c->n_obs < 2) return 0;   // (the normal pdf is cheap)
+    const double bytes = (double)(c->n_obs - 1) * c->n_obs_cols * (tot + 1) * sizeof(double);
+    return bytes <= 1073741824.0 ? (int)tot : 0;
+}
 static WsLayout ws_layout(const sem_pf_config *c) {
     WsLayout w;
     w.ppb = choose_ppb(c);
@@ -669,6 +714,8 @@ static WsLayout ws_layout(const sem_pf_config *c) {
     for (int i = 0; i < 2; i++) w.total[i] = take(F * sizeof(double));
     w.part = take(2 * F * w.nb * sizeof(double2));
     w.counter = take(F * sizeof(unsigned int));
+    w.wt_n = weight_table_n(c);
+    w.wtab = take(w.wt_n ? (size_t)(c->n_obs - 1) * c->n_obs_cols * ((size_t)w.wt_n + 1) * sizeof(double) : 0);
     w.bytes = off;
     return w;
 }
@@ -676,7 +723,10 @@ static WsLayout ws_layout(const sem_pf_config *c) {
 template <class Model>
 static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 grid, int threads, cudaStream_t s) {
     const size_t smem = P.pfx_in_smem ? (size_t)P.nb * sizeof(double) : 0;
-    if (p == 0) pf_init<Model><<<grid, threads, 0, s>>>(P);
+    if (p == 0) {
+        if (P.wtab) weight_table_kernel<<<sm_count() * 8, 256, 0, s>>>(P);
+        pf_init<Model><<<grid, threads, 0, s>>>(P);
+    }
     else if (replay) pf_step<Model, SEM_ARITH_REFERENCE, true><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_UNIFORMIZED) pf_step<Model, SEM_ARITH_UNIFORMIZED, false><<<grid, threads, smem, s>>>(P, p);
@@ -743,6 +793,9 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
         P.scale[i] = (double *)(ws + w.scale[i]); P.total[i] = (double *)(ws + w.total[i]);
     }
     P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
+    // the table covers counts up to the configured population: only valid when X_0 is drawn from it (pmcmc.py:156-169)
+    P.wt_n = (P.init_poisson && !replay) ? w.wt_n : 0;
+    P.wtab = P.wt_n ? (double *)(ws + w.wtab) : nullptr;
     P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr; P.split_main = 0;
     P.iter_out = buf->iteration_result; P.path_exact = (int)cfg->path_exact;
     if (P.iter_out && !cfg->store_history) { set_error("iteration_result needs store_history = 1"); return SEM_ERR_INVALID; }
@@ -823,7 +876,8 @@ extern "C" {
 
 int sem_pf_launch_count(const sem_pf_config *c) {
     if (validate(c)) return 0;
-    return use_persistent(c, ws_layout(c), false) ? 1 : c->n_obs;
+    const WsLayout w = ws_layout(c);
+    return use_persistent(c, w, false) ? 1 : c->n_obs + (w.wt_n ? 1 : 0);      // (+ the weight-table kernel; assumes X_0 drawn on the device)
 }
 
 int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream) {

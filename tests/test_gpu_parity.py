@@ -619,7 +619,7 @@ def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, 
             torch.cuda.synchronize()
             outs.append((r.launches, r.X_hist.cpu().numpy(), r.ancestry.cpu().numpy(), r.log_zetas.cpu().numpy(), r.n_events.cpu().numpy(),
                          r.status.cpu().numpy()))
-        assert outs[0][0] == 1 and outs[1][0] == T
+        assert outs[0][0] == 1 and outs[1][0] == T + 1                        # T steps + the weight-table kernel
         assert np.array_equal(outs[0][5], outs[1][5])                          # status (0, or the step of the collapse)
         for f in range(F):
             upto = int(outs[0][5][f]) or T                                     # rows before a collapse are defined, later ones are not
