@@ -35,13 +35,13 @@ import workloads  # noqa: E402
 # Thread-instructions per SSA event (SIR, fp64), the per-unit figure of the issue roofline.  SURVEY 8(d) declared a
 # budget of 128 "to be replaced by ncu smsp__inst_executed / events once the kernel exists"; these are the measured
 # values: smsp__inst_executed.sum x thread_inst_per_inst / n_events over the whole-filter kernel
-# (profiles/r01b_pf_persistent_fast32.txt: 4.4516e9 x 26.71 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
-I_ALG_BY_ARITH = {"fast32": 74.4, "fast": 106.0}
+# (profiles/r01c_pf_persistent_final.txt: 4.4271e9 x 26.49 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
+I_ALG_BY_ARITH = {"fast32": 73.4, "fast": 106.0}
 I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
 LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
 # dram__bytes_read.sum + dram__bytes_write.sum of one whole-filter launch (ncu --set full, same profile)
-DRAM_TRAFFIC_PER_PASS = {"fast32": 312.32e3 + 112.229888e6}
+DRAM_TRAFFIC_PER_PASS = {"fast32": 883.968e3 + 143.988224e6}
 
 
 def measured_peaks():
