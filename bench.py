@@ -5,7 +5,8 @@
 
 A "step" is one pass of the bootstrap particle filter (X_0 init, then T-1 x [weigh, accumulate likelihood,
 resample, gather, Gillespie-SSA propagate]) = one PMCMC likelihood evaluation, on the BASELINE.json metric
-workload: SIR, population 1e4, 1e5 particles, 100 observation intervals (workloads.HEADLINE).
+workload: SIR, population 1e4, 1e5 particles, 100 observation intervals (workloads.HEADLINE).  One pass is one
+cooperative kernel launch (pf_persistent).
 Metric: particle-steps/s (one particle advanced across one observation interval, including its share of
 weighting + resampling).  Prints ONE JSON line (rank 0).
 

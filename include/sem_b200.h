@@ -67,7 +67,8 @@ int sem_device_info(int *sm_count, int *cc_major, int *cc_minor);
  * Particle filter: replaces the body of particle_filter (pmcmc.py:123-233): X_0 initialisation,
  * and for p = 1..T-1: weight X[p-1] against Y[p-1] (min over columns), accumulate the likelihood,
  * resample, propagate every particle one observation interval with exact Gillespie SSA
- * (gillespie_algo.py:10-233).  The whole time loop runs on the device, one launch per step.
+ * (gillespie_algo.py:10-233).  The whole time loop runs on the device: ONE cooperative launch for the whole filter when
+ * all CTAs are co-resident (grid-wide barrier per step), else one launch per step.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct sem_pf_config {
     int32_t model;          /* SEM_MODEL_* */

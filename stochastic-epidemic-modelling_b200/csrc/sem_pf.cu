@@ -1,6 +1,7 @@
 // sem_pf.cu -- bootstrap particle filter on the device (replaces pmcmc.py:123-233).
 //
-// One kernel launch per observation step p (the launch boundary is the resampling barrier):
+// pf_persistent runs the whole filter in ONE cooperative launch (grid.sync() is the resampling barrier); pf_init +
+// pf_step run the same phases with one kernel launch per observation step p (the launch boundary is the barrier):
 //   pf_step(p):  [resample]   ancestor a_j = first i with cdf_{p-1}(i) > u_j * total      (pmcmc.py:187-193)
 //                [gather]     x = X[p-1][:, a_j]   (fused into the load, no separate gather pass, :195-199)
 //                [propagate]  exact Gillespie SSA over one observation interval            (gillespie_algo.py)
