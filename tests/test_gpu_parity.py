@@ -658,3 +658,35 @@ def test_iteration_result_equals_separate_calls(sem, exact):
     res = sem.engine.run_pf(cfg, Yc, np.array([2.0, 1.0]), iter_out=it)
     torch.cuda.synchronize()
     assert int(res.status[0]) == 4 and it[0, 1].item() == 4.0 and it[0, 3].item() == -1.0 and it[0, 0].item() == float("-inf")
+
+
+@pytest.mark.parametrize("F,N,model,G,theta,npop,mu", [
+    (1, 148 * 140, 0, 1, [2.0, 1.0], [1000], [20]),            # 128 main + 12 time-split particles per CTA (one helper group)
+    (2, 74 * 140, 0, 1, [2.0, 1.0], [1000], [20]),             # two filters side by side, same layout
+    (1, 148 * 190, 1, 1, [4.0, 1.0, 1.0], [1000], [20]),       # 128 + 62: two helper groups, SEIR
+    (1, 148 * 161 + 7, 3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20]),   # 128 + 34 (ragged last CTA), 2 subgroups: blocks of 2 events
+])
+def test_balanced_layout_matches_oracle(sem, c_oracle, F, N, model, G, theta, npop, mu):
+    """The whole-filter kernel's scheduler balancing (extra particles time-split between helper warps, continuation handed
+    over in shared memory) is a pure scheduling change: states, ancestors, likelihood and event count equal the oracle's
+    and the launch-per-step path's."""
+    import torch
+    T = 6
+    Y = _truth_Y(model, T, 5, .1, False, G=G)
+    th = np.tile(np.array(theta, float), (F, 1))
+    runs = []
+    for per_step in (False, True):
+        cfg = sem.engine.make_pf_config(model, N, T, G=G, n_filters=F, probs=.1, resampler=1, arith=3, seed=99, filter_id0=4, mu=mu,
+                                        n_population=npop, launch_per_step=per_step)
+        r = sem.engine.run_pf(cfg, Y, th)
+        torch.cuda.synchronize()
+        runs.append(r)
+    assert runs[0].launches == 1 and runs[1].launches > 1
+    assert torch.equal(runs[0].X_hist, runs[1].X_hist) and torch.equal(runs[0].ancestry, runs[1].ancestry)
+    assert torch.equal(runs[0].log_zetas, runs[1].log_zetas) and torch.equal(runs[0].n_events, runs[1].n_events)
+    for f in range(F):
+        ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=3, seed=99, filter_id=4 + f, mu=mu, npop=npop)
+        assert np.array_equal(runs[0].X_hist[f].permute(0, 2, 1).cpu().numpy(), ref["X_hist"])
+        assert np.array_equal(runs[0].ancestry[f].cpu().numpy(), ref["ancestry"])
+        np.testing.assert_allclose(runs[0].log_zetas[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
+        assert int(runs[0].n_events[f]) == ref["n_events"]
