@@ -1,4 +1,5 @@
-"""Debug: per-step phase timestamps of CTA 0 in the cooperative kernel.  Builds a -DSEM_PHASES copy of the library into
+"""Debug: per-step phase timestamps of CTA 0, thread 0 in the cooperative kernel (run with SEM_NO_SPLIT=1 for a clean
+reading of the SSA phase: in the balanced layout warp 0 is not on the critical path).  Builds a -DSEM_PHASES copy of the library into
 /tmp and loads it instead of the in-tree one."""
 import ctypes as C, os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
