@@ -414,18 +414,22 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         double M, total;
         combine_partials(P, f, par ^ 1, tid, sm, s_pfx, s_scale, M, total);
         const bool ok = (M > -CUDART_INF && M < CUDART_INF) && (total > 0.0);
-        if (b == 0 && tid == 0) {
-            double *lzp = P.log_zetas + (size_t)f * P.T;
-            if (!ok) {
+        if (!ok) {
+            if (b == 0 && tid == 0) {
+                double *lzp = P.log_zetas + (size_t)f * P.T;
                 P.status[f] = p;                             // np.random.choice raises at step p (pmcmc.py:191-192)
                 for (int q = p; q < P.T; q++) lzp[q] = -CUDART_INF;
-            } else {
-                lz = lz + M + log(total) - log((double)N);  // zetas[p] = zetas[p-1] * mean(w), pmcmc.py:183
-                lzp[p] = lz;
             }
+            dead = true;
+            continue;
         }
-        if (!ok) { dead = true; continue; }
         __syncthreads();                                     // s_pfx / s_scale complete
+        // zetas[p] = zetas[p-1] * mean(w) (pmcmc.py:183), off the CTA's critical path: by the last thread, whose warp is
+        // a second-leg helper waiting for its hand-over in the balanced layout
+        if (b == 0 && tid == (int)blockDim.x - 1) {
+            lz = lz + M + log(total) - log((double)N);
+            P.log_zetas[(size_t)f * P.T + p] = lz;
+        }
         PHASE(2);
         long long pairs = 0;
         int32_t *Xr = Xf + (size_t)row * Model::C * N;
