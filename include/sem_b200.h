@@ -47,8 +47,10 @@ enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
  * fired event lifts the total propensity above B, that candidate's time is drawn from its order-statistic (Beta)
  * law and the rest of the interval restarts with a new bound.
  * FAST32 is FAST with 32-bit uniforms: event k of a particle-step takes two words of Philox call k/2 (u1 = words 0/2,
- * u2 = words 1/3), so one Philox4x32-10 call serves two events; all arithmetic stays fp64. */
-enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2, SEM_ARITH_FAST32 = 3 };
+ * u2 = words 1/3), so one Philox4x32-10 call serves two events; all arithmetic stays fp64.
+ * UNIFORMIZED32 is UNIFORMIZED with 32-bit candidate uniforms: candidate c takes word (c & 3) of Philox call c >> 2 (four
+ * candidates per call), and every interval is uniformized (no direct-method tail). */
+enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2, SEM_ARITH_FAST32 = 3, SEM_ARITH_UNIFORMIZED32 = 4 };
 
 enum {
     SEM_OK = 0,

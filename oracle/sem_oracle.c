@@ -44,7 +44,7 @@
 #define SO_MAX_R (SO_MAX_G * SO_MAX_G + SO_MAX_G)
 
 enum { M_SIR = 0, M_SEIR = 1, M_SUB = 2, M_SUB2 = 3 };
-enum { ARITH_REF = 0, ARITH_FAST = 1, ARITH_UNIF = 2, ARITH_FAST32 = 3 };
+enum { ARITH_REF = 0, ARITH_FAST = 1, ARITH_UNIF = 2, ARITH_FAST32 = 3, ARITH_UNIF32 = 4 };
 enum { DOM_SSA = 1, DOM_RESAMPLE = 2, DOM_INIT = 3, DOM_PATH = 4, DOM_ABC_PRIOR = 5, DOM_ABC_SSA = 6, DOM_SIM = 7, DOM_AUX = 8 };
 
 /* ------------------------------------------------------------------ Philox4x32-10 (Salmon et al., SC'11) */
@@ -188,11 +188,14 @@ static inline void model_apply(const so_model *m, double *x, int j) {
 /* Run the direct method until max_time or extinction.  Returns number of uniform PAIRS drawn (events incl. the
  * discarded overshoot, gillespie_algo.py:62-66).  If times/states given, records accepted events. */
 static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_stream *s);
+static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_stream *s);
 
 static int64_t ssa_run(const so_model *m, double *x, double max_time, int arith, so_stream *s,
                        double *times, double *states, int64_t max_rec, int64_t *n_rec) {
     if (arith == ARITH_UNIF && s->philox && !times) return ssa_run_unif(m, x, max_time, s);
+    if (arith == ARITH_UNIF32 && s->philox && !times) return ssa_run_unif32(m, x, max_time, s);
     if (arith == ARITH_UNIF) arith = ARITH_FAST;
+    if (arith == ARITH_UNIF32) arith = ARITH_FAST32;            /* event times only exist in the direct method */
     if (arith == ARITH_FAST32) { arith = ARITH_FAST; s->bits32 = s->philox; }   /* same arithmetic, 32-bit streams */
     double r[SO_MAX_R], cdf[SO_MAX_R];
     const int R = m->R, C = m->C;
@@ -425,6 +428,77 @@ static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_st
     return fired;
 }
 
+/* Uniformized interval with 32-bit candidates (arith 4; specification: the comment above ssa_unif32_leg in
+ * csrc/sem_common.cuh).  Candidate c of the particle-step = word (c & 3) of Philox call c >> 2 of the SSA stream,
+ * u = w / 2^32; bound B = max(a0(x), a0(x + drift * t_rem)) * (c0 + c1 / sqrt(a0 t_rem + 1)); K and the gammas of the
+ * restart time come from the DOM_AUX stream (52-bit pairs) as in ssa_run_unif; no direct-method tail. */
+static void model_drift(const so_model *m, const double *x, const double *r, double t, double *xp) {
+    if (m->model == M_SIR) {
+        double f0 = r[0] * t, f1 = r[1] * t;
+        xp[0] = fmax(x[0] - f0, 0.0); xp[1] = fmax(x[1] + (f0 - f1), 0.0); xp[2] = x[2];
+    } else if (m->model == M_SEIR) {
+        double f0 = r[0] * t, f1 = r[1] * t, f2 = r[2] * t;
+        xp[0] = fmax(x[0] - f0, 0.0); xp[1] = fmax(x[1] + (f0 - f1), 0.0); xp[2] = fmax(x[2] + (f1 - f2), 0.0); xp[3] = x[3];
+    } else {
+        int G = m->G;
+        for (int b = 0; b < G; b++) {
+            double inflow = 0.0;
+            for (int a = 0; a < G; a++) inflow = inflow + r[a * (G + 1) + b];
+            double fS = inflow * t, fR = r[b * (G + 1) + G] * t;
+            xp[3 * b] = fmax(x[3 * b] - fS, 0.0); xp[3 * b + 1] = fmax(x[3 * b + 1] + (fS - fR), 0.0); xp[3 * b + 2] = x[3 * b + 2];
+        }
+    }
+}
+
+static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_stream *s) {
+    const double c0 = 1.05, c1 = 2.0;                         /* SEM_U32_C0 / SEM_U32_C1 */
+    so_stream aux = *s;
+    aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
+    const int R = m->R;
+    double r[SO_MAX_R], rp[SO_MAX_R], xp[SO_MAX_C], N = model_popsize(m, x), invN = 1.0 / N, t_rem = max_time;
+    int64_t fired = 0;
+    uint32_t cand = 0;
+    while (model_alive(m, x)) {
+        double a0 = 0, a0p = 0;
+        model_rates_fast(m, x, invN, r);
+        for (int i = 0; i < R; i++) a0 = a0 + r[i];
+        if (!(a0 > 0)) break;
+        double expect = a0 * t_rem;
+        model_drift(m, x, r, t_rem, xp);
+        model_rates_fast(m, xp, invN, rp);
+        for (int i = 0; i < R; i++) a0p = a0p + rp[i];
+        double amax = a0p > a0 ? a0p : a0;
+        double B = amax * (c0 + c1 / sqrt(expect + 1.0));
+        double Kd = poisson_draw(&aux, B * t_rem);
+        uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+        uint32_t first = cand, last = cand + K;
+        int violated = 0;
+        while (cand < last) {
+            uint32_t ctr[4] = {cand >> 2, s->c1, s->c2, s->c3}, w[4];
+            so_philox4x32(ctr, s->key, w);
+            double u = (double)w[cand & 3u] * (1.0 / 4294967296.0);
+            cand++;
+            double v = fma(u + 1.0, B, -B);                    /* u*B with one rounding, as the kernel's fma(d,B,-B) */
+            if (v < a0) {
+                double acc = r[0]; int j = (acc <= v);
+                for (int i = 1; i < R - 1; i++) { acc = acc + r[i]; j += (acc <= v); }
+                model_apply(m, x, j);
+                fired++;
+                model_rates_fast(m, x, invN, r);
+                a0 = 0; for (int i = 0; i < R; i++) a0 = a0 + r[i];
+                if (!(a0 > 0 && a0 <= B)) { violated = a0 > B; break; }
+            }
+        }
+        if (!violated) break;
+        uint32_t done = cand - first;
+        double g1 = gamma_draw(&aux, (double)done), g2 = gamma_draw(&aux, (double)(K - done) + 1.0);
+        t_rem = t_rem - t_rem * (g1 / (g1 + g2));
+        if (!(t_rem > 0)) break;
+    }
+    s->k = (cand + 3) >> 2;
+    return fired;
+}
+
 /* ------------------------------------------------------------------ particle filter */
 typedef struct {
     int32_t model, obs_kind, resampler /*0 multinomial, 1 systematic*/, arith, philox;
@@ -588,7 +662,7 @@ int so_abc_trials(const so_abc_cfg *cfg, const double *obs, int64_t n_trials, ui
             gamma = cfg->prior[2] + (cfg->prior[3] - cfg->prior[2]) * u2;     /* :37 */
             for (int c = 0; c < 3; c++) x[c] = poisson_draw(&ps, (double)(int64_t)obs[c]);   /* :39-40 */
             philox_stream(&s, cfg->seed, (uint32_t)id, (uint32_t)(id >> 32), DOM_ABC_SSA, 0);
-            s.bits32 = (cfg->arith == ARITH_FAST32);
+            s.bits32 = (cfg->arith == ARITH_FAST32 || cfg->arith == ARITH_UNIF32);   /* (the ABC loop needs event times: direct method) */
         } else {
             beta = theta_in[2 * i]; gamma = theta_in[2 * i + 1];
             for (int c = 0; c < 3; c++) x[c] = (double)n_start_in[3 * i + c];

@@ -308,6 +308,14 @@ struct SirModel {
         if (TRACK_R) x[2] = x[2] + (inf ? 0.0 : 1.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[2] = N - x[0] - x[1]; }
+    // state after the expected net change over a time t (Euler step of the mean-field drift, clamped at 0): the
+    // uniformized interval uses it to anticipate growth of the total propensity
+    __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
+        const double f0 = __dmul_rn(r[0], t), f1 = __dmul_rn(r[1], t);
+        xp[0] = fmax(__dsub_rn(x[0], f0), 0.0);
+        xp[1] = fmax(__dadd_rn(x[1], __dsub_rn(f0, f1)), 0.0);
+        xp[2] = x[2];
+    }
 };
 
 struct SeirModel {
@@ -334,6 +342,13 @@ struct SeirModel {
         if (TRACK_R) x[3] = x[3] + ((j == 2) ? 1.0 : 0.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[3] = N - x[0] - x[1] - x[2]; }
+    __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
+        const double f0 = __dmul_rn(r[0], t), f1 = __dmul_rn(r[1], t), f2 = __dmul_rn(r[2], t);
+        xp[0] = fmax(__dsub_rn(x[0], f0), 0.0);
+        xp[1] = fmax(__dadd_rn(x[1], __dsub_rn(f0, f1)), 0.0);
+        xp[2] = fmax(__dadd_rn(x[2], __dsub_rn(f1, f2)), 0.0);
+        xp[3] = x[3];
+    }
 };
 
 template <int G_>
@@ -391,6 +406,18 @@ struct SubModel {
     __device__ __forceinline__ void fix_removed(double *x) const {
 #pragma unroll
         for (int g = 0; g < G; g++) x[3 * g + 2] = Ng[g] - x[3 * g] - x[3 * g + 1];
+    }
+    __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
+#pragma unroll
+        for (int b = 0; b < G; b++) {
+            double inflow = 0.0;                                          // new infections of group b, from every infector group
+#pragma unroll
+            for (int a = 0; a < G; a++) inflow = __dadd_rn(inflow, r[a * (G + 1) + b]);
+            const double fS = __dmul_rn(inflow, t), fR = __dmul_rn(r[b * (G + 1) + G], t);
+            xp[3 * b] = fmax(__dsub_rn(x[3 * b], fS), 0.0);
+            xp[3 * b + 1] = fmax(__dadd_rn(x[3 * b + 1], __dsub_rn(fS, fR)), 0.0);
+            xp[3 * b + 2] = x[3 * b + 2];
+        }
     }
 };
 
@@ -699,6 +726,7 @@ struct UnifTuning { double c0, c1, direct_below; };
 // B = a0 * (c0 + c1 / sqrt(a0 * t_rem + 1)); intervals expecting fewer than direct_below events use the direct method
 __device__ __forceinline__ UnifTuning unif_tuning() { return UnifTuning{1.25, 3.0, 2.0}; }
 
+
 // one candidate of the thinned stream, branch-free: returns true when the batch must stop (absorbed or bound violated)
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ bool unif_candidate(const Model &m, double *x, double *r, double &a0, const double B, const double d,
@@ -759,6 +787,104 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
     return total_fired;
 }
 
+// Uniformized interval with 32-bit candidate uniforms (SEM_ARITH_UNIFORMIZED32).  Candidate c of a particle-step takes
+// word (c & 3) of Philox call c >> 2, so one call serves FOUR candidates (a candidate needs one uniform: is it a real
+// event, and which).  A group of four candidates is straight-line code: once the batch has to stop (absorbed state,
+// bound violated, K reached) the remaining candidates of the group are predicated off and their words are served again
+// after the restart.  The bound anticipates growth: B = max(a0(x), a0(x + expected drift over t_rem)) * (c0 + c1 /
+// sqrt(expected events + 1)).  Every interval is uniformized (no direct-method tail).
+// The loop is re-entrant (Unif32State) so that two warps can share one particle's interval: with `handoff` the call
+// returns false -- at a group boundary, once half of the current batch's candidates are served -- and a second call
+// with the same state finishes the interval (pf_persistent's scheduler balancing).
+#ifndef SEM_U32_C0
+#define SEM_U32_C0 1.05
+#define SEM_U32_C1 2.0
+#endif
+struct Unif32State { double t_rem, B; uint32_t cand, first, last, aux_k; int in_batch; };
+
+__device__ __forceinline__ void unif32_begin(Unif32State &st, double max_time) {
+    st.t_rem = max_time; st.B = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
+}
+
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32State &st, long long &fired_total, const bool handoff,
+                                               PairSource<false> &src, PairSource<false> &aux, const double2 *tab) {
+    PairSource<false> loc = src;
+    aux.k = st.aux_k;
+    bool finished = true;
+    for (;;) {
+        double r[Model::R], a0;
+        if (!st.in_batch) {
+            if (!m.alive(x)) break;
+            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+            if (!(a0 > 0)) break;
+            const double expect = __dmul_rn(a0, st.t_rem);
+            double xp[Model::C], rp[Model::R];
+            m.drift(x, r, st.t_rem, xp);
+            const double a0p = ssa_total<Model, SEM_ARITH_FAST>(m, xp, rp);
+            const double amax = a0p > a0 ? a0p : a0;
+            st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
+            const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.t_rem));
+            const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+            st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
+        } else {
+            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed by the second leg
+        }
+        const double B = st.B;
+        const uint32_t last = st.last, half = st.first + ((st.last - st.first) >> 1);
+        uint32_t cand = st.cand;
+        int fired = 0;
+        bool stop = false, pass = false;
+        while (cand < last && !stop) {
+            if (handoff && cand >= half && (cand & 3u) == 0u) { pass = true; break; }
+            loc.k = cand >> 2;
+            const uint4 w = loc.raw();
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+            const uint32_t base = cand & ~3u;
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint32_t c = base + q;
+                const bool live = !stop && c >= cand && c < last;      // (c >= cand: words already served before a restart)
+                const double v = __fma_rn(word_to_d12(words[q]), B, -B);   // u * B
+                const bool hit = live && v < a0;
+                double acc = r[0];
+                int j = (acc <= v) ? 1 : 0;
+#pragma unroll
+                for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
+                if (hit) m.template apply<TRACK_R>(x, j);
+                fired += hit ? 1 : 0;
+                a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+                stop = stop || (hit && !(a0 > 0 && a0 <= B));          // absorbed (a0 = 0) or bound violated
+                cand += live ? 1u : 0u;
+            }
+        }
+        st.cand = cand;
+        fired_total += fired;
+        if (pass) { finished = false; break; }
+        if (!(stop && a0 > B)) break;                                  // not violated: the batch covered the rest of the interval
+        // the bound held up to candidate `done`; its time is the done-th order statistic of K uniforms on [0, t_rem]
+        const uint32_t done = cand - st.first, K = st.last - st.first;
+        const double g1 = gamma_draw(aux, (double)done), g2 = gamma_draw(aux, (double)(K - done) + 1.0);
+        st.t_rem = __dsub_rn(st.t_rem, __dmul_rn(st.t_rem, __ddiv_rn(g1, __dadd_rn(g1, g2))));
+        st.in_batch = 0;
+        if (!(st.t_rem > 0)) break;
+    }
+    st.aux_k = aux.k;
+    src.k = loc.k;
+    if (finished && !TRACK_R) m.fix_removed(x);
+    return finished;
+}
+
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ long long ssa_run_unif32(const Model &m, double *x, double max_time, PairSource<false> &src,
+                                                    PairSource<false> &aux, const double2 *tab) {
+    Unif32State st;
+    unif32_begin(st, max_time);
+    long long fired = 0;
+    ssa_unif32_leg<Model, TRACK_R>(m, x, st, fired, false, src, aux, tab);
+    return fired;
+}
+
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,
                                              const double2 *tab, Rec rec) {
@@ -770,6 +896,10 @@ __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double m
     else if constexpr (ARITH == SEM_ARITH_UNIFORMIZED && !REPLAY) {
         PairSource<false> aux; aux.init(*src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
         return ssa_run_unif<Model, TRACK_R>(m, x, max_time, src, aux, tab);
+    }
+    else if constexpr (ARITH == SEM_ARITH_UNIFORMIZED32 && !REPLAY) {
+        PairSource<false> aux; aux.init(*src.key, src.c1, src.c2, (src.c3 & 0xFFFFFFu) | (DOM_AUX << 24));
+        return ssa_run_unif32<Model, TRACK_R>(m, x, max_time, src, aux, tab);
     }
     else return ssa_run_ref<Model, REPLAY>(m, x, max_time, src, rec);
 }

@@ -736,6 +736,7 @@ static void launch_model(const PfDev &P, int p, int arith, bool replay, dim3 gri
     else if (arith == SEM_ARITH_REFERENCE) pf_step<Model, SEM_ARITH_REFERENCE, false><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_UNIFORMIZED) pf_step<Model, SEM_ARITH_UNIFORMIZED, false><<<grid, threads, smem, s>>>(P, p);
     else if (arith == SEM_ARITH_FAST32) pf_step<Model, SEM_ARITH_FAST32, false><<<grid, threads, smem, s>>>(P, p);
+    else if (arith == SEM_ARITH_UNIFORMIZED32) pf_step<Model, SEM_ARITH_UNIFORMIZED32, false><<<grid, threads, smem, s>>>(P, p);
     else pf_step<Model, SEM_ARITH_FAST, false><<<grid, threads, smem, s>>>(P, p);
 }
 
@@ -830,6 +831,7 @@ template <class Model>
 static const void *persistent_fn(int arith) {
     return arith == SEM_ARITH_REFERENCE ? (const void *)pf_persistent<Model, SEM_ARITH_REFERENCE>
            : arith == SEM_ARITH_FAST32  ? (const void *)pf_persistent<Model, SEM_ARITH_FAST32>
+           : arith == SEM_ARITH_UNIFORMIZED32 ? (const void *)pf_persistent<Model, SEM_ARITH_UNIFORMIZED32>
                                         : (const void *)pf_persistent<Model, SEM_ARITH_FAST>;
 }
 static const void *persistent_kernel(const sem_pf_config *cfg) {

@@ -78,18 +78,20 @@ __global__ void __launch_bounds__(128) sim_kernel(const __grid_constant__ SimDev
     if constexpr (REPLAY) src.init(P.replay_u, P.replay_off[i], P.replay_off[i + 1]);
     else src.init(P.key, P.sim0 + (uint32_t)i, 0u, stream_word(DOM_SIM, 0));
     long long rows = 1;
+    // event times / daily states only exist in the direct method: the uniformized orders log with their direct counterpart
+    constexpr int kLogArith = ARITH == SEM_ARITH_UNIFORMIZED ? SEM_ARITH_FAST : ARITH == SEM_ARITH_UNIFORMIZED32 ? SEM_ARITH_FAST32 : ARITH;
     if (P.daily > 0) {
         DailyLog<Model::C> log;
         log.rows = P.states + (size_t)i * P.daily * Model::C; log.H = P.daily; log.day = 1;
 #pragma unroll
         for (int c = 0; c < Model::C; c++) log.prev[c] = x[c];
-        const long long pr = ssa_run<Model, ARITH == SEM_ARITH_UNIFORMIZED ? SEM_ARITH_FAST : ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, DailyLogRef<Model::C>{&log});
+        const long long pr = ssa_run<Model, kLogArith, REPLAY, true>(m, x, P.max_time, src, s_tab, DailyLogRef<Model::C>{&log});
         log.flush_to(1e300);                                              // forward fill to the horizon
         rows = pr < 0 ? -1 : P.daily;
     } else if (P.cap > 0) {
         EventLog<Model::C> log{P.times + (size_t)i * P.cap, P.states + (size_t)i * P.cap * Model::C, P.cap, 0};
         log(0.0, x);                                                      // row 0 = initial state at time 0 (gillespie_algo.py:28-33)
-        const long long pr = ssa_run<Model, ARITH == SEM_ARITH_UNIFORMIZED ? SEM_ARITH_FAST : ARITH, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
+        const long long pr = ssa_run<Model, kLogArith, REPLAY, true>(m, x, P.max_time, src, s_tab, EventLogRef<Model::C>{&log});
         rows = pr < 0 ? -1 : log.n;
     } else {
         const long long pr = ssa_run<Model, ARITH, REPLAY, false>(m, x, P.max_time, src, s_tab, NoRec());
@@ -107,7 +109,9 @@ static void launch_sim(const SimDev &P, int arith, bool replay, cudaStream_t s) 
     else if (arith == SEM_ARITH_REFERENCE) sim_kernel<Model, SEM_ARITH_REFERENCE, false><<<blocks, threads, 0, s>>>(P);
     else if (arith == SEM_ARITH_UNIFORMIZED && P.cap == 0 && P.daily == 0)      // no event times exist to log
         sim_kernel<Model, SEM_ARITH_UNIFORMIZED, false><<<blocks, threads, 0, s>>>(P);
-    else if (arith == SEM_ARITH_FAST32) sim_kernel<Model, SEM_ARITH_FAST32, false><<<blocks, threads, 0, s>>>(P);
+    else if (arith == SEM_ARITH_UNIFORMIZED32 && P.cap == 0 && P.daily == 0)
+        sim_kernel<Model, SEM_ARITH_UNIFORMIZED32, false><<<blocks, threads, 0, s>>>(P);
+    else if (arith == SEM_ARITH_FAST32 || arith == SEM_ARITH_UNIFORMIZED32) sim_kernel<Model, SEM_ARITH_FAST32, false><<<blocks, threads, 0, s>>>(P);
     else sim_kernel<Model, SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);
 }
 
@@ -334,7 +338,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     const int threads = 128;
     const void *fn = replay ? (const void *)abc_kernel<SEM_ARITH_REFERENCE, true>
                      : cfg->arith == SEM_ARITH_REFERENCE ? (const void *)abc_kernel<SEM_ARITH_REFERENCE, false>
-                     : cfg->arith == SEM_ARITH_FAST32 ? (const void *)abc_kernel<SEM_ARITH_FAST32, false>
+                     : (cfg->arith == SEM_ARITH_FAST32 || cfg->arith == SEM_ARITH_UNIFORMIZED32) ? (const void *)abc_kernel<SEM_ARITH_FAST32, false>
                                                       : (const void *)abc_kernel<SEM_ARITH_FAST, false>;   // (UNIFORMIZED: the ABC loop needs event times)
     int per_sm = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }

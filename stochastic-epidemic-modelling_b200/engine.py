@@ -14,7 +14,7 @@ from . import _lib
 
 MODEL_NAMES = {"sir": 0, "seir": 1, "sir_subgroups": 2, "sir_subgroups2": 3}
 RESAMPLERS = {"multinomial": 0, "systematic": 1}
-ARITH = {"reference": 0, "fast": 1, "uniformized": 2, "fast32": 3}
+ARITH = {"reference": 0, "fast": 1, "uniformized": 2, "fast32": 3, "uniformized32": 4}
 
 
 def require_cuda(device=None):

@@ -231,6 +231,13 @@ PHILOX_CASES = [
     (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 3, 0),
     (2, 4, [3, 1, .5, .2, .3, 2, 1, 1, .7, .2, 4, .8, .1, .6, .9, 2.5, .8], [200, 300, 150, 250], [5, 8, 4, 6], 500, 6, False, .2, 1, 3, 0),
     (2, 4, [3, 1, .5, .2, .3, 2, 1, 1, .7, .2, 4, .8, .1, .6, .9, 2.5, .8], [200, 300, 150, 250], [5, 8, 4, 6], 500, 6, False, .2, 1, 1, 0),
+    # uniformized intervals with 32-bit candidates and the drift-anticipating bound (arith 4)
+    (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 4, 0),
+    (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 0, 4, 96),
+    (0, 1, [0.5, 3.0], [300], [3], 777, 8, False, .5, 0, 4, 0),          # many extinctions
+    (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1500, 8, False, .1, 1, 4, 0),
+    (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1200, 7, False, .1, 1, 4, 32),
+    (2, 3, [3, 1, .5, .2, 2, 1, 1, .7, 4, .8], [200, 300, 150], [5, 8, 4], 600, 6, False, .2, 1, 4, 0),
     # uniformized intervals (arith 2): exact law without waiting times, bit-checked against the oracle's statement
     (0, 1, [2.0, 1.0], [1000], [20], 2000, 10, False, .1, 1, 2, 0),
     (0, 1, [2.0, 1.0], [1000], [20], 1999, 8, True, .1, 0, 2, 96),
@@ -476,21 +483,23 @@ def test_predict_forward_daily_states(sem, c_oracle):
             assert np.array_equal(out[i, d - 1], ref["states"][k].astype(np.int32)), (i, d)
 
 
-def test_uniformized_headline_workload_vs_oracle(sem, c_oracle):
-    """arith='uniformized' on the BASELINE workload shape (pop 1e4, 101 rows) at 8000 particles: exact match with the
-    oracle, and the likelihood estimate agrees with the direct method's within Monte-Carlo error."""
+@pytest.mark.parametrize("unif", [2, 4])
+def test_uniformized_headline_workload_vs_oracle(sem, c_oracle, unif):
+    """arith='uniformized' / 'uniformized32' on the BASELINE workload shape (pop 1e4, 101 rows) at 8000 particles: exact
+    match with the oracle, and the likelihood estimate agrees with the direct method's within Monte-Carlo error."""
     import torch
     N, T, pop = 8000, 101, 10_000
     Y = bench_truth(T, pop)
-    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=2, seed=31, mu=[20], n_population=[pop])
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=unif, seed=31, mu=[20], n_population=[pop])
     r = sem.engine.run_pf(cfg, Y, np.array([.4, .2]))
-    o = c_oracle.pf_run(0, Y, [.4, .2], False, .1, N, resampler=1, arith=2, seed=31, mu=[20], npop=[pop])
+    o = c_oracle.pf_run(0, Y, [.4, .2], False, .1, N, resampler=1, arith=unif, seed=31, mu=[20], npop=[pop])
     torch.cuda.synchronize()
     assert np.array_equal(r.ancestry[0].cpu().numpy(), o["ancestry"])
     assert np.array_equal(r.X_hist[0].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
     np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
-    lz = {a: [] for a in (1, 2)}
-    for a in (1, 2):
+    lz = {a: [] for a in (1, unif)}
+    lz[2] = lz[unif]
+    for a in (1, unif):
         for sd in range(6):
             c = sem.engine.make_pf_config(0, 20000, T, probs=.1, resampler=1, arith=a, seed=100 + sd, mu=[20], n_population=[pop])
             lz[a].append(float(sem.engine.run_pf(c, Y, np.array([.4, .2])).log_zetas[0, -1].cpu()))
@@ -509,7 +518,7 @@ def test_logz_distribution_vs_reference(sem):
     N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
     ref = g["zetas_last"]
     runs = 1200
-    for resampler, arith in [(0, 3), (1, 3), (0, 1), (0, 0), (1, 1), (0, 2)]:       # 3 = fast32, the production default
+    for resampler, arith in [(0, 3), (1, 3), (0, 4), (1, 4), (0, 1), (0, 0), (1, 1), (0, 2)]:   # 3 = fast32, the production default
         cfg = sem.engine.make_pf_config(0, N, len(g["Y"]), n_filters=runs, probs=float(g["probs"]), resampler=resampler,
                                         arith=arith, seed=2024 + 7 * resampler + arith, mu=[mu], n_population=[npop])
         res = sem.engine.run_pf(cfg, g["Y"], np.tile(g["theta"], (runs, 1)))
@@ -603,6 +612,7 @@ def test_seir_hidden_exposed_column(sem, c_oracle):
 @pytest.mark.parametrize("model,G,theta,npop,mu,arith", [(0, 1, [2.0, 1.0], [1000], [20], 1), (0, 1, [2.0, 1.0], [1000], [20], 0),
                                                           (1, 1, [4.0, 1.0, 1.0], [1000], [20], 1), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 1),
                                                           (0, 1, [2.0, 1.0], [1000], [20], 3), (1, 1, [4.0, 1.0, 1.0], [1000], [20], 3),
+                                                          (0, 1, [2.0, 1.0], [1000], [20], 4), (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 4),
                                                           (3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 3)])
 def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, npop, mu, arith):
     """The whole-filter cooperative kernel (grid.sync() as the resampling barrier) and the launch-per-step path are

@@ -178,7 +178,7 @@ def test_oracle_philox_logz_distribution_vs_reference(c_oracle):
     g = golden("stat_logz_sir")
     N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
     ref = g["zetas_last"]
-    for arith in (0, 1, 2, 3):
+    for arith in (0, 1, 2, 3, 4):
         z = np.array([np.exp(c_oracle.pf_run(0, g["Y"], g["theta"], False, float(g["probs"]), N, resampler=0, arith=arith,
                                              seed=1000 + s, mu=[mu], npop=[npop])["log_zetas"][-1]) for s in range(300)])
         se = np.sqrt(ref.var() / ref.size + z.var() / z.size)

@@ -37,7 +37,12 @@ __global__ void __launch_bounds__(768) k_loop(const double *theta, const int32_t
         else if constexpr (V == 2) pairs = ssa_run_spec<SirModel, 4, false, false>(m, x, dt, src, s_tab, NoRec());
         else if constexpr (V == 3) pairs = ssa_run_spec<SirModel, 2, true, false>(m, x, dt, src, s_tab, NoRec());
         else if constexpr (V == 4) pairs = ssa_run_spec<SirModel, 4, true, false>(m, x, dt, src, s_tab, NoRec());
-        else pairs = ssa_run_spec<SirModel, 6, true, false>(m, x, dt, src, s_tab, NoRec());
+        else if constexpr (V == 5) pairs = ssa_run_spec<SirModel, 6, true, false>(m, x, dt, src, s_tab, NoRec());
+        else {
+            PairSource<false> aux; aux.init(key, (uint32_t)j, (uint32_t)rep, stream_word(DOM_AUX, 0));
+            if constexpr (V == 6) pairs = ssa_run_unif<SirModel, false>(m, x, dt, src, aux, s_tab);
+            else pairs = ssa_run_unif32<SirModel, false>(m, x, dt, src, aux, s_tab);
+        }
         my += (unsigned long long)pairs;
         xo[0] += x[0]; xo[1] += x[1]; xo[2] += x[2];
     }
@@ -100,6 +105,9 @@ int main(int argc, char **argv) {
         run<3>(w, d_theta, d_X0, d_out, d_ev, reps, &c0);
         run<4>(w, d_theta, d_X0, d_out, d_ev, reps, &c); if (c != c0) printf("   MISMATCH v4\n");
         run<5>(w, d_theta, d_X0, d_out, d_ev, reps, &c); if (c != c0) printf("   MISMATCH v5\n");
+        run<6>(w, d_theta, d_X0, d_out, d_ev, reps, &c);      // uniformized, 52-bit candidates (2 per call)
+        run<7>(w, d_theta, d_X0, d_out, d_ev, reps, &c);      // uniformized, 32-bit candidates (4 per call), drift-anticipating bound
+
     }
     return 0;
 }
