@@ -451,7 +451,7 @@ static void model_drift(const so_model *m, const double *x, const double *r, dou
 }
 
 static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_stream *s) {
-    const double c0 = 1.05, c1 = 2.0;                         /* SEM_U32_C0 / SEM_U32_C1 */
+    const double c0 = 1.0, c1 = 2.0;                          /* SEM_U32_C0 / SEM_U32_C1 */
     so_stream aux = *s;
     aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
     const int R = m->R;

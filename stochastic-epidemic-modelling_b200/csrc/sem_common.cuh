@@ -797,7 +797,7 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
 // returns false -- at a group boundary, once half of the current batch's candidates are served -- and a second call
 // with the same state finishes the interval (pf_persistent's scheduler balancing).
 #ifndef SEM_U32_C0
-#define SEM_U32_C0 1.05
+#define SEM_U32_C0 1.0
 #define SEM_U32_C1 2.0
 #endif
 struct Unif32State { double t_rem, B; uint32_t cand, first, last, aux_k; int in_batch; };
@@ -871,7 +871,7 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
     }
     st.aux_k = aux.k;
     src.k = loc.k;
-    if (finished && !TRACK_R) m.fix_removed(x);
+    if (!TRACK_R) m.fix_removed(x);                                      // (also on a hand-over: the next leg's setup sums the state)
     return finished;
 }
 
