@@ -451,7 +451,7 @@ static void model_drift(const so_model *m, const double *x, const double *r, dou
 }
 
 static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_stream *s) {
-    const double c0 = 1.0, c1 = 2.0;                          /* SEM_U32_C0 / SEM_U32_C1 */
+    const double c0 = 1.0, c1 = 2.0, gmax = 1.25;             /* SEM_U32_C0 / SEM_U32_C1 / SEM_U32_GMAX */
     so_stream aux = *s;
     aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
     const int R = m->R;
@@ -463,16 +463,17 @@ static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_
         model_rates_fast(m, x, invN, r);
         for (int i = 0; i < R; i++) a0 = a0 + r[i];
         if (!(a0 > 0)) break;
-        double expect = a0 * t_rem;
         model_drift(m, x, r, t_rem, xp);
         model_rates_fast(m, xp, invN, rp);
         for (int i = 0; i < R; i++) a0p = a0p + rp[i];
-        double amax = a0p > a0 ? a0p : a0;
+        double amax = a0p > a0 ? a0p : a0, h = t_rem, cap = gmax * a0;
+        if (amax > cap) { h = t_rem * ((cap - a0) / (a0p - a0)); amax = cap; }     /* fast growth: a shorter batch */
+        double expect = a0 * h;
         double B = amax * (c0 + c1 / sqrt(expect + 1.0));
-        double Kd = poisson_draw(&aux, B * t_rem);
+        double Kd = poisson_draw(&aux, B * h);
         uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
         uint32_t first = cand, last = cand + K;
-        int violated = 0;
+        int violated = 0, absorbed = 0;
         while (cand < last) {
             uint32_t ctr[4] = {cand >> 2, s->c1, s->c2, s->c3}, w[4];
             so_philox4x32(ctr, s->key, w);
@@ -486,13 +487,17 @@ static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_
                 fired++;
                 model_rates_fast(m, x, invN, r);
                 a0 = 0; for (int i = 0; i < R; i++) a0 = a0 + r[i];
-                if (!(a0 > 0 && a0 <= B)) { violated = a0 > B; break; }
+                if (!(a0 > 0 && a0 <= B)) { violated = a0 > B; absorbed = !violated; break; }
             }
         }
-        if (!violated) break;
+        if (!violated) {                                       /* the batch covered its h exactly */
+            if (absorbed || !(h < t_rem)) break;
+            t_rem = t_rem - h;
+            continue;
+        }
         uint32_t done = cand - first;
         double g1 = gamma_draw(&aux, (double)done), g2 = gamma_draw(&aux, (double)(K - done) + 1.0);
-        t_rem = t_rem - t_rem * (g1 / (g1 + g2));
+        t_rem = t_rem - h * (g1 / (g1 + g2));
         if (!(t_rem > 0)) break;
     }
     s->k = (cand + 3) >> 2;

@@ -791,19 +791,22 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
 // word (c & 3) of Philox call c >> 2, so one call serves FOUR candidates (a candidate needs one uniform: is it a real
 // event, and which).  A group of four candidates is straight-line code: once the batch has to stop (absorbed state,
 // bound violated, K reached) the remaining candidates of the group are predicated off and their words are served again
-// after the restart.  The bound anticipates growth: B = max(a0(x), a0(x + expected drift over t_rem)) * (c0 + c1 /
-// sqrt(expected events + 1)).  Every interval is uniformized (no direct-method tail).
+// after the restart.  The bound anticipates growth: B = max(a0(x), a0(x + expected drift over h)) * (c0 + c1 /
+// sqrt(expected events + 1)), and a batch covers h <= t_rem chosen so that the anticipated growth stays below GMAX (fast
+// epidemics take several batches per interval; a batch that completes without violating its bound has covered exactly h).
+// Every interval is uniformized (no direct-method tail).
 // The loop is re-entrant (Unif32State) so that two warps can share one particle's interval: with `handoff` the call
 // returns false -- at a group boundary, once half of the current batch's candidates are served -- and a second call
 // with the same state finishes the interval (pf_persistent's scheduler balancing).
 #ifndef SEM_U32_C0
 #define SEM_U32_C0 1.0
 #define SEM_U32_C1 2.0
+#define SEM_U32_GMAX 1.25          /* largest anticipated growth of the total propensity within one batch */
 #endif
-struct Unif32State { double t_rem, B; uint32_t cand, first, last, aux_k; int in_batch; };
+struct Unif32State { double t_rem, h, B; uint32_t cand, first, last, aux_k; int in_batch; };
 
 __device__ __forceinline__ void unif32_begin(Unif32State &st, double max_time) {
-    st.t_rem = max_time; st.B = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
+    st.t_rem = max_time; st.h = max_time; st.B = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
 }
 
 template <class Model, bool TRACK_R>
@@ -818,13 +821,19 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
             if (!m.alive(x)) break;
             a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
             if (!(a0 > 0)) break;
-            const double expect = __dmul_rn(a0, st.t_rem);
             double xp[Model::C], rp[Model::R];
             m.drift(x, r, st.t_rem, xp);
             const double a0p = ssa_total<Model, SEM_ARITH_FAST>(m, xp, rp);
-            const double amax = a0p > a0 ? a0p : a0;
+            double amax = a0p > a0 ? a0p : a0;
+            st.h = st.t_rem;
+            const double cap = __dmul_rn(SEM_U32_GMAX, a0);
+            if (amax > cap) {                                             // fast growth: a shorter batch, so that the (linearised)
+                st.h = __dmul_rn(st.t_rem, __ddiv_rn(__dsub_rn(cap, a0), __dsub_rn(a0p, a0)));   // drift lifts a0 by GMAX at most
+                amax = cap;
+            }
+            const double expect = __dmul_rn(a0, st.h);
             st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
-            const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.t_rem));
+            const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.h));
             const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
             st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
         } else {
@@ -861,12 +870,16 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
         st.cand = cand;
         fired_total += fired;
         if (pass) { finished = false; break; }
-        if (!(stop && a0 > B)) break;                                  // not violated: the batch covered the rest of the interval
-        // the bound held up to candidate `done`; its time is the done-th order statistic of K uniforms on [0, t_rem]
+        st.in_batch = 0;
+        if (!(stop && a0 > B)) {                                       // not violated: the batch covered its h exactly
+            if (stop || !(st.h < st.t_rem)) break;                     // absorbed, or h was the rest of the interval
+            st.t_rem = __dsub_rn(st.t_rem, st.h);
+            continue;
+        }
+        // the bound held up to candidate `done`; its time is the done-th order statistic of K uniforms on [0, h]
         const uint32_t done = cand - st.first, K = st.last - st.first;
         const double g1 = gamma_draw(aux, (double)done), g2 = gamma_draw(aux, (double)(K - done) + 1.0);
-        st.t_rem = __dsub_rn(st.t_rem, __dmul_rn(st.t_rem, __ddiv_rn(g1, __dadd_rn(g1, g2))));
-        st.in_batch = 0;
+        st.t_rem = __dsub_rn(st.t_rem, __dmul_rn(st.h, __ddiv_rn(g1, __dadd_rn(g1, g2))));
         if (!(st.t_rem > 0)) break;
     }
     st.aux_k = aux.k;
