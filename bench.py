@@ -248,7 +248,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--particles", type=int, default=None, help="override n_particles (not the headline then)")
     ap.add_argument("--resampler", default="systematic")
-    ap.add_argument("--arith", default="fast32")
+    ap.add_argument("--arith", default="auto", help="auto = uniformized32 for SIR/SEIR filters, fast32 otherwise (and for ABC)")
     ap.add_argument("--block", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -261,6 +261,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
+    from sem_b200 import engine as _engine            # report the resolved interval simulation, not "auto"
+    args.arith = _engine.ARITH_NAMES[_engine.resolve_arith({"pf": 0, "abc": None, "sharded": 3}[args.workload], args.arith)]
     if args.workload == "abc":
         return run_abc(args)
     if args.workload == "sharded":

@@ -15,6 +15,16 @@ from . import _lib
 MODEL_NAMES = {"sir": 0, "seir": 1, "sir_subgroups": 2, "sir_subgroups2": 3}
 RESAMPLERS = {"multinomial": 0, "systematic": 1}
 ARITH = {"reference": 0, "fast": 1, "uniformized": 2, "fast32": 3, "uniformized32": 4}
+ARITH_NAMES = {v: k for k, v in ARITH.items()}
+
+
+def resolve_arith(model, arith):
+    """'auto' (the filters' default) = the fastest exact interval simulation measured for the model family: uniformized
+    intervals with 32-bit candidates for SIR / SEIR (2-3 reactions), the direct method with 32-bit streams for the
+    subgroup models (their G^2+G propensities make a uniformized candidate as dear as a direct event)."""
+    if arith == "auto":            # (model None: simulations with event logs and ABC trials need event times -> direct method)
+        return ARITH["uniformized32"] if model in (0, 1) else ARITH["fast32"]
+    return ARITH.get(arith, arith)
 
 
 def require_cuda(device=None):
@@ -83,12 +93,12 @@ class PfResult:
         return traj
 
 
-def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="fast32",
+def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="auto",
                    seed=0, filter_id0=0, mu=None, n_population=None, dt=1.0, store_history=True, block_particles=0,
                    launch_per_step=False, path_exact=False):
     Cn, P, Cobs = model_dims(model, G)
     cfg = _lib.PfConfig(model=model, obs_kind=int(bool(observations)), resampler=RESAMPLERS.get(resampler, resampler),
-                        arith=ARITH.get(arith, arith), n_particles=int(N), n_obs=int(T), n_groups=int(G),
+                        arith=resolve_arith(model, arith), n_particles=int(N), n_obs=int(T), n_groups=int(G),
                         n_obs_cols=Cobs, n_filters=int(n_filters), block_particles=int(block_particles),
                         store_history=int(bool(store_history)), reserved=int(bool(launch_per_step)), probs=float(probs),
                         dt=float(dt), path_exact=int(bool(path_exact)),
@@ -187,7 +197,7 @@ def simulate(model, x0, theta, max_time, G=1, arith="fast32", seed=0, sim_index0
             n = len(replay["off"]) - 1
         elif n_sims is not None:
             n = int(n_sims)
-        cfg = _lib.SimConfig(model=model, n_groups=G, arith=ARITH.get(arith, arith), n_sims=n,
+        cfg = _lib.SimConfig(model=model, n_groups=G, arith=resolve_arith(None, arith), n_sims=n,
                              shared_theta=int(shared_th), shared_x0=int(shared_x0), record_capacity=int(record_capacity),
                              max_time=float(max_time), seed=int(seed) & (2**64 - 1), sim_index0=int(sim_index0),
                              daily_rows=int(daily_rows))
@@ -219,7 +229,7 @@ def abc_trials(obs, n_trials, threshold, priors, seed=0, trial0=0, trial_ids=Non
         if trial_ids is not None:
             ids = torch.as_tensor(np.asarray(trial_ids, dtype=np.int64)).to(dev)
             n_trials = ids.numel()
-        cfg = _lib.AbcConfig(n_days=T, arith=ARITH.get(arith, arith), early_reject=int(bool(early_reject)),
+        cfg = _lib.AbcConfig(n_days=T, arith=resolve_arith(None, arith), early_reject=int(bool(early_reject)),
                              n_trials=int(n_trials), trial0=int(trial0), threshold=float(threshold),
                              prior=(C.c_double * 4)(*[float(v) for v in priors]), seed=int(seed) & (2**64 - 1))
         theta = torch.empty((n_trials, 2), dtype=torch.float64, device=dev)

@@ -67,7 +67,7 @@ def _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_po
 
 
 def particle_filter(Y, type_model, theta_proposal, observations=False, probs=.1, n_particles=1000, n_population=4820,
-                    mu=20, jobs=4, *, resampler="systematic", seed=None, arith="fast32", X0=None, replay=None,
+                    mu=20, jobs=4, *, resampler="systematic", seed=None, arith="auto", X0=None, replay=None,
                     output="numpy", filter_id=0, block_particles=0):
     """Bootstrap particle filter (pmcmc.py:123-233).
 
@@ -104,7 +104,7 @@ def particle_filter(Y, type_model, theta_proposal, observations=False, probs=.1,
 
 
 def pf_loglik(Y, type_model, theta_proposal, observations=False, probs=.1, n_particles=1000, n_population=4820,
-              mu=20, *, resampler="systematic", seed=None, arith="fast32", filter_id=0):
+              mu=20, *, resampler="systematic", seed=None, arith="auto", filter_id=0):
     """log of the likelihood estimate zetas[-1] only (no history leaves the device); -inf on collapse."""
     seed = engine.new_seed() if seed is None else seed
     cfg, Y, theta = _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_population, mu,
@@ -134,7 +134,7 @@ def particle_path_sampler(hidden_process, ancestry_matrix, *, exact_genealogy=Fa
 
 def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_chains=1000, observations=False,
                   probs=.1, n_particles=1000, n_population=4820, mu=20, jobs=4, *, resampler="systematic", seed=None,
-                  arith="fast32", exact_genealogy=False, return_log=False, progress=False, stats=None):
+                  arith="auto", exact_genealogy=False, return_log=False, progress=False, stats=None):
     """Particle marginal Metropolis-Hastings (pmcmc.py:251-408).
 
     Returns (thetas[n_chains,P], likelihoods[n_chains], sampled_trajs[T,n_chains,C]).  likelihoods are the linear

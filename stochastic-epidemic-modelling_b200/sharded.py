@@ -100,7 +100,7 @@ def exchange_plan(G, total, u0, n_global, world):
 
 # ------------------------------------------------------------------------------------------ one shard on one device
 class Shard:
-    def __init__(self, rank, world, model, Y, theta, n_global, G=1, observations=False, probs=.1, arith="fast32", seed=0,
+    def __init__(self, rank, world, model, Y, theta, n_global, G=1, observations=False, probs=.1, arith="auto", seed=0,
                  filter_id=0, mu=None, n_population=None, store_history=True, device=None):
         self.rank, self.world, self.n_global = rank, world, n_global
         self.j0, self.n_local = shard_bounds(n_global, world)[rank]

@@ -29,7 +29,7 @@ def main():
     out = sharded.run_distributed(Y, 0, np.array([2.0, 1.0]), N, probs=.1, seed=777, filter_id=2, mu=[20], n_population=[pop])
     assert out["collapsed"] == 0
     sh = out["shard"]
-    cfg = sem_b200.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=3, seed=777, filter_id0=2, mu=[20], n_population=[pop])
+    cfg = sem_b200.engine.make_pf_config(0, N, T, probs=.1, resampler=1, seed=777, filter_id0=2, mu=[20], n_population=[pop])
     one = sem_b200.engine.run_pf(cfg, Y, np.array([2.0, 1.0]))
     torch.cuda.synchronize()
     lo, cnt = sh.j0, sh.n_local
@@ -41,7 +41,7 @@ def main():
     assert int(ev) == int(one.n_events[0])
     if rank == 0:
         from oracle import c_oracle as co
-        ref = co.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=3, seed=777, filter_id=2, mu=[20], npop=[pop])
+        ref = co.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=cfg.arith, seed=777, filter_id=2, mu=[20], npop=[pop])
         assert np.array_equal(one.ancestry[0].cpu().numpy(), ref["ancestry"])
         print(f"sharded filter over {world} GPUs == single GPU == oracle: OK  logZ={out['log_zetas'][-1]:.6f}")
     # ABC across ranks

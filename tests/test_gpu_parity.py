@@ -455,12 +455,13 @@ def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta,
     assert out["collapsed"] == 0
     X = torch.cat([sh.X_hist for sh in out["shards"]], dim=2).permute(0, 2, 1).cpu().numpy()       # (T,N,C)
     A = torch.cat([sh.ancestry for sh in out["shards"]], dim=1).cpu().numpy()
-    ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=3, seed=4242, filter_id=5, mu=mu, npop=npop)
+    arith = sem.engine.resolve_arith(model, "auto")                       # the sharded filter's default
+    ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=arith, seed=4242, filter_id=5, mu=mu, npop=npop)
     assert np.array_equal(A, ref["ancestry"])
     assert np.array_equal(X, ref["X_hist"])
     np.testing.assert_allclose(out["log_zetas"], ref["log_zetas"], rtol=1e-11)
     assert sum(sh.n_events for sh in out["shards"]) == ref["n_events"]
-    cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=3, seed=4242, filter_id0=5, mu=mu,
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=arith, seed=4242, filter_id0=5, mu=mu,
                                     n_population=npop)
     one = sem.engine.run_pf(cfg, Y, np.array(theta, float))
     assert np.array_equal(one.X_hist[0].permute(0, 2, 1).cpu().numpy(), X)
