@@ -796,8 +796,8 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
 // epidemics take several batches per interval; a batch that completes without violating its bound has covered exactly h).
 // Every interval is uniformized (no direct-method tail).
 // The loop is re-entrant (Unif32State) so that two warps can share one particle's interval: with `handoff` the call
-// returns false -- at a group boundary, once half of the current batch's candidates are served -- and a second call
-// with the same state finishes the interval (pf_persistent's scheduler balancing).
+// serves the first half of the current batch's candidates and returns false; a second call with the same state
+// finishes the interval (pf_persistent's scheduler balancing).
 #ifndef SEM_U32_C0
 #define SEM_U32_C0 1.0
 #define SEM_U32_C1 2.0
@@ -840,12 +840,12 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
             a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed by the second leg
         }
         const double B = st.B;
-        const uint32_t last = st.last, half = st.first + ((st.last - st.first) >> 1);
+        // a first leg serves the first half of the batch's candidates only: the loop is the same, its bound differs
+        const uint32_t last = handoff ? st.first + ((st.last - st.first) >> 1) : st.last;
         uint32_t cand = st.cand;
         int fired = 0;
-        bool stop = false, pass = false;
+        bool stop = false;
         while (cand < last && !stop) {
-            if (handoff && cand >= half && (cand & 3u) == 0u) { pass = true; break; }
             loc.k = cand >> 2;
             const uint4 w = loc.raw();
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
@@ -869,7 +869,7 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
         }
         st.cand = cand;
         fired_total += fired;
-        if (pass) { finished = false; break; }
+        if (!stop && cand < st.last) { finished = false; break; }      // hand-over point reached (first leg only)
         st.in_batch = 0;
         if (!(stop && a0 > B)) {                                       // not violated: the batch covered its h exactly
             if (stop || !(st.h < st.t_rem)) break;                     // absorbed, or h was the rest of the interval

@@ -351,17 +351,20 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
     // interval and owns the particle in the weights / scan.  Every scheduler then carries W + 1/2 rounds.  The legs
     // reproduce the single run bit for bit (ssa_run_spec_leg).
     constexpr bool kLegs = LegLoop<Model, ARITH>::available;
+    constexpr bool kUnif = ARITH == SEM_ARITH_UNIFORMIZED32;  // its own two-leg loop (ssa_unif32_leg)
     const int N = P.N, warp = tid >> 5, lane = tid & 31;
-    const int main_n = (kLegs && P.split_main > 0) ? P.split_main : (int)blockDim.x;
+    const int main_n = ((kLegs || kUnif) && P.split_main > 0) ? P.split_main : (int)blockDim.x;
     const int helper = tid < main_n ? -1 : warp - (main_n >> 5);          // -1 main; 0,1 first leg of group 0,1; 2,3 second leg
     const int pidx = helper < 0 ? tid : main_n + 32 * (helper & 1) + lane;
     const int j = b * P.ppb + pidx;
     const bool has = pidx < P.ppb && j < N;
     const bool starts = has && helper < 2;                   // resamples, gathers and starts the interval
     const bool active = has && (helper < 0 || helper >= 2);  // owns the particle at the observation time (store, weigh, scan)
-    __shared__ double s_cx[kLegs ? 2 : 1][32][Model::C], s_ct[kLegs ? 2 : 1][32];
-    __shared__ uint32_t s_ck[kLegs ? 2 : 1][32];
-    __shared__ int s_cfin[kLegs ? 2 : 1][32];
+    __shared__ double s_cx[(kLegs || kUnif) ? 2 : 1][32][Model::C], s_ct[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ uint32_t s_ck[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ int s_cfin[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ double s_cB[kUnif ? 2 : 1][32], s_ch[kUnif ? 2 : 1][32];   // rest of the uniformized loop's continuation
+    __shared__ uint32_t s_cu[kUnif ? 2 : 1][32][3];
     const uint32_t fid = P.filter_id0 + f;
     int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
@@ -446,7 +449,46 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
             src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
             PHASE(7);
         }
-        if constexpr (kLegs) {
+        if constexpr (kUnif) {
+            // same scheme with the uniformized loop: the first leg serves the first half of the batch's candidates
+            const int g = helper & 1;
+            const bool first_leg = (helper == 0 || helper == 1);
+            bool run = starts, fin = true;
+            Unif32State ust;
+            unif32_begin(ust, P.dt);
+            if (helper >= 2) {                               // second leg: wait for the continuation
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+                run = false;
+                if (has) {
+#pragma unroll
+                    for (int c = 0; c < Model::C; c++) x[c] = s_cx[g][lane][c];
+                    if (!s_cfin[g][lane]) {
+                        run = true;
+                        m.setup(P.theta + (size_t)f * P.ntheta, x);
+                        src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
+                        ust.t_rem = s_ct[g][lane]; ust.B = s_cB[g][lane]; ust.h = s_ch[g][lane];
+                        ust.cand = s_ck[g][lane]; ust.first = s_cu[g][lane][0]; ust.last = s_cu[g][lane][1]; ust.aux_k = s_cu[g][lane][2];
+                        ust.in_batch = 1;
+                    }
+                }
+            }
+            if (run) {                                       // ONE call site for every role
+                long long fired = 0;
+                PairSource<false> aux;
+                aux.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_AUX, fid));
+                fin = ssa_unif32_leg<Model, false>(m, x, ust, fired, first_leg, src, aux, s_tab);
+                pairs = fired;
+            }
+            if (first_leg) {                                 // hand over
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) s_cx[g][lane][c] = x[c];
+                s_ct[g][lane] = ust.t_rem; s_cB[g][lane] = ust.B; s_ch[g][lane] = ust.h;
+                s_ck[g][lane] = ust.cand; s_cu[g][lane][0] = ust.first; s_cu[g][lane][1] = ust.last; s_cu[g][lane][2] = ust.aux_k;
+                s_cfin[g][lane] = fin ? 1 : 0;
+                __threadfence_block();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+            }
+        } else if constexpr (kLegs) {
             // ONE call site of the event loop for every role: warps that ran different copies of the loop side by side
             // on a scheduler cost 14 % (instruction cache), measured
             const int g = helper & 1;
@@ -855,7 +897,7 @@ static const void *persistent_kernel(const sem_pf_config *cfg) {
 static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *split_main) {
     *split_main = 0;
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
-    const bool legs = cfg->arith == SEM_ARITH_FAST32 || (cfg->arith == SEM_ARITH_FAST && C <= 6);
+    const bool legs = cfg->arith == SEM_ARITH_FAST32 || cfg->arith == SEM_ARITH_UNIFORMIZED32 || (cfg->arith == SEM_ARITH_FAST && C <= 6);
     const int e = w.ppb % 128, main_n = w.ppb - e;
     static int env_off = -1;
     if (env_off < 0) { const char *s = getenv("SEM_NO_SPLIT"); env_off = (s && s[0] == '1') ? 1 : 0; }
