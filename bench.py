@@ -37,13 +37,13 @@ import workloads  # noqa: E402
 # budget of 128 "to be replaced by ncu smsp__inst_executed / events once the kernel exists"; these are the measured
 # values: smsp__inst_executed.sum x thread_inst_per_inst / n_events over the whole-filter kernel
 # (profiles/r01c_pf_persistent_final.txt: 4.4271e9 x 26.49 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
-# uniformized32 (profiles/r01d_pf_persistent_uniformized32.txt): 3.8613e9 x 25.04 / 1.588e9 fired events.
-I_ALG_BY_ARITH = {"uniformized32": 60.9, "fast32": 73.4, "fast": 106.0}
+# uniformized32 (profiles/r01d_pf_persistent_uniformized32.txt): 3.9110e9 x 25.10 / 1.588e9 fired events.
+I_ALG_BY_ARITH = {"uniformized32": 61.8, "fast32": 73.4, "fast": 106.0}
 I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
 LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
 # dram__bytes_read.sum + dram__bytes_write.sum of one whole-filter launch (ncu --set full, same profile)
-DRAM_TRAFFIC_PER_PASS = {"uniformized32": 1.314816e6 + 145.961728e6, "fast32": 883.968e3 + 143.988224e6}
+DRAM_TRAFFIC_PER_PASS = {"uniformized32": 1.192192e6 + 147.568384e6, "fast32": 883.968e3 + 143.988224e6}
 
 
 def measured_peaks():

@@ -18,12 +18,29 @@ ARITH = {"reference": 0, "fast": 1, "uniformized": 2, "fast32": 3, "uniformized3
 ARITH_NAMES = {v: k for k, v in ARITH.items()}
 
 
-def resolve_arith(model, arith):
-    """'auto' (the filters' default) = the fastest exact interval simulation measured for the model family: uniformized
-    intervals with 32-bit candidates for SIR / SEIR (2-3 reactions), the direct method with 32-bit streams for the
-    subgroup models (their G^2+G propensities make a uniformized candidate as dear as a direct event)."""
+AUTO_MAX_GROWTH = 0.5    # per observation interval; measured crossover between the two interval simulations
+
+
+def resolve_arith(model, arith, theta=None, dt=1.0):
+    """'auto' (the filters' default) = the faster exact interval simulation for the model family and dynamics:
+    uniformized intervals with 32-bit candidates for SIR / SEIR (2-3 reactions) -- unless the epidemic's early growth per
+    observation interval (from theta, when it is known on the host) is so fast that an interval needs many short
+    batches -- and the direct method with 32-bit streams otherwise: for the subgroup models (their G^2+G propensities
+    make a uniformized candidate as dear as a direct event), for ABC and for simulations that log event times."""
     if arith == "auto":            # (model None: simulations with event logs and ABC trials need event times -> direct method)
-        return ARITH["uniformized32"] if model in (0, 1) else ARITH["fast32"]
+        if model not in (0, 1):
+            return ARITH["fast32"]
+        if theta is not None and not isinstance(theta, torch.Tensor):
+            th = np.asarray(theta, dtype=np.float64).reshape(-1)
+            if model == 0 and th.size >= 2:
+                growth = (th[0] - th[1]) * dt                                    # SIR: beta - gamma
+            elif model == 1 and th.size >= 3:                                    # SEIR: dominant eigenvalue of the (E, I) linearisation
+                growth = 0.5 * (np.sqrt((th[1] - th[2]) ** 2 + 4 * th[1] * th[0]) - (th[1] + th[2])) * dt
+            else:
+                growth = 0.0
+            if growth > AUTO_MAX_GROWTH:
+                return ARITH["fast32"]
+        return ARITH["uniformized32"]
     return ARITH.get(arith, arith)
 
 

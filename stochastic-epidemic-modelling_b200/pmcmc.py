@@ -57,6 +57,7 @@ def _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_po
         raise ValueError("Y must be (T, columns)")
     G = len(mu) if model >= 2 else 1
     theta = _flatten_theta(model, theta_proposal)
+    arith = engine.resolve_arith(model, arith, theta=theta)                  # 'auto' looks at the dynamics too
     cfg = engine.make_pf_config(model, n_particles, Y.shape[0], G=G, observations=observations, probs=probs,
                                 resampler=resampler, arith=arith, seed=seed, filter_id0=filter_id,
                                 mu=np.atleast_1d(mu), n_population=np.atleast_1d(n_population),
