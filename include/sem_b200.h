@@ -48,8 +48,11 @@ enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
  * law and the rest of the interval restarts with a new bound.
  * FAST32 is FAST with 32-bit uniforms: event k of a particle-step takes two words of Philox call k/2 (u1 = words 0/2,
  * u2 = words 1/3), so one Philox4x32-10 call serves two events; all arithmetic stays fp64.
- * UNIFORMIZED32 is UNIFORMIZED with 32-bit candidate uniforms: candidate c takes word (c & 3) of Philox call c >> 2 (four
- * candidates per call), and every interval is uniformized (no direct-method tail). */
+ * UNIFORMIZED32 is the production form of UNIFORMIZED: 32-bit candidate uniforms (candidate c takes word (c & 3) of Philox
+ * call c >> 2: four candidates per call), a bound that anticipates growth (B = max(a0(x), a0(x + drift h)) (1 + 2/sqrt(a0 h + 1)),
+ * batches shortened so that the anticipated growth stays below 1.25), and no direct-method tail.  Same law of the state
+ * at the end of the interval as the direct method.  The Python layer's default "auto" picks UNIFORMIZED32 for SIR / SEIR
+ * filters and FAST32 otherwise. */
 enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2, SEM_ARITH_FAST32 = 3, SEM_ARITH_UNIFORMIZED32 = 4 };
 
 enum {

@@ -310,3 +310,30 @@ def test_helpers_match_reference_formulas(tmp_path):
     theta0, sigma = results_io.warm_start(d)
     uniq = np.unique(thetas[100:][::20], axis=0)
     assert theta0 == thetas[-1].tolist() and np.array_equal(sigma, np.cov(uniq.T, ddof=0))
+
+
+def test_hot_loops_fit_the_instruction_cache():
+    """The event loops of the whole-filter kernels must stay within 4 KB of SASS (256 instructions): a build whose direct-
+    method block grew to 264 instructions ran the filter 23 % slower with otherwise identical code (DESIGN.md section 4,
+    'Instruction cache').  Parsed from the built library with cuobjdump; skipped when cuobjdump is not installed."""
+    import re, shutil, subprocess
+    cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(cuobjdump):
+        pytest.skip("cuobjdump not available")
+    import sem_b200
+    sem_b200._lib.load()
+    sass = subprocess.run([cuobjdump, "-sass", sem_b200._lib.LIB_PATH], capture_output=True, text=True).stdout
+    for arith, min_wide in ((3, 30), (4, 15)):                  # fast32: two Philox calls per block; uniformized32: one per group
+        name = f"_ZN3sem13pf_persistentINS_8SirModelELi{arith}EEEvNS_5PfDevE"
+        body = sass[sass.index("Function : " + name):]
+        body = body[:body.index("Function : ", 20)] if "Function : " in body[20:] else body
+        ins = {int(m.group(1), 16): m.group(2) for m in re.finditer(r"/\*([0-9a-f]{4,6})\*/\s+([^;]+);", body)}
+        sizes = []
+        for a, t in ins.items():
+            m = re.search(r"BRA (?:P\d, )?0x([0-9a-f]+)", t)
+            if m and int(m.group(1), 16) < a:
+                loop = [ins[x] for x in range(int(m.group(1), 16), a + 16, 16) if x in ins]
+                if sum("IMAD.WIDE" in i for i in loop) >= min_wide:
+                    sizes.append(len(loop))
+        assert sizes, f"event loop of arith {arith} not found"
+        assert min(sizes) <= 256, (arith, min(sizes))
