@@ -313,9 +313,9 @@ def test_helpers_match_reference_formulas(tmp_path):
 
 
 def test_hot_loops_fit_the_instruction_cache():
-    """The event loops of the whole-filter kernels must stay within 4 KB of SASS (256 instructions): a build whose direct-
-    method block grew to 264 instructions ran the filter 23 % slower with otherwise identical code (DESIGN.md section 4,
-    'Instruction cache').  Parsed from the built library with cuobjdump; skipped when cuobjdump is not installed."""
+    """Pins the size of the event loops of the two headline kernels (<= 256 SASS instructions = 4 KB): a build whose
+    direct-method block grew to 264 instructions ran the filter 23 % slower ('Instruction cache /
+    code layout').  Parsed from the built library with cuobjdump; skipped when cuobjdump is not installed."""
     import re, shutil, subprocess
     cuobjdump = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
     if not os.path.exists(cuobjdump):
@@ -337,3 +337,20 @@ def test_hot_loops_fit_the_instruction_cache():
                     sizes.append(len(loop))
         assert sizes, f"event loop of arith {arith} not found"
         assert min(sizes) <= 256, (arith, min(sizes))
+
+
+def test_auto_interval_simulation_choice():
+    """arith='auto': uniformized32 for SIR / SEIR filters with slow dynamics (or unknown theta), the direct method with
+    32-bit streams for fast growth, subgroup models, ABC and logged simulations; explicit names pass through."""
+    from sem_b200 import engine
+    A = engine.ARITH
+    assert engine.resolve_arith(0, "auto") == A["uniformized32"] and engine.resolve_arith(1, "auto") == A["uniformized32"]
+    assert engine.resolve_arith(0, "auto", theta=[.4, .2]) == A["uniformized32"]          # the BASELINE workload
+    assert engine.resolve_arith(0, "auto", theta=[2.0, 1.0]) == A["fast32"]               # growth 1 per interval
+    assert engine.resolve_arith(1, "auto", theta=[.4, .1, .1]) == A["uniformized32"]
+    assert engine.resolve_arith(1, "auto", theta=[4.0, 1.0, 1.0]) == A["fast32"]
+    assert engine.resolve_arith(2, "auto") == engine.resolve_arith(3, "auto", theta=[5, 2, 1, 3, .5]) == A["fast32"]
+    assert engine.resolve_arith(None, "auto") == A["fast32"]
+    assert engine.resolve_arith(0, "fast") == 1 and engine.resolve_arith(0, 2) == 2
+    cfg = engine.make_pf_config(0, 100, 5, mu=[20], n_population=[1000])
+    assert cfg.arith == A["uniformized32"]
