@@ -341,7 +341,7 @@ def main():
     if not args.no_e2e:
         np.random.seed(rank)
         st = {}
-        n_it = max(4, min(K, 12))
+        n_it = max(8, min(K, 40))                                        # MH iterations in the timed call (its setup is inside)
         sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=3, probs=w["probs"], n_particles=N,
                                n_population=w["n_population"], mu=w["mu"], seed=77 + rank)          # warm-up
         torch.cuda.synchronize()

@@ -177,6 +177,53 @@ def run_pf(cfg, Y, theta, X0=None, replay=None, device=None, out=None, iter_out=
         return res
 
 
+class PreparedIteration:
+    """Everything one PMCMC iteration needs, set up once: device outputs + workspace, Y, a device theta fed from pinned
+    host memory, the packed iteration result and its pinned mirror.  run(theta, filter_id, probs, arith) is then one H2D
+    of theta, ONE sem_pf_run (filter + path sample + packing, sem_b200.h: iteration_result), one D2H and one stream
+    synchronisation -- no allocation and no Python-side tensor work per iteration."""
+
+    def __init__(self, cfg, Y, device=None):
+        self.L = _lib.load()
+        self.dev = require_cuda(device)
+        self.cfg = cfg
+        F, T = cfg.n_filters, cfg.n_obs
+        G = cfg.n_groups if cfg.model >= 2 else 1
+        self.Cn, self.P, _ = model_dims(cfg.model, G)
+        self.T = T
+        with torch.cuda.device(self.dev):
+            self.out = alloc_pf_outputs(cfg, self.dev)
+            self.Y = _dev_f64(Y, self.dev).reshape(T, -1)
+            self.pin_th = torch.empty((F, self.P), dtype=torch.float64).pin_memory()
+            self.dev_th = torch.empty((F, self.P), dtype=torch.float64, device=self.dev)
+            self.dev_it = torch.empty((F, ITER_HEADER + T * self.Cn), dtype=torch.float64, device=self.dev)
+            self.pin_it = torch.empty((F, ITER_HEADER + T * self.Cn), dtype=torch.float64).pin_memory()
+        X_hist, anc, logz, status, nev, ws = self.out
+        self.buf = _lib.PfBuffers(Y=_ptr(self.Y), theta=_ptr(self.dev_th), X0=None, X_hist=_ptr(X_hist), ancestry=_ptr(anc),
+                                  log_zetas=_ptr(logz), status=_ptr(status), n_events=_ptr(nev), workspace=_ptr(ws),
+                                  iteration_result=_ptr(self.dev_it))
+        self.th_host = self.pin_th.numpy()
+        self.it_host = self.pin_it.numpy()
+        self.launches = self.L.sem_pf_launch_count(C.byref(cfg))
+
+    def run(self, theta, filter_id, probs=None, arith=None):
+        """Returns the pinned [F, ITER_HEADER + T*C] result (valid until the next run)."""
+        cfg = self.cfg
+        cfg.filter_id0 = int(filter_id) & 0xFFFFFF
+        if probs is not None:
+            cfg.probs = float(probs)
+        if arith is not None:
+            cfg.arith = int(arith)
+        self.th_host[...] = theta
+        stream = torch.cuda.current_stream(self.dev)
+        with torch.cuda.stream(stream):
+            self.dev_th.copy_(self.pin_th, non_blocking=True)
+            _lib.check(self.L.sem_pf_run(C.byref(cfg), C.byref(self.buf), C.c_void_p(stream.cuda_stream)), "sem_pf_run")
+            self.pin_it.copy_(self.dev_it, non_blocking=True)
+        stream.synchronize()
+        return self.it_host
+
+
 def alloc_pf_outputs(cfg, device=None):
     """Pre-allocated output + workspace tensors for repeated run_pf calls (e.g. the MH loop)."""
     L = _lib.load()

@@ -157,30 +157,19 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     counters = dict(filter_runs=0, acceptances=1, launches=0)
 
     # One iteration = ONE launch (the filter, the path sample of pmcmc.py:371 and the packing of the results happen in
-    # the whole-filter kernel) + one small H2D (theta) + one small D2H (log-likelihood, status, sampled trajectory).
+    # the whole-filter kernel) + one small H2D (theta) + one small D2H (log-likelihood, status, sampled trajectory);
+    # buffers, config and pointers are prepared once (engine.PreparedIteration).
     cfg0, _, _ = _setup(Y, type_model, _split(model, G, np.asarray(parameters, dtype=float), probs)[0], observations,
                         .5, n_particles, n_population, mu, resampler, seed, arith, 0)
-    out = engine.alloc_pf_outputs(cfg0, dev)
-    Yd = torch.from_numpy(Y).to(dev)
-    n_theta = engine.model_dims(model, G)[1]
-    pin_th = torch.empty((n_theta,), dtype=torch.float64).pin_memory()
-    dev_th = torch.empty((n_theta,), dtype=torch.float64, device=dev)
-    dev_it = torch.empty((1, engine.ITER_HEADER + T * Cn), dtype=torch.float64, device=dev)
-    pin_it = torch.empty((1, engine.ITER_HEADER + T * Cn), dtype=torch.float64).pin_memory()
+    cfg0.path_exact = int(bool(exact_genealogy))
+    prep = engine.PreparedIteration(cfg0, Y, dev)
 
     def run_filter(theta_vec, it):
         theta2, probs2 = _split(model, G, theta_vec, probs)
-        cfg, _, th = _setup(Y, type_model, theta2, observations, probs2, n_particles, n_population, mu, resampler, seed,
-                            arith, it)
-        cfg.path_exact = int(bool(exact_genealogy))
-        pin_th.numpy()[:] = th
-        dev_th.copy_(pin_th, non_blocking=True)
-        res = engine.run_pf(cfg, Yd, dev_th, out=out, iter_out=dev_it)
-        pin_it.copy_(dev_it, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        th = _flatten_theta(model, theta2)
+        r = prep.run(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th))[0]
         counters["filter_runs"] += 1
-        counters["launches"] += res.launches + (0 if res.launches == 1 else 1)
-        r = pin_it.numpy()[0]
+        counters["launches"] += prep.launches + (0 if prep.launches == 1 else 1)
         if int(r[1]) != 0:
             return None, None
         return float(r[0]), r[engine.ITER_HEADER:].reshape(T, Cn).copy()
