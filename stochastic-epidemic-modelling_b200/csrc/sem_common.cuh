@@ -810,6 +810,33 @@ __device__ __forceinline__ void unif32_begin(Unif32State &st, double max_time) {
     st.t_rem = max_time; st.h = max_time; st.B = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
 }
 
+// First-batch / next-batch setup of the uniformized loop: bound B, covered time h, candidate count K ~ Poisson(B h).
+// Returns false when the state is absorbed (nothing left to simulate).  K is known BEFORE the loop runs, which is what
+// lets pf_persistent sort a CTA's particles by their exact amount of work (see there).
+template <class Model>
+__device__ __forceinline__ bool unif32_batch_setup(const Model &m, const double *x, Unif32State &st, PairSource<false> &aux,
+                                                   double *r, double &a0) {
+    if (!m.alive(x)) return false;
+    a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
+    if (!(a0 > 0)) return false;
+    double xp[Model::C], rp[Model::R];
+    m.drift(x, r, st.t_rem, xp);
+    const double a0p = ssa_total<Model, SEM_ARITH_FAST>(m, xp, rp);
+    double amax = a0p > a0 ? a0p : a0;
+    st.h = st.t_rem;
+    const double cap = __dmul_rn(SEM_U32_GMAX, a0);
+    if (amax > cap) {                                             // fast growth: a shorter batch, so that the (linearised)
+        st.h = __dmul_rn(st.t_rem, __ddiv_rn(__dsub_rn(cap, a0), __dsub_rn(a0p, a0)));   // drift lifts a0 by GMAX at most
+        amax = cap;
+    }
+    const double expect = __dmul_rn(a0, st.h);
+    st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
+    const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.h));
+    const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+    st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
+    return true;
+}
+
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32State &st, long long &fired_total, const bool handoff,
                                                PairSource<false> &src, PairSource<false> &aux, const double2 *tab) {
@@ -819,26 +846,9 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
     for (;;) {
         double r[Model::R], a0;
         if (!st.in_batch) {
-            if (!m.alive(x)) break;
-            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
-            if (!(a0 > 0)) break;
-            double xp[Model::C], rp[Model::R];
-            m.drift(x, r, st.t_rem, xp);
-            const double a0p = ssa_total<Model, SEM_ARITH_FAST>(m, xp, rp);
-            double amax = a0p > a0 ? a0p : a0;
-            st.h = st.t_rem;
-            const double cap = __dmul_rn(SEM_U32_GMAX, a0);
-            if (amax > cap) {                                             // fast growth: a shorter batch, so that the (linearised)
-                st.h = __dmul_rn(st.t_rem, __ddiv_rn(__dsub_rn(cap, a0), __dsub_rn(a0p, a0)));   // drift lifts a0 by GMAX at most
-                amax = cap;
-            }
-            const double expect = __dmul_rn(a0, st.h);
-            st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
-            const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.h));
-            const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
-            st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
+            if (!unif32_batch_setup(m, x, st, aux, r, a0)) break;
         } else {
-            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed by the second leg
+            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed (second leg, or set up by the caller)
         }
         const double B = st.B;
         // a first leg serves the first half of the batch's candidates only: the loop is the same, its bound differs

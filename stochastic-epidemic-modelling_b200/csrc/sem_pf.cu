@@ -337,7 +337,7 @@ template <class Model, int ARITH>
 __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_constant__ PfDev P) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
-    extern __shared__ double s_dyn[];                        // pfx[nb], scale[nb] of the previous step
+    extern __shared__ __align__(16) double s_dyn[];          // pfx[nb], scale[nb] of the previous step (+ the sorted layout's exchange area)
     double *s_pfx = s_dyn, *s_scale = s_dyn + P.nb;
     __shared__ double sm[32];
     __shared__ double2 s_tab[kLogTabSize];
@@ -353,18 +353,16 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
     constexpr bool kLegs = LegLoop<Model, ARITH>::available;
     constexpr bool kUnif = ARITH == SEM_ARITH_UNIFORMIZED32;  // its own two-leg loop (ssa_unif32_leg)
     const int N = P.N, warp = tid >> 5, lane = tid & 31;
-    const int main_n = ((kLegs || kUnif) && P.split_main > 0) ? P.split_main : (int)blockDim.x;
+    const int main_n = (kLegs && P.split_main > 0) ? P.split_main : (int)blockDim.x;
     const int helper = tid < main_n ? -1 : warp - (main_n >> 5);          // -1 main; 0,1 first leg of group 0,1; 2,3 second leg
     const int pidx = helper < 0 ? tid : main_n + 32 * (helper & 1) + lane;
     const int j = b * P.ppb + pidx;
     const bool has = pidx < P.ppb && j < N;
     const bool starts = has && helper < 2;                   // resamples, gathers and starts the interval
     const bool active = has && (helper < 0 || helper >= 2);  // owns the particle at the observation time (store, weigh, scan)
-    __shared__ double s_cx[(kLegs || kUnif) ? 2 : 1][32][Model::C], s_ct[(kLegs || kUnif) ? 2 : 1][32];
-    __shared__ uint32_t s_ck[(kLegs || kUnif) ? 2 : 1][32];
-    __shared__ int s_cfin[(kLegs || kUnif) ? 2 : 1][32];
-    __shared__ double s_cB[kUnif ? 2 : 1][32], s_ch[kUnif ? 2 : 1][32];   // rest of the uniformized loop's continuation
-    __shared__ uint32_t s_cu[kUnif ? 2 : 1][32][3];
+    __shared__ double s_cx[kLegs ? 2 : 1][32][Model::C], s_ct[kLegs ? 2 : 1][32];
+    __shared__ uint32_t s_ck[kLegs ? 2 : 1][32];
+    __shared__ int s_cfin[kLegs ? 2 : 1][32];
     const uint32_t fid = P.filter_id0 + f;
     int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
@@ -426,6 +424,12 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
             dead = true;
             continue;
         }
+        if constexpr (kUnif) {                               // sorted layout: clear the bins and the range of K
+            if (P.split_main < 0) {
+                uint32_t *bins = (uint32_t *)(s_dyn + 2 * P.nb + 2 * blockDim.x) + (2 * Model::C + 3) * blockDim.x;
+                for (int i = tid; i < 130; i += blockDim.x) bins[i] = i == 129 ? 0xffffffffu : 0u;
+            }
+        }
         __syncthreads();                                     // s_pfx / s_scale complete
         // zetas[p] = zetas[p-1] * mean(w) (pmcmc.py:183), off the CTA's critical path: by the last thread, whose warp is
         // a second-leg helper waiting for its hand-over in the balanced layout
@@ -450,43 +454,84 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
             PHASE(7);
         }
         if constexpr (kUnif) {
-            // same scheme with the uniformized loop: the first leg serves the first half of the batch's candidates
-            const int g = helper & 1;
-            const bool first_leg = (helper == 0 || helper == 1);
-            bool run = starts, fin = true;
+            // The uniformized loop knows its amount of work BEFORE it runs: the candidate count K of the (first) batch is
+            // drawn in the setup.  Sorted layout (P.split_main < 0): every thread sets up its own particle, the CTA sorts
+            // the particles by K (counting sort over 128 bins in shared memory) and thread t runs the particle at sorted
+            // position slot(t), so the 32 lanes of a warp carry (nearly) equal work, and the sorted chunks of 32 are dealt
+            // to the warps in snake order over the four schedulers (warp w issues on scheduler w & 3), which balances
+            // the schedulers' sums.  The end state returns to the particle's home thread through shared memory.  Streams
+            // are keyed by the particle, so WHO runs it changes nothing: results stay bit-identical to the plain layout.
+            const bool sorted = P.split_main < 0;
+            bool run = false;
             Unif32State ust;
             unif32_begin(ust, P.dt);
-            if (helper >= 2) {                               // second leg: wait for the continuation
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
-                run = false;
+            PairSource<false> aux;
+            int home = has ? pidx : -1;
+            if (starts) {
+                aux.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_AUX, fid));
+                double r0[Model::R], a00;
+                run = unif32_batch_setup(m, x, ust, aux, r0, a00);
+                ust.aux_k = aux.k;
+            }
+            if (sorted) {
+                const int NT = blockDim.x;
+                double *x_h = s_dyn + 2 * P.nb, *x_B = x_h + NT;
+                int32_t *x_x = (int32_t *)(x_B + NT), *x_ret = x_x + Model::C * NT;
+                uint32_t *x_K = (uint32_t *)(x_ret + Model::C * NT), *x_aux = x_K + NT;
+                int32_t *x_home = (int32_t *)(x_aux + NT);
+                uint32_t *x_hist = (uint32_t *)(x_home + NT);         // [128] bins + [2] range; zeroed before the barrier above
+                const uint32_t K = run ? ust.last : 0u;
+                const uint32_t wmax = __reduce_max_sync(0xffffffffu, K), wmin = __reduce_min_sync(0xffffffffu, K ? K : 0xffffffffu);
+                if (lane == 0) { atomicMax(&x_hist[128], wmax); atomicMin(&x_hist[129], wmin); }
+                __syncthreads();
+                const uint32_t kmax = x_hist[128], kmin = min(x_hist[129], kmax);
+                const float inv = 127.0f / (float)(kmax - kmin + 1u);
+                const int bin = K ? min(127, (int)((float)(kmax - K) * inv)) : 127;      // descending in K
+                const uint32_t rank = atomicAdd(&x_hist[bin], 1u);
+                __syncthreads();
+                const uint4 hh = reinterpret_cast<const uint4 *>(x_hist)[lane];           // every warp scans the 128 bins itself
+                const uint32_t s4 = hh.x + hh.y + hh.z + hh.w;
+                uint32_t inc = s4;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+                const uint32_t e0 = inc - s4, e1 = e0 + hh.x, e2 = e1 + hh.y, e3 = e2 + hh.z;
+                const int sl = bin >> 2, sk = bin & 3;
+                const uint32_t t0 = __shfl_sync(0xffffffffu, e0, sl), t1 = __shfl_sync(0xffffffffu, e1, sl),
+                               t2 = __shfl_sync(0xffffffffu, e2, sl), t3 = __shfl_sync(0xffffffffu, e3, sl);
+                const int pos = (int)((sk == 0 ? t0 : sk == 1 ? t1 : sk == 2 ? t2 : t3) + rank);
+                x_K[pos] = K; x_home[pos] = home; x_h[pos] = ust.h; x_B[pos] = ust.B; x_aux[pos] = ust.aux_k;
                 if (has) {
 #pragma unroll
-                    for (int c = 0; c < Model::C; c++) x[c] = s_cx[g][lane][c];
-                    if (!s_cfin[g][lane]) {
-                        run = true;
-                        m.setup(P.theta + (size_t)f * P.ntheta, x);
-                        src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
-                        ust.t_rem = s_ct[g][lane]; ust.B = s_cB[g][lane]; ust.h = s_ch[g][lane];
-                        ust.cand = s_ck[g][lane]; ust.first = s_cu[g][lane][0]; ust.last = s_cu[g][lane][1]; ust.aux_k = s_cu[g][lane][2];
-                        ust.in_batch = 1;
-                    }
+                    for (int c = 0; c < Model::C; c++) x_x[c * NT + pos] = (int32_t)x[c];
+                }
+                __syncthreads();
+                const int nchunks = NT >> 5, rnd = warp >> 2, r_last = (nchunks - 1) >> 2;
+                const int chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (warp & 3) : 3 - (warp & 3));
+                const int slot = 32 * chunk + lane;
+                home = x_home[slot];
+                run = x_K[slot] > 0u;
+                if (home >= 0) {
+#pragma unroll
+                    for (int c = 0; c < Model::C; c++) x[c] = (double)x_x[c * NT + slot];
+                }
+                if (run) {
+                    const int jr = b * P.ppb + home;
+                    m.setup(P.theta + (size_t)f * P.ntheta, x);
+                    src.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_SSA, fid));
+                    aux.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_AUX, fid));
+                    ust.h = x_h[slot]; ust.B = x_B[slot]; ust.last = x_K[slot]; ust.aux_k = x_aux[slot]; ust.in_batch = 1;
                 }
             }
-            if (run) {                                       // ONE call site for every role
+            if (run) {                                       // ONE call site of the loop
                 long long fired = 0;
-                PairSource<false> aux;
-                aux.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_AUX, fid));
-                fin = ssa_unif32_leg<Model, false>(m, x, ust, fired, first_leg, src, aux, s_tab);
+                ssa_unif32_leg<Model, false>(m, x, ust, fired, false, src, aux, s_tab);
                 pairs = fired;
             }
-            if (first_leg) {                                 // hand over
+            if (sorted && home >= 0) {                       // back to the home thread (read after the barrier below)
+                const int NT = blockDim.x;
+                int32_t *x_ret = (int32_t *)(s_dyn + 2 * P.nb + 2 * NT) + Model::C * NT;
 #pragma unroll
-                for (int c = 0; c < Model::C; c++) s_cx[g][lane][c] = x[c];
-                s_ct[g][lane] = ust.t_rem; s_cB[g][lane] = ust.B; s_ch[g][lane] = ust.h;
-                s_ck[g][lane] = ust.cand; s_cu[g][lane][0] = ust.first; s_cu[g][lane][1] = ust.last; s_cu[g][lane][2] = ust.aux_k;
-                s_cfin[g][lane] = fin ? 1 : 0;
-                __threadfence_block();
-                asm volatile("bar.sync %0, 64;" ::"r"(1 + g) : "memory");
+                for (int c = 0; c < Model::C; c++) x_ret[c * NT + home] = (int32_t)x[c];
             }
         } else if constexpr (kLegs) {
             // ONE call site of the event loop for every role: warps that ran different copies of the loop side by side
@@ -521,7 +566,8 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         } else {
             if (starts) pairs = ssa_run<Model, ARITH, false, false>(m, x, P.dt, src, s_tab, NoRec());
         }
-        if (active) {
+        const bool via_smem = kUnif && P.split_main < 0;     // sorted layout: the state comes home after the barrier
+        if (active && !via_smem) {
 #pragma unroll
             for (int c = 0; c < Model::C; c++) Xr[(size_t)c * N + j] = (int32_t)x[c];
         }
@@ -531,6 +577,17 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
         __syncthreads();                                     // keep the CTA in the SSA loop until its last warp is done: letting early
 #endif
         PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
+        if constexpr (kUnif) {
+            if (active && via_smem) {
+                const int32_t *x_ret = (const int32_t *)(s_dyn + 2 * P.nb + 2 * blockDim.x) + Model::C * blockDim.x;
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) {
+                    const int32_t v = x_ret[c * blockDim.x + pidx];
+                    x[c] = (double)v;
+                    Xr[(size_t)c * N + j] = v;
+                }
+            }
+        }
         if (p < P.T - 1) weigh_local<Model>(P, p, f, b, tid, active, j, x, sm, s_tab);
         PHASE(5);
     }
@@ -891,18 +948,43 @@ static const void *persistent_kernel(const sem_pf_config *cfg) {
     }
 }
 
-// Threads per CTA of the whole-filter kernel and the balanced layout's main-thread count (0 = plain layout): when a
-// CTA's ppb particles are W full warps per scheduler plus at most two more warps' worth, those extra particles are
-// time-split between four helper warps (see pf_persistent).  SEM_NO_SPLIT=1 keeps the plain layout.
+// Threads per CTA of the whole-filter kernel and its layout (*split_main): 0 = plain; > 0 = balanced -- when a CTA's
+// ppb particles are W full warps per scheduler plus at most two more warps' worth, those extra particles are time-split
+// between four helper warps (direct-method loops; see pf_persistent); < 0 = sorted by the candidate count (uniformized32,
+// SIR / SEIR).  SEM_NO_SPLIT=1 keeps the plain layout.
 static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *split_main) {
     *split_main = 0;
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
-    const bool legs = cfg->arith == SEM_ARITH_FAST32 || cfg->arith == SEM_ARITH_UNIFORMIZED32 || (cfg->arith == SEM_ARITH_FAST && C <= 6);
+    const bool legs = cfg->arith == SEM_ARITH_FAST32 || (cfg->arith == SEM_ARITH_FAST && C <= 6);
     const int e = w.ppb % 128, main_n = w.ppb - e;
     static int env_off = -1;
     if (env_off < 0) { const char *s = getenv("SEM_NO_SPLIT"); env_off = (s && s[0] == '1') ? 1 : 0; }
+    if (cfg->arith == SEM_ARITH_UNIFORMIZED32 && !env_off && C <= 4 && w.ppb > 32) *split_main = -1;
     if (legs && !env_off && main_n >= 128 && e > 0 && e <= 64 && main_n + 128 <= kMaxThreads) { *split_main = main_n; return main_n + 128; }
     return (w.ppb + 31) / 32 * 32;
+}
+
+// dynamic shared memory of the whole-filter kernel: pfx / scale of the CTAs, plus the sorted layout's exchange area
+// (h, B, state out, state back, K, aux counter, home index per thread, 128 bins + range)
+static size_t persistent_smem(const sem_pf_config *cfg, const WsLayout &w, int threads, int split_main) {
+    size_t b = 2 * (size_t)w.nb * sizeof(double);
+    if (split_main < 0) {
+        const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
+        b += (size_t)threads * (2 * sizeof(double) + (2 * C + 3) * sizeof(int32_t)) + 132 * sizeof(uint32_t);
+    }
+    return b;
+}
+
+// opt in to more than 48 KB of shared memory per CTA where the exchange area needs it (once per kernel)
+static int persistent_prepare(const void *fn, size_t smem) {
+    static const void *done_fn[32];
+    static size_t done_sz[32];
+    static int n_done = 0;
+    if (smem <= 24 * 1024) return SEM_OK;
+    for (int i = 0; i < n_done; i++) if (done_fn[i] == fn && done_sz[i] >= smem) return SEM_OK;
+    SEM_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (n_done < 32) { done_fn[n_done] = fn; done_sz[n_done] = smem; n_done++; }
+    return SEM_OK;
 }
 
 // One cooperative launch for the whole filter when every CTA can be co-resident (SEM_NO_PERSISTENT=1 or
@@ -916,7 +998,8 @@ static bool use_persistent(const sem_pf_config *cfg, const WsLayout &w, bool rep
     if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess || !coop) return false;
     int split_main;
     const int threads = persistent_threads(cfg, w, &split_main);
-    const size_t smem = 2 * (size_t)w.nb * sizeof(double);
+    const size_t smem = persistent_smem(cfg, w, threads, split_main);
+    if (persistent_prepare(persistent_kernel(cfg), smem) != SEM_OK) { cudaGetLastError(); return false; }
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_kernel(cfg), threads, smem) != cudaSuccess) { cudaGetLastError(); return false; }
     return (long long)per_sm * sm_count() >= (long long)w.nb * cfg->n_filters;
 }
@@ -937,7 +1020,7 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     if (use_persistent(cfg, w, replay)) {                    // one launch, nothing else (the kernel initialises its outputs)
         void *args[] = {(void *)&P};
         const dim3 grid(w.nb, cfg->n_filters), block(persistent_threads(cfg, w, &P.split_main));
-        SEM_CUDA(cudaLaunchCooperativeKernel(persistent_kernel(cfg), grid, block, args, 2 * (size_t)w.nb * sizeof(double), s));
+        SEM_CUDA(cudaLaunchCooperativeKernel(persistent_kernel(cfg), grid, block, args, persistent_smem(cfg, w, block.x, P.split_main), s));
         return SEM_OK;
     }
     SEM_CUDA(cudaMemsetAsync(P.counter, 0, cfg->n_filters * sizeof(unsigned int), s));
