@@ -51,6 +51,8 @@ def lib():
         L.so_norm_logpdf.argtypes = [C.c_double] * 3
         L.so_poisson_philox.restype = C.c_double
         L.so_poisson_philox.argtypes = [C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+        L.so_poisson_u_philox.restype = C.c_double
+        L.so_poisson_u_philox.argtypes = [C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
         L.so_ssa_replay.restype = C.c_int64
         L.so_ssa_philox.restype = C.c_int64
         L.so_pf_run.restype = C.c_int
@@ -94,6 +96,12 @@ def norm_logpdf(y, x, probs):
 def poisson_philox(mu, seed, c1, c2, domain=DOM_INIT, fid=0):
     return lib().so_poisson_philox(float(mu), C.c_uint64(seed), C.c_uint32(c1), C.c_uint32(c2),
                                    C.c_uint32(domain), C.c_uint32(fid))
+
+
+def poisson_u_philox(mu, seed, c1, c2, domain=8, fid=0):
+    """Candidate count of a uniformized32 batch (sem_oracle.c poisson_draw_u; DOM_AUX stream)."""
+    return lib().so_poisson_u_philox(float(mu), C.c_uint64(seed), C.c_uint32(c1), C.c_uint32(c2),
+                                     C.c_uint32(domain), C.c_uint32(fid))
 
 
 def ssa(model, G, x0, theta, max_time, arith=0, u=None, seed=None, sim_index=0, max_rec=0):

@@ -378,6 +378,41 @@ static double gamma_draw(so_stream *aux, double shape) {
     }
 }
 
+/* The candidate count of a uniformized32 batch: PTRS as above with the slow path's logarithms folded into three
+ * (csrc/sem_common.cuh poisson_draw_u, which reads them from its table; libm here). */
+static double poisson_draw_u(so_stream *s, double mu) {
+    double u1, u2;
+    if (!(mu > 0)) return 0.0;
+    if (mu < 10) {
+        stream_pair(s, &u1, &u2);
+        double pk = exp(-mu), F = pk, k = 0;
+        while (u1 > F && k < 1000) { k += 1; pk *= mu / k; F += pk; }
+        return k;
+    }
+    double slam = sqrt(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    double vr = 0.9277 - 3.6224 / (b - 2);
+    for (;;) {
+        stream_pair(s, &u1, &u2);
+        double U = u1 - 0.5, V = u2, us = 0.5 - fabs(U);
+        double k = floor((2 * a / us + b) * U + mu + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (k < 0 || (us < 0.013 && V > us)) continue;
+        double invalpha = 1.1239 + 1.1328 / (b - 3.4);
+        double q = V * invalpha / (a / (us * us) + b);
+        if (k < 2 || !(q >= 2.3e-308)) {
+            if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -mu + k * log(mu) - log_factorial(k)) return k;
+            continue;
+        }
+        double rhs = (k - mu) + k * log(mu / k) - 0.5 * log(6.283185307179586 * k) - stirlerr(k);
+        if (log(q) <= rhs) return k;
+    }
+}
+
+double so_poisson_u_philox(double mu, uint64_t seed, uint32_t c1, uint32_t c2, uint32_t domain, uint32_t fid) {
+    so_stream s; philox_stream(&s, seed, c1, c2, domain, fid);
+    return poisson_draw_u(&s, mu);
+}
+
 /* diagnostics (single-threaded use): batches, violations, candidates, fired, direct fallbacks */
 int64_t so_unif_counters[5];
 
@@ -470,7 +505,7 @@ static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_
         if (amax > cap) { h = t_rem * ((cap - a0) / (a0p - a0)); amax = cap; }     /* fast growth: a shorter batch */
         double expect = a0 * h;
         double B = amax * (c0 + c1 / sqrt(expect + 1.0));
-        double Kd = poisson_draw(&aux, B * h);
+        double Kd = poisson_draw_u(&aux, B * h);
         uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
         uint32_t first = cand, last = cand + K;
         int violated = 0, absorbed = 0;

@@ -279,6 +279,43 @@ __device__ __noinline__ double poisson_draw(Src &src, double mu) {
     }
 }
 
+// The candidate count of a uniformized batch (every particle, every step): the same PTRS sampler, arranged for the
+// 86 % of draws that the squeeze accepts -- nothing but vr is prepared up front, log(mu) and invalpha move into the
+// slow path, whose six logarithms are folded into three (log of the quotient; k log(mu/k); log(2 pi k)) and read from
+// the shared-memory table.  The C oracle states the same formulas with libm logarithms and IEEE divisions;
+// the two can disagree only when the acceptance test is decided within a few ulp (~1e-15 per draw).
+template <class Src>
+__device__ __noinline__ double poisson_draw_u(Src &src, double mu, const double2 *tab) {
+    double u1, u2;
+    if (!(mu > 0)) return 0.0;
+    if (mu < 10) {
+        src.next(u1, u2);
+        double pk = exp(-mu), F = pk, k = 0;
+        while (u1 > F && k < 1000) { k += 1; pk *= mu / k; F += pk; }
+        return k;
+    }
+    // quotients through the Newton reciprocal (<= 1 ulp from the IEEE division the oracle states)
+    const double slam = sqrt(mu), b = 0.931 + 2.53 * slam, a = -0.059 + 0.02483 * b;
+    const double vr = 0.9277 - 3.6224 * rcp_nr(b - 2);
+    for (;;) {
+        src.next(u1, u2);
+        const double U = u1 - 0.5, V = u2, us = 0.5 - fabs(U);
+        const double k = floor((2 * a * rcp_nr(us) + b) * U + mu + 0.43);
+        if (us >= 0.07 && V <= vr) return k;
+        if (!(k >= 0) || (us < 0.013 && V > us)) continue;
+        const double invalpha = 1.1239 + 1.1328 * rcp_nr(b - 3.4);
+        const double q = V * invalpha * rcp_nr(a * rcp_nr(us * us) + b);
+        if (k < 2 || !(q >= 2.3e-308)) {                       // (never at these means; stated for completeness)
+            if (log(V) + log(invalpha) - log(a / (us * us) + b) <= -mu + k * log(mu) - log_factorial(k)) return k;
+            continue;
+        }
+        const double ik = rcp_nr(k);
+        const double serr = k < 16 ? stirlerr(k) : (1.0 / 12 - (1.0 / 360 - (1.0 / 1260 - (1.0 / 1680 - 1.0 / 1188 * (ik * ik)) * (ik * ik)) * (ik * ik)) * (ik * ik)) * ik;
+        const double rhs = (k - mu) + k * log_tab(mu * ik, tab) - 0.5 * log_tab(6.283185307179586 * k, tab) - serr;
+        if (log_tab(q, tab) <= rhs) return k;
+    }
+}
+
 // ------------------------------------------------------------------------------------------ models
 // State is kept as fp64 integers in registers (exact up to 2^53); converted to int32 at observation boundaries.
 // rates<ARITH>() fills r[] in the reference's reaction order; REF divides by N per event like
@@ -815,7 +852,7 @@ __device__ __forceinline__ void unif32_begin(Unif32State &st, double max_time) {
 // lets pf_persistent sort a CTA's particles by their exact amount of work (see there).
 template <class Model>
 __device__ __forceinline__ bool unif32_batch_setup(const Model &m, const double *x, Unif32State &st, PairSource<false> &aux,
-                                                   double *r, double &a0) {
+                                                   double *r, double &a0, const double2 *tab) {
     if (!m.alive(x)) return false;
     a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
     if (!(a0 > 0)) return false;
@@ -831,7 +868,7 @@ __device__ __forceinline__ bool unif32_batch_setup(const Model &m, const double 
     }
     const double expect = __dmul_rn(a0, st.h);
     st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
-    const double Kd = poisson_draw(aux, __dmul_rn(st.B, st.h));
+    const double Kd = poisson_draw_u(aux, __dmul_rn(st.B, st.h), tab);
     const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
     st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
     return true;
@@ -846,7 +883,7 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
     for (;;) {
         double r[Model::R], a0;
         if (!st.in_batch) {
-            if (!unif32_batch_setup(m, x, st, aux, r, a0)) break;
+            if (!unif32_batch_setup(m, x, st, aux, r, a0, tab)) break;
         } else {
             a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed (second leg, or set up by the caller)
         }

@@ -56,7 +56,10 @@ struct PfDev {
     double *summary;
 };
 
-constexpr int kMaxThreads = 768;
+#ifndef SEM_MAX_THREADS
+#define SEM_MAX_THREADS 768
+#endif
+constexpr int kMaxThreads = SEM_MAX_THREADS;
 constexpr int kMaxThreadsUnif = 352;      // the uniformized step keeps more live state: two 352-thread CTAs per SM, <= 93 registers
 
 // CTA-wide max / inclusive scan: warp shuffles, one shared-memory slot per warp, and a second shuffle pass over the
@@ -133,8 +136,13 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
 #ifdef SEM_PHASES
 __device__ unsigned long long g_phase[16 * 256];
 #define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 16 + (k)] = (unsigned long long)clock64(); } } while (0)
+__device__ unsigned long long g_warp_end[256 * 32];          // CTA 0: when each warp left the SSA loop, and its work
+__device__ unsigned int g_warp_work[256 * 32];
+#define WARP_END(work) do { const unsigned int wk_ = __reduce_max_sync(0xffffffffu, (unsigned int)(work)); \
+    if ((tid & 31) == 0 && b == 0 && p < 256) { g_warp_end[p * 32 + (tid >> 5)] = (unsigned long long)clock64(); g_warp_work[p * 32 + (tid >> 5)] = wk_; } } while (0)
 #else
 #define PHASE(k)
+#define WARP_END(work)
 #endif
 
 // Weigh the CTA's particles against Y[p] and CTA-local scan: writes L[par] and the CTA partial (m_b, s_b).
@@ -272,6 +280,12 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const __grid_constant__ P
     if (P.T > 1) weigh_scan_finalize<Model>(P, 0, f, b, tid, active, j, x, sm, s_tab, &is_last);
 }
 
+// The step's single systematic-resampling uniform (one Philox call, the same for every thread)
+__device__ __forceinline__ double systematic_u0(const PfDev &P, const int p, const uint32_t fid) {
+    const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
+    return bits_to_d12(w.x, w.y) - 1.0;
+}
+
 // Ancestor of slot j at step p (pmcmc.py:187-193): first particle whose cdf exceeds u_j * total, by a two-level
 // search: CTA prefixes (shared or global memory), then the CTA's local scan L of the previous step.
 template <bool REPLAY>
@@ -281,9 +295,7 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
     double u;
     if (REPLAY) u = P.res_u[(size_t)(p - 1) * N + j];
     else if (P.resampler == SEM_RESAMPLE_SYSTEMATIC) {
-        const uint4 w = philox4x32_10(0u, 0u, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
-        const double u0 = bits_to_d12(w.x, w.y) - 1.0;
-        u = __ddiv_rn(__dadd_rn((double)j, u0), (double)N);
+        u = __ddiv_rn(__dadd_rn((double)j, systematic_u0(P, p, fid)), (double)N);
     } else {
         const uint4 w = philox4x32_10(0u, (uint32_t)j, (uint32_t)p, stream_word(DOM_RESAMPLE, fid), P.key);
         u = bits_to_d12(w.x, w.y) - 1.0;
@@ -334,7 +346,11 @@ __global__ void iteration_epilogue_kernel(const __grid_constant__ PfDev P) {
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
 // waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
 template <class Model, int ARITH>
+#ifdef SEM_PERSIST_MAXNREG
+__global__ void __maxnreg__(SEM_PERSIST_MAXNREG) pf_persistent(const __grid_constant__ PfDev P) {
+#else
 __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_constant__ PfDev P) {
+#endif
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double s_dyn[];          // pfx[nb], scale[nb] of the previous step (+ the sorted layout's exchange area)
@@ -360,9 +376,11 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
     const bool has = pidx < P.ppb && j < N;
     const bool starts = has && helper < 2;                   // resamples, gathers and starts the interval
     const bool active = has && (helper < 0 || helper >= 2);  // owns the particle at the observation time (store, weigh, scan)
-    __shared__ double s_cx[kLegs ? 2 : 1][32][Model::C], s_ct[kLegs ? 2 : 1][32];
-    __shared__ uint32_t s_ck[kLegs ? 2 : 1][32];
-    __shared__ int s_cfin[kLegs ? 2 : 1][32];
+    __shared__ double s_cx[(kLegs || kUnif) ? 2 : 1][32][Model::C], s_ct[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ uint32_t s_ck[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ int s_cfin[(kLegs || kUnif) ? 2 : 1][32];
+    __shared__ double s_cB[kUnif ? 2 : 1][32], s_ch[kUnif ? 2 : 1][32];   // rest of the uniformized loop's continuation
+    __shared__ uint32_t s_cu[kUnif ? 2 : 1][32][3];
     const uint32_t fid = P.filter_id0 + f;
     int32_t *Xf = P.X_hist + (size_t)f * P.hist_rows * Model::C * N;
     int32_t *Af = P.ancestry + (size_t)f * P.hist_rows * N;
@@ -466,13 +484,14 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
             Unif32State ust;
             unif32_begin(ust, P.dt);
             PairSource<false> aux;
-            int home = has ? pidx : -1;
+            int home = has ? pidx : -1, leg = 0, hg = 0;     // leg: 0 whole interval, 1 / 2 first / second leg of helper group hg
             if (starts) {
                 aux.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_AUX, fid));
                 double r0[Model::R], a00;
-                run = unif32_batch_setup(m, x, ust, aux, r0, a00);
+                run = unif32_batch_setup(m, x, ust, aux, r0, a00, s_tab);
                 ust.aux_k = aux.k;
             }
+            PHASE(12);
             if (sorted) {
                 const int NT = blockDim.x;
                 double *x_h = s_dyn + 2 * P.nb, *x_B = x_h + NT;
@@ -484,11 +503,14 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                 const uint32_t wmax = __reduce_max_sync(0xffffffffu, K), wmin = __reduce_min_sync(0xffffffffu, K ? K : 0xffffffffu);
                 if (lane == 0) { atomicMax(&x_hist[128], wmax); atomicMin(&x_hist[129], wmin); }
                 __syncthreads();
+                PHASE(13);
                 const uint32_t kmax = x_hist[128], kmin = min(x_hist[129], kmax);
-                const float inv = 127.0f / (float)(kmax - kmin + 1u);
-                const int bin = K ? min(127, (int)((float)(kmax - K) * inv)) : 127;      // descending in K
+                const float inv = 126.0f / (float)(kmax - kmin + 1u);
+                // descending in K; then the absorbed particles (nothing to run); threads without a particle come last
+                const int bin = !has ? 127 : K ? min(125, (int)((float)(kmax - K) * inv)) : 126;
                 const uint32_t rank = atomicAdd(&x_hist[bin], 1u);
                 __syncthreads();
+                PHASE(14);
                 const uint4 hh = reinterpret_cast<const uint4 *>(x_hist)[lane];           // every warp scans the 128 bins itself
                 const uint32_t s4 = hh.x + hh.y + hh.z + hh.w;
                 uint32_t inc = s4;
@@ -505,29 +527,72 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                     for (int c = 0; c < Model::C; c++) x_x[c * NT + pos] = (int32_t)x[c];
                 }
                 __syncthreads();
-                const int nchunks = NT >> 5, rnd = warp >> 2, r_last = (nchunks - 1) >> 2;
-                const int chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (warp & 3) : 3 - (warp & 3));
+                PHASE(15);
+                // Sorted chunk -> warp.  The main warps take the chunks in snake order over the schedulers.  When the
+                // chunks are 4 W + 1 or 4 W + 2 (P.split_main == -2) the last one or two are shared in TIME by two helper
+                // warps each, on different schedulers: warp 4W + g serves the first half of the batch's candidates
+                // and hands the continuation over, warp 4W + 2 + g finishes the interval -- W + 1/2 rounds per scheduler
+                // instead of W + 1 on two of them.
+#ifdef SEM_U32_NO_HELPERS
+                const int nw = NT >> 5, main_w = nw;
+#else
+                const int nw = NT >> 5, main_w = P.split_main == -2 ? nw - 4 : nw;
+#endif
+                int chunk;
+                if (warp < main_w) {
+                    const int rnd = warp >> 2, r_last = (main_w - 1) >> 2;
+                    chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (warp & 3) : 3 - (warp & 3));
+                } else {
+                    hg = (warp - main_w) & 1;
+                    leg = (warp - main_w) < 2 ? 1 : 2;
+                    chunk = main_w + hg;
+                }
                 const int slot = 32 * chunk + lane;
                 home = x_home[slot];
-                run = x_K[slot] > 0u;
-                if (home >= 0) {
+                run = false;
+                if (leg == 2) {                              // second leg: wait for the continuation
+                    asm volatile("bar.sync %0, 64;" ::"r"(1 + hg) : "memory");
+                    if (home >= 0) {
 #pragma unroll
-                    for (int c = 0; c < Model::C; c++) x[c] = (double)x_x[c * NT + slot];
-                }
-                if (run) {
-                    const int jr = b * P.ppb + home;
-                    m.setup(P.theta + (size_t)f * P.ntheta, x);
-                    src.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_SSA, fid));
-                    aux.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_AUX, fid));
-                    ust.h = x_h[slot]; ust.B = x_B[slot]; ust.last = x_K[slot]; ust.aux_k = x_aux[slot]; ust.in_batch = 1;
+                        for (int c = 0; c < Model::C; c++) x[c] = s_cx[hg][lane][c];
+                        if (!s_cfin[hg][lane]) {
+                            run = true;
+                            ust.t_rem = s_ct[hg][lane]; ust.B = s_cB[hg][lane]; ust.h = s_ch[hg][lane];
+                            ust.cand = s_ck[hg][lane]; ust.first = s_cu[hg][lane][0]; ust.last = s_cu[hg][lane][1]; ust.aux_k = s_cu[hg][lane][2];
+                        }
+                    }
+                } else {
+                    run = x_K[slot] > 0u;
+                    if (home >= 0) {
+#pragma unroll
+                        for (int c = 0; c < Model::C; c++) x[c] = (double)x_x[c * NT + slot];
+                    }
+                    if (run) { ust.h = x_h[slot]; ust.B = x_B[slot]; ust.last = x_K[slot]; ust.aux_k = x_aux[slot]; }
                 }
             }
+            if (sorted && run) m.setup(P.theta + (size_t)f * P.ntheta, x);
+            PHASE(11);
+            bool fin = true;
             if (run) {                                       // ONE call site of the loop
+                const int jr = sorted ? b * P.ppb + home : j;
                 long long fired = 0;
-                ssa_unif32_leg<Model, false>(m, x, ust, fired, false, src, aux, s_tab);
+                ust.in_batch = 1;
+                src.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_SSA, fid));
+                aux.init(P.key, (uint32_t)(P.j0 + jr), (uint32_t)p, stream_word(DOM_AUX, fid));
+                fin = ssa_unif32_leg<Model, false>(m, x, ust, fired, leg == 1, src, aux, s_tab);
                 pairs = fired;
             }
-            if (sorted && home >= 0) {                       // back to the home thread (read after the barrier below)
+            if (leg == 1) {                                  // hand over
+#pragma unroll
+                for (int c = 0; c < Model::C; c++) s_cx[hg][lane][c] = x[c];
+                s_ct[hg][lane] = ust.t_rem; s_cB[hg][lane] = ust.B; s_ch[hg][lane] = ust.h;
+                s_ck[hg][lane] = ust.cand; s_cu[hg][lane][0] = ust.first; s_cu[hg][lane][1] = ust.last; s_cu[hg][lane][2] = ust.aux_k;
+                s_cfin[hg][lane] = fin ? 1 : 0;
+                __threadfence_block();
+                asm volatile("bar.sync %0, 64;" ::"r"(1 + hg) : "memory");
+            }
+            WARP_END(run ? ust.last : 0u);
+            if (sorted && home >= 0 && leg != 1) {           // back to the home thread (read after the barrier below)
                 const int NT = blockDim.x;
                 int32_t *x_ret = (int32_t *)(s_dyn + 2 * P.nb + 2 * NT) + Model::C * NT;
 #pragma unroll
@@ -913,6 +978,7 @@ static void launch_step(const sem_pf_config *cfg, const PfDev &P, const WsLayout
     const dim3 grid(w.nb, cfg->n_filters);
     switch (cfg->model) {
         case SEM_MODEL_SIR: launch_model<SirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
+#ifndef SEM_ONLY_SIR                                         /* (reduced build of the probe / variant tools) */
         case SEM_MODEL_SEIR: launch_model<SeirModel>(P, p, cfg->arith, replay, grid, threads, s); break;
         default:
             switch (G) {
@@ -921,6 +987,9 @@ static void launch_step(const sem_pf_config *cfg, const PfDev &P, const WsLayout
                 case 3: launch_model<SubModel<3>>(P, p, cfg->arith, replay, grid, threads, s); break;
                 default: launch_model<SubModel<4>>(P, p, cfg->arith, replay, grid, threads, s); break;
             }
+#else
+        default: break;
+#endif
     }
 }
 
@@ -937,6 +1006,7 @@ static const void *persistent_kernel(const sem_pf_config *cfg) {
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
     switch (cfg->model) {
         case SEM_MODEL_SIR: return persistent_fn<SirModel>(cfg->arith);
+#ifndef SEM_ONLY_SIR
         case SEM_MODEL_SEIR: return persistent_fn<SeirModel>(cfg->arith);
         default:
             switch (G) {
@@ -945,6 +1015,9 @@ static const void *persistent_kernel(const sem_pf_config *cfg) {
                 case 3: return persistent_fn<SubModel<3>>(cfg->arith);
                 default: return persistent_fn<SubModel<4>>(cfg->arith);
             }
+#else
+        default: return persistent_fn<SirModel>(cfg->arith);
+#endif
     }
 }
 
@@ -959,7 +1032,19 @@ static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *
     const int e = w.ppb % 128, main_n = w.ppb - e;
     static int env_off = -1;
     if (env_off < 0) { const char *s = getenv("SEM_NO_SPLIT"); env_off = (s && s[0] == '1') ? 1 : 0; }
-    if (cfg->arith == SEM_ARITH_UNIFORMIZED32 && !env_off && C <= 4 && w.ppb > 32) *split_main = -1;
+    if (cfg->arith == SEM_ARITH_UNIFORMIZED32 && !env_off && C <= 4 && w.ppb > 32) {
+        const int nchunks = (w.ppb + 31) / 32, extra = nchunks % 4;          // sorted layout; helper legs for 4 W + 1 or + 2 chunks
+        static int env_nh = -1;
+        if (env_nh < 0) { const char *s = getenv("SEM_NO_HELPERS"); env_nh = (s && s[0] == '1') ? 1 : 0; }
+#ifdef SEM_U32_NO_HELPERS
+        env_nh = 1;
+#endif
+        if (!env_nh && nchunks >= 4 && (extra == 1 || extra == 2) && (nchunks - extra + 4) * 32 <= kMaxThreads) {
+            *split_main = -2;
+            return (nchunks - extra + 4) * 32;
+        }
+        *split_main = -1;
+    }
     if (legs && !env_off && main_n >= 128 && e > 0 && e <= 64 && main_n + 128 <= kMaxThreads) { *split_main = main_n; return main_n + 128; }
     return (w.ppb + 31) / 32 * 32;
 }
@@ -1101,6 +1186,11 @@ int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, con
 #ifdef SEM_PHASES
 int sem_debug_phases(unsigned long long *host_out) {
     SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 16 * 256));
+    return SEM_OK;
+}
+int sem_debug_warps(unsigned long long *end_out, unsigned int *work_out) {
+    SEM_CUDA(cudaMemcpyFromSymbol(end_out, g_warp_end, sizeof(unsigned long long) * 32 * 256));
+    SEM_CUDA(cudaMemcpyFromSymbol(work_out, g_warp_work, sizeof(unsigned int) * 32 * 256));
     return SEM_OK;
 }
 #endif

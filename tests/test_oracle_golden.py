@@ -186,6 +186,21 @@ def test_oracle_philox_logz_distribution_vs_reference(c_oracle):
         assert stats.ks_2samp(np.log(z), np.log(ref)).pvalue > 1e-3, arith             # same N, multinomial => same law
 
 
+@pytest.mark.parametrize("mu", [10.0, 37.5, 185.3, 2411.0])
+def test_batch_count_sampler_is_poisson(c_oracle, mu):
+    """The candidate count of a uniformized32 batch (PTRS with the slow path's logarithms folded, poisson_draw_u) follows
+    Poisson(mu): mean, variance and a Kolmogorov-Smirnov distance against scipy's cdf (discrete => conservative)."""
+    from scipy import stats
+    n = 40000
+    k = np.array([c_oracle.poisson_u_philox(mu, 77, i, 3) for i in range(n)])
+    assert np.all(k == np.floor(k)) and k.min() >= 0
+    assert abs(k.mean() - mu) < 4.5 * np.sqrt(mu / n)
+    assert abs(k.var() - mu) < 4.5 * mu * np.sqrt(2.0 / n + 1.0 / (mu * n))
+    ks = np.max(np.abs(np.searchsorted(np.sort(k), np.arange(k.min(), k.max() + 1), side="right") / n
+                       - stats.poisson.cdf(np.arange(k.min(), k.max() + 1), mu)))
+    assert ks < 1.95 / np.sqrt(n), ks                           # alpha ~ 1e-3 for a continuous law
+
+
 def test_fast32_stream_layout(c_oracle):
     """arith 3 (fast32): event k of a simulation takes words (2(k&1), 2(k&1)+1) of Philox call k>>1 as 32-bit uniforms
     u = w / 2^32; everything else is the FAST arithmetic.  Restated here in plain Python from the raw Philox words."""

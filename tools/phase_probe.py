@@ -5,10 +5,13 @@ import ctypes as C, os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = os.path.join(ROOT, "stochastic-epidemic-modelling_b200")
-dbg = "/tmp/libsem_b200_phases.so"
+dbg = os.path.join(ROOT, "tools", "micro", "libsem_b200_phases.so")      # git-ignored, travels with the snapshot
 src = [os.path.join(pkg, "csrc", f) for f in ("sem_pf.cu", "sem_sim_abc.cu")]
-subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--fmad=false", "-DSEM_PHASES",
-                       "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", dbg] + src)
+if "--build" in sys.argv or not os.path.exists(dbg):                       # (build it in the container: python tools/phase_probe.py --build)
+    subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--fmad=false", "-DSEM_PHASES",
+                           "-DSEM_ONLY_SIR", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", dbg] + src)
+    if "--build" in sys.argv:
+        sys.exit(0)
 import numpy as np, torch
 import sem_b200, workloads
 from sem_b200 import engine, _lib
@@ -16,7 +19,7 @@ _lib.LIB_PATH = dbg
 _lib._lib = None
 L = _lib.load()
 Y = workloads.headline_Y()
-N = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
+N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 100000
 cfg = engine.make_pf_config(0, N, 101, probs=.1, seed=1, mu=[20], n_population=[10000])
 out = engine.alloc_pf_outputs(cfg)
 for _ in range(3):
@@ -27,8 +30,8 @@ assert L.sem_debug_phases(buf.ctypes.data_as(C.c_void_p)) == 0
 ph = buf.reshape(256, 16)[1:100].astype(np.int64)
 # slots: 0 before grid.sync, 1 after, 2 after combine, 6 after ancestor search, 7 after gather+setup, 3 after SSA+store (own warp),
 # 4 after the CTA barrier, 8 after the thread's log-weight, 9 after the CTA max, 10 after exp + CTA scan, 5 after the stores.  SM cycle counter of CTA 0's SM (1.965 GHz).
-order = [0, 1, 2, 6, 7, 3, 4, 8, 9, 10, 5]
-names = ["grid.sync", "combine", "ancestor search", "gather+setup", "SSA+store (warp 0)", "wait CTA", "weights (warp 0)", "CTA max", "exp + CTA scan",
+order = [0, 1, 2, 6, 7, 12, 13, 14, 15, 11, 3, 4, 8, 9, 10, 5]
+names = ["grid.sync", "combine", "ancestor search", "gather+setup", "batch setup (K draw)", "sort: range", "sort: bins", "sort: scan + write", "sort: read", "SSA+store (warp 0)", "wait CTA", "weights (warp 0)", "CTA max", "exp + CTA scan",
          "store L, partial"]
 t = ph[:, order] / 1965.0
 d = np.diff(t, axis=1)
@@ -39,3 +42,16 @@ step = (t[1:, 0] - t[:-1, 0])
 print("  step-to-step            mean %.2f  total %.2f ms" % (step.mean(), step.sum() / 1e3))
 for p in (1, 10, 28, 60, 95):
     print("  step", p + 1, np.round(d[p], 2))
+
+# per-warp view of the SSA phase (CTA 0): when each warp left the loop (us after the phase started) and its candidate count
+we = np.zeros(256 * 32, dtype=np.uint64); ww = np.zeros(256 * 32, dtype=np.uint32)
+if hasattr(L, "sem_debug_warps") and L.sem_debug_warps(we.ctypes.data_as(C.c_void_p), ww.ctypes.data_as(C.c_void_p)) == 0:
+    we = we.reshape(256, 32).astype(np.int64); ww = ww.reshape(256, 32)
+    buf2 = buf.reshape(256, 16).astype(np.int64)
+    for p in (11, 29, 45, 61):
+        t0 = buf2[p, 11]
+        nw = int((we[p] > 0).sum())
+        rel = (we[p, :nw] - t0) / 1965.0
+        print(f"  step {p}: SSA phase of warp w (us after the exchange) / its largest K;  CTA barrier released at {(buf2[p, 4] - t0) / 1965.0:.2f}")
+        for s4 in range(4):
+            print("     sched", s4, " ".join(f"{rel[w]:7.2f}/{ww[p, w]:<5d}" for w in range(s4, nw, 4)))
