@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                 const uint32_t t0 = __shfl_sync(0xffffffffu, e0, sl), t1 = __shfl_sync(0xffffffffu, e1, sl),
                                t2 = __shfl_sync(0xffffffffu, e2, sl), t3 = __shfl_sync(0xffffffffu, e3, sl);
                 const int pos = (int)((sk == 0 ? t0 : sk == 1 ? t1 : sk == 2 ? t2 : t3) + rank);
-                x_K[pos] = K; x_home[pos] = home; x_h[pos] = ust.h; x_B[pos] = ust.B; x_aux[pos] = ust.aux_k;
+                x_K[pos] = K; x_home[pos] = home < 0 ? -1 : (home | (run ? 0x40000000 : 0)); x_h[pos] = ust.h;   // (K = 0 may still have to run: a batch that covers only part of the interval)
+                x_B[pos] = ust.B; x_aux[pos] = ust.aux_k;
                 if (has) {
 #pragma unroll
                     for (int c = 0; c < Model::C; c++) x_x[c * NT + pos] = (int32_t)x[c];
@@ -548,7 +549,9 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                     chunk = main_w + hg;
                 }
                 const int slot = 32 * chunk + lane;
-                home = x_home[slot];
+                const int hv = x_home[slot];
+                const bool run_rec = hv >= 0 && (hv & 0x40000000) != 0;
+                home = hv < 0 ? -1 : (hv & 0x3fffffff);
                 run = false;
                 if (leg == 2) {                              // second leg: wait for the continuation
                     asm volatile("bar.sync %0, 64;" ::"r"(1 + hg) : "memory");
@@ -562,7 +565,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                         }
                     }
                 } else {
-                    run = x_K[slot] > 0u;
+                    run = run_rec;
                     if (home >= 0) {
 #pragma unroll
                         for (int c = 0; c < Model::C; c++) x[c] = (double)x_x[c * NT + slot];

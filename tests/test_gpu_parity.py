@@ -701,3 +701,39 @@ def test_balanced_layout_matches_oracle(sem, c_oracle, F, N, model, G, theta, np
         assert np.array_equal(runs[0].ancestry[f].cpu().numpy(), ref["ancestry"])
         np.testing.assert_allclose(runs[0].log_zetas[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
         assert int(runs[0].n_events[f]) == ref["n_events"]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("F,N,model,theta,npop,mu,T", [
+    (1, 148 * 140, 0, [2.0, 1.0], [1000], [20], 6),             # 5 chunks of 32: 4 main warps + one helper group (4W+1)
+    (1, 148 * 170, 0, [2.0, 1.0], [1000], [20], 6),             # 6 chunks: two helper groups (4W+2)
+    (1, 148 * 128 - 7, 0, [2.0, 1.0], [1000], [20], 6),         # 4 chunks, no helpers, ragged last CTA
+    (1, 148 * 224, 0, [0.9, 0.5], [3000], [12], 8),             # 7 chunks (4W+3): no helpers
+    (2, 74 * 190, 1, [4.0, 1.0, 1.0], [1000], [20], 6),         # SEIR, two filters side by side, 6 chunks
+    (1, 148 * 140 + 33, 0, [1.1, 1.0], [400], [1.5], 12),       # most particles start or go extinct (nothing to run: K = 0)
+])
+def test_sorted_layout_matches_oracle(sem, c_oracle, F, N, model, theta, npop, mu, T):
+    """The uniformized whole-filter kernel sorts a CTA's particles by the candidate count of their batch, runs them at
+    their sorted position (helper legs for the last chunks) and sends the end state home through shared memory: a pure
+    scheduling change.  States, ancestors, likelihood and event count equal the launch-per-step path's and the oracle's."""
+    import torch
+    Y = _truth_Y(model, T, 5, .1, False)
+    th = np.tile(np.array(theta, float), (F, 1))
+    runs = []
+    for per_step in (False, True):
+        cfg = sem.engine.make_pf_config(model, N, T, n_filters=F, probs=.1, resampler=1, arith=4, seed=123, filter_id0=2, mu=mu,
+                                        n_population=npop, launch_per_step=per_step)
+        r = sem.engine.run_pf(cfg, Y, th)
+        torch.cuda.synchronize()
+        runs.append(r)
+    assert runs[0].launches == 1 and runs[1].launches > 1
+    assert torch.equal(runs[0].X_hist, runs[1].X_hist) and torch.equal(runs[0].ancestry, runs[1].ancestry)
+    assert torch.equal(runs[0].n_events, runs[1].n_events) and torch.equal(runs[0].status, runs[1].status)
+    np.testing.assert_allclose(runs[0].log_zetas.cpu().numpy(), runs[1].log_zetas.cpu().numpy(), rtol=1e-12, atol=1e-12)
+    for f in range(F):
+        ref = c_oracle.pf_run(model, Y, theta, False, .1, N, resampler=1, arith=4, seed=123, filter_id=2 + f, mu=mu, npop=npop)
+        assert int(runs[0].status[f]) == ref["collapsed"]
+        assert np.array_equal(runs[0].X_hist[f].permute(0, 2, 1).cpu().numpy(), ref["X_hist"])
+        assert np.array_equal(runs[0].ancestry[f].cpu().numpy(), ref["ancestry"])
+        np.testing.assert_allclose(runs[0].log_zetas[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
+        assert int(runs[0].n_events[f]) == ref["n_events"]
