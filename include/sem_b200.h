@@ -51,7 +51,9 @@ enum { SEM_RESAMPLE_MULTINOMIAL = 0, SEM_RESAMPLE_SYSTEMATIC = 1 };
  * UNIFORMIZED32 is the production form of UNIFORMIZED: 32-bit candidate uniforms (candidate c takes word (c & 3) of Philox
  * call c >> 2: four candidates per call), a bound that anticipates growth (B = max(a0(x), a0(x + drift h)) (1 + 2/sqrt(a0 h + 1)),
  * batches shortened so that the anticipated growth stays below 1.25), and no direct-method tail.  Same law of the state
- * at the end of the interval as the direct method.  The Python layer's default "auto" picks UNIFORMIZED32 for SIR / SEIR
+ * at the end of the interval as the direct method.  Because a batch's candidate count is drawn BEFORE the loop runs, the
+ * whole-filter kernel sorts each CTA's particles by it so that the lanes of a warp carry equal work (a scheduling change
+ * only: streams are keyed by the particle).  The Python layer's default "auto" picks UNIFORMIZED32 for SIR / SEIR
  * filters and FAST32 otherwise. */
 enum { SEM_ARITH_REFERENCE = 0, SEM_ARITH_FAST = 1, SEM_ARITH_UNIFORMIZED = 2, SEM_ARITH_FAST32 = 3, SEM_ARITH_UNIFORMIZED32 = 4 };
 
