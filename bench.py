@@ -37,15 +37,14 @@ import workloads  # noqa: E402
 # budget of 128 "to be replaced by ncu smsp__inst_executed / events once the kernel exists"; these are the measured
 # values: smsp__inst_executed.sum x thread_inst_per_inst / n_events over the whole-filter kernel
 # (profiles/r01c_pf_persistent_final.txt: 4.4271e9 x 26.49 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
-# uniformized32, sorted layout (profiles/r01e_pf_persistent_uniformized32_sorted.txt): 3.4163e9 x 29.39 / 1.5888e9 fired
-# events (the plain / balanced layouts read 61.8 with 25.1 active lanes: the sorted layout executes 13 % fewer warp
-# instructions with fuller warps).
-I_ALG_BY_ARITH = {"uniformized32": 63.2, "fast32": 73.4, "fast": 106.0}
+# uniformized32, sorted layout (profiles/r01e_pf_persistent_uniformized32_sorted.txt): 3.2797e9 x 29.34 / 1.5888e9 fired
+# events (the balanced layout of round 1d read 3.911e9 x 25.10 / 1.588e9 = 61.8: 16 % more warp instructions, emptier warps).
+I_ALG_BY_ARITH = {"uniformized32": 60.6, "fast32": 73.4, "fast": 106.0}
 I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
 LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
 # dram__bytes_read.sum + dram__bytes_write.sum of one whole-filter launch (ncu --set full, same profile)
-DRAM_TRAFFIC_PER_PASS = {"uniformized32": 0.632832e6 + 146.818048e6, "fast32": 883.968e3 + 143.988224e6}
+DRAM_TRAFFIC_PER_PASS = {"uniformized32": 0.62848e6 + 149.0688e6, "fast32": 883.968e3 + 143.988224e6}
 
 
 def measured_peaks():

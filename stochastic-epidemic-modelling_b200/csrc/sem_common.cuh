@@ -874,12 +874,27 @@ __device__ __forceinline__ bool unif32_batch_setup(const Model &m, const double 
     return true;
 }
 
+// Every reaction of these models lowers sum_g (3 S_g + 2 E_g + I_g) by exactly one (infection: S-1 and E+1 or I+1;
+// E -> I; recovery: I-1; the SIR models have no E), so the number of fired events of a leg is the drop of that tally --
+// the loop need not count (two instructions per candidate).  Exact: the counts are integers far below 2^53.
+template <class Model>
+__device__ __forceinline__ double event_tally(const double *x) {
+    double t = 0.0;
+    if constexpr (Model::C == 4) t = 3.0 * x[0] + 2.0 * x[1] + x[2];          // SEIR: S, E, I, R
+    else {
+#pragma unroll
+        for (int g = 0; g < Model::G; g++) t += 2.0 * x[3 * g] + x[3 * g + 1]; // SIR (sub)groups: S, I, R per group
+    }
+    return t;
+}
+
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32State &st, long long &fired_total, const bool handoff,
                                                PairSource<false> &src, PairSource<false> &aux, const double2 *tab) {
     PairSource<false> loc = src;
     aux.k = st.aux_k;
     bool finished = true;
+    const double tally0 = event_tally<Model>(x);
     for (;;) {
         double r[Model::R], a0;
         if (!st.in_batch) {
@@ -891,7 +906,6 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
         // a first leg serves the first half of the batch's candidates only: the loop is the same, its bound differs
         const uint32_t last = handoff ? st.first + ((st.last - st.first) >> 1) : st.last;
         uint32_t cand = st.cand;
-        int fired = 0;
         bool stop = false;
         while (cand < last && !stop) {
             loc.k = cand >> 2;
@@ -909,14 +923,12 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
 #pragma unroll
                 for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
                 if (hit) m.template apply<TRACK_R>(x, j);
-                fired += hit ? 1 : 0;
                 a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
                 stop = stop || (hit && !(a0 > 0 && a0 <= B));          // absorbed (a0 = 0) or bound violated
                 cand += live ? 1u : 0u;
             }
         }
         st.cand = cand;
-        fired_total += fired;
         if (!stop && cand < st.last) { finished = false; break; }      // hand-over point reached (first leg only)
         st.in_batch = 0;
         if (!(stop && a0 > B)) {                                       // not violated: the batch covered its h exactly
@@ -932,6 +944,7 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
     }
     st.aux_k = aux.k;
     src.k = loc.k;
+    fired_total += (long long)(tally0 - event_tally<Model>(x));
     if (!TRACK_R) m.fix_removed(x);                                      // (also on a hand-over: the next leg's setup sums the state)
     return finished;
 }
