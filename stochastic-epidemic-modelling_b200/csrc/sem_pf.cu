@@ -56,10 +56,7 @@ struct PfDev {
     double *summary;
 };
 
-#ifndef SEM_MAX_THREADS
-#define SEM_MAX_THREADS 768
-#endif
-constexpr int kMaxThreads = SEM_MAX_THREADS;
+constexpr int kMaxThreads = 768;
 constexpr int kMaxThreadsUnif = 352;      // the uniformized step keeps more live state: two 352-thread CTAs per SM, <= 93 registers
 
 // CTA-wide max / inclusive scan: warp shuffles, one shared-memory slot per warp, and a second shuffle pass over the
@@ -346,11 +343,7 @@ __global__ void iteration_epilogue_kernel(const __grid_constant__ PfDev P) {
 // a grid.sync(); after it every CTA combines the nb CTA partials itself (nb <= 1024 values, redundantly) instead of
 // waiting for a "last CTA" and a new launch.  Same arithmetic as pf_init + pf_step, bit-identical results.
 template <class Model, int ARITH>
-#ifdef SEM_PERSIST_MAXNREG
-__global__ void __maxnreg__(SEM_PERSIST_MAXNREG) pf_persistent(const __grid_constant__ PfDev P) {
-#else
 __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_constant__ PfDev P) {
-#endif
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double s_dyn[];          // pfx[nb], scale[nb] of the previous step (+ the sorted layout's exchange area)
@@ -534,11 +527,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_persistent(const __grid_consta
                 // warps each, on different schedulers: warp 4W + g serves the first half of the batch's candidates
                 // and hands the continuation over, warp 4W + 2 + g finishes the interval -- W + 1/2 rounds per scheduler
                 // instead of W + 1 on two of them.
-#ifdef SEM_U32_NO_HELPERS
-                const int nw = NT >> 5, main_w = nw;
-#else
                 const int nw = NT >> 5, main_w = P.split_main == -2 ? nw - 4 : nw;
-#endif
                 int chunk;
                 if (warp < main_w) {
                     const int rnd = warp >> 2, r_last = (main_w - 1) >> 2;
@@ -1039,9 +1028,6 @@ static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *
         const int nchunks = (w.ppb + 31) / 32, extra = nchunks % 4;          // sorted layout; helper legs for 4 W + 1 or + 2 chunks
         static int env_nh = -1;
         if (env_nh < 0) { const char *s = getenv("SEM_NO_HELPERS"); env_nh = (s && s[0] == '1') ? 1 : 0; }
-#ifdef SEM_U32_NO_HELPERS
-        env_nh = 1;
-#endif
         if (!env_nh && nchunks >= 4 && (extra == 1 || extra == 2) && (nchunks - extra + 4) * 32 <= kMaxThreads) {
             *split_main = -2;
             return (nchunks - extra + 4) * 32;

@@ -5,7 +5,7 @@ import ctypes as C, os, sys, subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = os.path.join(ROOT, "stochastic-epidemic-modelling_b200")
-dbg = os.path.join(ROOT, "tools", "micro", "libsem_b200_phases.so")      # git-ignored, travels with the snapshot
+dbg = os.environ.get("SEM_PHASES_LIB") or os.path.join(ROOT, "tools", "micro", "libsem_b200_phases.so")      # git-ignored, travels with the snapshot
 src = [os.path.join(pkg, "csrc", f) for f in ("sem_pf.cu", "sem_sim_abc.cu")]
 if "--build" in sys.argv or not os.path.exists(dbg):                       # (build it in the container: python tools/phase_probe.py --build)
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--fmad=false", "-DSEM_PHASES",
