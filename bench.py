@@ -10,8 +10,11 @@ cooperative kernel launch (pf_persistent).
 Metric: particle-steps/s (one particle advanced across one observation interval, including its share of
 weighting + resampling).  Prints ONE JSON line (rank 0).
 
-N > 1 (torchrun): every rank runs its own independent filter (independent PMCMC chains shard trivially,
-SURVEY 8(e)(2)); no data-path collective; weak scaling; value = all ranks' particle-steps / max-over-ranks time.
+N > 1 (torchrun): ONE filter of N x 1e5 particles sharded over the N ranks (SURVEY 8(e)(3), weak scaling): global
+systematic resampling, the resampling barrier and the particle migration run inside the ranks' kernels over peer
+memory (NVLink), one cooperative launch per rank and pass (sem_pf_run_sharded).  value = the sharded filter's
+particle-steps / max-over-ranks device time.  The figure for N independent filters (independent PMCMC chains,
+SURVEY 8(e)(2), no data-path exchange) is kept as the secondary key "independent_chains".
 
 --impl reference: the reference's CPU algorithm for the same path, timed on this box's host cores.  The reference
 itself is pure Python and cannot travel to the GPU box, so this arm runs its C restatement (oracle/sem_oracle.c,
@@ -257,6 +260,9 @@ def main():
     ap.add_argument("--resampler", default="systematic")
     ap.add_argument("--arith", default="auto", help="auto = uniformized32 for SIR/SEIR filters, fast32 otherwise (and for ABC)")
     ap.add_argument("--block", type=int, default=0)
+    ap.add_argument("--exchange", default="auto", choices=["auto", "pull", "push"],
+                    help="N = 1 only: pull = whole-filter kernel with grid barrier + ancestor search (sem_pf_run); push = the "
+                         "sharded filter's kernel with one rank (resampling in offspring form through the record buffers)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded"],
@@ -307,8 +313,25 @@ def main():
     thd = torch.from_numpy(theta).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream()
+    sharded_mode = world > 1 or args.exchange == "push"
+    peer = None
+    if sharded_mode:                                                      # one filter of world x N particles over the ranks
+        from sem_b200 import sharded as shd
+        peer = shd.PeerFilter(rank, world, 0, Y, N, theta=theta, probs=w["probs"], observations=w["observations"],
+                              arith=args.arith, seed=1234, mu=[w["mu"]], n_population=[w["n_population"]],
+                              block_particles=args.block, want_handle=world > 1)
+        if world > 1:
+            shd.connect_distributed(peer)
+
+    class _Res:                                                           # what the report below reads
+        pass
 
     def one_pass(i):
+        if peer is not None:
+            peer.run(theta, filter_id=i)
+            r = _Res()
+            r.n_events, r.status, r.log_zetas, r.launches = peer.out[4], peer.out[3], peer.out[2], 1
+            return r
         cfg.filter_id0 = (rank * 4096 + i) & 0xFFFFFF
         return engine.run_pf(cfg, Yd, thd, out=out)
 
@@ -341,6 +364,27 @@ def main():
         dist.all_reduce(t_max, op=dist.ReduceOp.MAX)
     dev_ms_max = float(t_max.cpu()[0])
     value = world * K * N * (T - 1) / (dev_ms_max / 1e3)
+    events_all = torch.tensor([events_last], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(events_all)                                      # the sharded filter's events are spread over the ranks
+    independent = None
+    if world > 1:                                                        # secondary: N independent filters (no exchange at all)
+        K2 = max(3, min(K, 10))
+        cfg.filter_id0 = rank * 4096
+        for i in range(2):
+            engine.run_pf(cfg, Yd, thd, out=out)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(K2):
+            cfg.filter_id0 = (rank * 4096 + 100 + i) & 0xFFFFFF
+            engine.run_pf(cfg, Yd, thd, out=out)
+        e1.record(stream)
+        torch.cuda.synchronize()
+        t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        independent = {"value": world * K2 * N * (T - 1) / (float(t2.cpu()[0]) / 1e3), "unit": "particle-steps/s", "steps": K2,
+                       "note": "N independent filters of 1e5 particles, one per GPU (independent PMCMC chains); L2 not flushed"}
 
     # ---------------------------------------------------------------- end-to-end through the public API
     e2e = None
@@ -348,15 +392,16 @@ def main():
         np.random.seed(rank)
         st = {}
         n_it = max(8, min(K, 40))                                        # MH iterations in the timed call (its setup is inside)
-        sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=3, probs=w["probs"], n_particles=N,
-                               n_population=w["n_population"], mu=w["mu"], seed=77 + rank)          # warm-up
+        shard_kw = dict(sharded=True) if world > 1 else {}
+        sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=3, probs=w["probs"], n_particles=world * N,
+                               n_population=w["n_population"], mu=w["mu"], seed=77, **shard_kw)          # warm-up
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
         sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=n_it, probs=w["probs"],
-                               n_particles=N, n_population=w["n_population"], mu=w["mu"], seed=99 + rank, stats=st,
-                               resampler=args.resampler, arith=args.arith)
+                               n_particles=world * N, n_population=w["n_population"], mu=w["mu"], seed=99, stats=st,
+                               resampler=args.resampler, arith=args.arith, **shard_kw)
         torch.cuda.synchronize()
         te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
         if world > 1:
@@ -364,10 +409,14 @@ def main():
         e2e_s = float(te.cpu()[0])
         runs = st["filter_runs"]
         e2e = {"value": world * runs * N * (T - 1) / e2e_s, "unit": "particle-steps/s",
-               "h2d_bytes_per_step": int(theta.nbytes + Y.nbytes / runs), "d2h_bytes_per_step": int(8 * (4 + T * 3)),
+               "h2d_bytes_per_step": int(world * (theta.nbytes + Y.nbytes / runs)), "d2h_bytes_per_step": int(world * 8 * (4 + T * 3)),
                "api": "sem_b200.particle_mcmc (drop-in for pmcmc.py:251): host numpy in, host numpy out, one filter pass + "
-                      "path sample per MH iteration", "iterations": runs, "pmcmc_iters_per_s": world * runs / e2e_s}
+                      "path sample per MH iteration" + ("; sharded=True: ONE chain whose filter of world x 1e5 particles is "
+                      "sharded over the ranks (setup of the peer arenas inside the timed call)" if world > 1 else ""),
+               "iterations": runs, "pmcmc_iters_per_s": (1 if world > 1 else world) * runs / e2e_s}
         # the other public call: particle_filter returning the reference's full (T,N,C)+(T,N) float64 history on the host
+        sem_b200.particle_filter(Y, sem_b200.ModelType.SIR, theta, w["observations"], w["probs"], N, w["n_population"], w["mu"],
+                                 seed=4, resampler=args.resampler, arith=args.arith)                    # warm-up (staging buffers)
         t0 = time.perf_counter()
         z, H, A = sem_b200.particle_filter(Y, sem_b200.ModelType.SIR, theta, w["observations"], w["probs"], N,
                                            w["n_population"], w["mu"], seed=5, resampler=args.resampler, arith=args.arith)
@@ -382,12 +431,14 @@ def main():
         hbm_peak, sm_max, how = measured_peaks()
         f_sm = (clocks["sm_mhz"] or sm_max) * 1e6
         per_gpu_ms = dev_ms / K
-        events_per_s = events_last / (per_gpu_ms / 1e3)
+        events_per_s = float(events_all.cpu()[0]) / world / (per_gpu_ms / 1e3)          # per GPU
+        events_last = float(events_all.cpu()[0]) / world
         issue_peak = LANES * f_sm
         i_alg = I_ALG_BY_ARITH.get(args.arith, I_ALG_DECLARED)
         launches = res.launches
         traffic = DRAM_TRAFFIC_PER_PASS.get(args.arith) if (N == workloads.HEADLINE["n_particles"] and launches == 1) else None
-        roofline = {"bound": "issue", "kernel": ("pf_persistent" if launches == 1 else "pf_step") + f"<SirModel, {args.arith}>",
+        kname = "pf_persistent_x" if sharded_mode else ("pf_persistent" if launches == 1 else "pf_step")
+        roofline = {"bound": "issue", "kernel": kname + f"<SirModel, {args.arith}>",
                     "achieved": events_per_s * i_alg / 1e9, "peak": issue_peak / 1e9, "unit": "Gthread-inst/s",
                     "frac": events_per_s * i_alg / issue_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
                     "events_per_s": events_per_s,
@@ -410,7 +461,13 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": w["name"], "model": "SIR", "n_particles": N, "n_obs": T, "population": w["n_population"],
                        "theta": list(theta), "obs_model": "binomial p=0.1", "resampler": args.resampler, "arith": args.arith,
-                       "l2": "flushed between timed iterations (256 MiB write)", "parallelism": f"{world} independent filters"},
+                       "l2": "flushed between timed iterations (256 MiB write)",
+                       "n_particles_global": world * N,
+                       "parallelism": (f"one filter of {world}x{N} particles sharded over {world} GPUs: global systematic resampling, "
+                                       "CTA weight partials + child records exchanged through peer memory inside one cooperative "
+                                       "launch per rank (no NCCL call, no host work per step)") if world > 1 else
+                                      ("1 GPU, push-form resampling (sharded kernel, one rank)" if sharded_mode else "1 GPU")},
+            "independent_chains": independent,
             "pmcmc_iters_per_s": world * K / (dev_ms_max / 1e3), "events_per_s": events_per_s * world,
             "log_likelihood": logz, "gpu_launches": K * res.launches, "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "e2e": e2e, "wall_s_timed_region": t_wall,

@@ -62,7 +62,8 @@ enum {
     SEM_ERR_INVALID = -1,   /* bad argument */
     SEM_ERR_CUDA = -2,      /* CUDA runtime error */
     SEM_ERR_REPLAY = -3,    /* replay buffer exhausted */
-    SEM_ERR_NO_DEVICE = -4  /* no sm_100 device */
+    SEM_ERR_NO_DEVICE = -4, /* no sm_100 device */
+    SEM_ERR_PEER = -5       /* sharded filter: a peer rank did not answer within the exchange's time limit */
 };
 
 int sem_abi_version(void);
@@ -170,6 +171,51 @@ int sem_shard_offspring(const sem_pf_config *cfg, const sem_pf_buffers *buf, con
  * ancestry[p] (global indices), weighs against Y[p] and refreshes summary */
 int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, const sem_shard_step *st,
                         const int32_t *recv_records, double *summary, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Particle-sharded filter with the exchange on the device (one cooperative launch per rank for the WHOLE filter,
+ * no host work and no collective call per step).  Every rank runs sem_pf_run_sharded with the same cfg
+ * (cfg->n_particles = particles per rank, equal on all ranks; n_filters = 1; resampler = systematic); rank r owns the
+ * global particles [r n, (r+1) n).  The resampling barrier and the particle migration go through peer memory (NVLink):
+ * each rank owns an "arena" that every other rank has mapped (CUDA IPC between processes, peer access inside one
+ * process).  Per step every CTA stores its 16-byte weight partial into every rank's arena and every parent particle
+ * stores one record (state, global parent index) per child into the arena of the rank that owns the child's slot;
+ * readers poll for the data itself.  Replaces the globalised form of pmcmc.py:183-199.
+ * Results equal the single-GPU filter of W n particles with the same seed and CTA size.
+ * ---------------------------------------------------------------------------------------------- */
+#define SEM_MAX_RANKS 8
+typedef struct sem_xchg_desc {
+    int32_t world, rank;
+    uint32_t generation;    /* running counter of exchange generations: 0 after sem_xchg_reset; advanced by every run */
+    uint32_t launch_tag;    /* advanced by every run (path-sampler tokens) */
+    double timeout_s;       /* a rank that waits longer than this for a peer gives up: status SEM_ERR_PEER (<= 0: 20 s) */
+    void *arena[SEM_MAX_RANKS];  /* every rank's arena as mapped in THIS process; arena[rank] is this rank's own */
+} sem_xchg_desc;
+
+/* bytes of one rank's arena for this configuration (identical on every rank) */
+size_t sem_xchg_bytes(const sem_pf_config *cfg, int32_t world);
+/* cudaMalloc an arena on the current device and export its CUDA IPC handle (64 bytes, may be NULL) */
+int sem_xchg_alloc(size_t bytes, void **arena, unsigned char *ipc_handle);
+/* map a peer process's arena from its IPC handle / unmap it / free an own arena */
+int sem_xchg_open(const unsigned char *ipc_handle, void **peer_arena);
+int sem_xchg_close(void *peer_arena);
+int sem_xchg_free(void *arena);
+/* same-process multi-GPU: let `device` access `peer_device`'s memory (idempotent) */
+int sem_peer_enable(int32_t device, int32_t peer_device);
+/* fill an own arena with the "empty" marks.  Needed once before the first run and after a run that ended with a
+ * non-zero status (collapse or SEM_ERR_PEER); all ranks must have reset (host barrier) before any rank launches again,
+ * and the descriptor's generation restarts at 0. */
+int sem_xchg_reset(const sem_pf_config *cfg, int32_t world, void *arena, void *stream);
+/* this rank's packed iteration result inside its arena (device double[SEM_ITER_HEADER + T*C]); pass it as
+ * buf->iteration_result to have the run end with the path sample over all shards: every rank receives the same
+ * trajectory; header = { log_zetas[T-1], status, this rank's n_events, chosen GLOBAL final particle } */
+double *sem_xchg_iteration_result(const sem_pf_config *cfg, int32_t world, void *arena);
+/* 1 when this configuration can run with the device-side exchange (all CTAs of a rank co-resident, n_filters = 1,
+ * systematic resampling, world <= SEM_MAX_RANKS, Philox mode), else 0 with the reason in sem_last_error() */
+int sem_pf_sharded_supported(const sem_pf_config *cfg, int32_t world);
+/* one filter pass of this rank's shard.  ancestry holds GLOBAL parent indices; log_zetas / status are identical on all
+ * ranks.  X0 (if given) is this rank's slice [C][n].  Advances x->generation and x->launch_tag. */
+int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_xchg_desc *x, void *stream);
 
 /* particle_path_sampler (pmcmc.py:236-248).  chosen < 0: pick uniformly with Philox(seed); exact = 0 keeps
  * the reference's off-by-one ancestry indexing, 1 follows the true genealogy.  traj: device [T][C] int32. */

@@ -14,12 +14,16 @@ OBS_BINOMIAL, OBS_NORMAL = 0, 1
 RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC = 0, 1
 ARITH_REFERENCE, ARITH_FAST = 0, 1
 ERR_REPLAY = -3
+ERR_PEER = -5
+SEM_MAX_RANKS = 8
 
 EXPORTS = [
     "sem_abi_version", "sem_last_error", "sem_device_info",
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
     "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
     "sem_ssa_simulate", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
+    "sem_xchg_bytes", "sem_xchg_alloc", "sem_xchg_open", "sem_xchg_close", "sem_xchg_free", "sem_peer_enable",
+    "sem_xchg_reset", "sem_xchg_iteration_result", "sem_pf_sharded_supported", "sem_pf_run_sharded",
     "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson", "sem_test_fast_math",
 ]
 
@@ -48,6 +52,13 @@ class ShardStep(C.Structure):
         ("step", C.c_int32), ("particle_offset", C.c_int32), ("n_global", C.c_int64), ("u0", C.c_double),
         ("total", C.c_double), ("total_local", C.c_double), ("G", C.c_double), ("G_next", C.c_double), ("s", C.c_double),
         ("slot0", C.c_int64),
+    ]
+
+
+class XchgDesc(C.Structure):
+    _fields_ = [
+        ("world", C.c_int32), ("rank", C.c_int32), ("generation", C.c_uint32), ("launch_tag", C.c_uint32),
+        ("timeout_s", C.c_double), ("arena", C.c_void_p * SEM_MAX_RANKS),
     ]
 
 
@@ -102,6 +113,26 @@ def load():
     L.sem_shard_propagate.restype = C.c_int
     L.sem_shard_propagate.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(ShardStep), C.c_void_p, C.c_void_p,
                                       C.c_void_p]
+    L.sem_xchg_bytes.restype = C.c_size_t
+    L.sem_xchg_bytes.argtypes = [C.POINTER(PfConfig), C.c_int32]
+    L.sem_xchg_alloc.restype = C.c_int
+    L.sem_xchg_alloc.argtypes = [C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]
+    L.sem_xchg_open.restype = C.c_int
+    L.sem_xchg_open.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    L.sem_xchg_close.restype = C.c_int
+    L.sem_xchg_close.argtypes = [C.c_void_p]
+    L.sem_xchg_free.restype = C.c_int
+    L.sem_xchg_free.argtypes = [C.c_void_p]
+    L.sem_peer_enable.restype = C.c_int
+    L.sem_peer_enable.argtypes = [C.c_int32, C.c_int32]
+    L.sem_xchg_reset.restype = C.c_int
+    L.sem_xchg_reset.argtypes = [C.POINTER(PfConfig), C.c_int32, C.c_void_p, C.c_void_p]
+    L.sem_xchg_iteration_result.restype = C.c_void_p
+    L.sem_xchg_iteration_result.argtypes = [C.POINTER(PfConfig), C.c_int32, C.c_void_p]
+    L.sem_pf_sharded_supported.restype = C.c_int
+    L.sem_pf_sharded_supported.argtypes = [C.POINTER(PfConfig), C.c_int32]
+    L.sem_pf_run_sharded.restype = C.c_int
+    L.sem_pf_run_sharded.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(XchgDesc), C.c_void_p]
     L.sem_path_sample.restype = C.c_int
     L.sem_path_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]

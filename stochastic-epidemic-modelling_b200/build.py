@@ -13,14 +13,16 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsem_b200.so")
-SOURCES = ["sem_pf.cu", "sem_sim_abc.cu"]
-HEADERS = ["sem_common.cuh", "sem_host.h", "sem_logtab.inc", os.path.join("..", "..", "include", "sem_b200.h")]
+SOURCES = ["sem_pf.cu", "sem_pf_xchg.cu", "sem_sim_abc.cu"]
+HEADERS = ["sem_common.cuh", "sem_host.h", "sem_pf_dev.cuh", "sem_pf_host.h", "sem_logtab.inc",
+           os.path.join("..", "..", "include", "sem_b200.h")]
+OBJ_DIR = os.path.join(HERE, "build")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
     "--fmad=false",          # integer outcomes must not depend on FMA contraction (parity with the CPU oracle)
-    "-Xcompiler", "-fPIC", "-shared",
+    "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ]
 
@@ -41,17 +43,34 @@ def stale():
 
 
 def build(force=False, verbose=False):
+    """One nvcc process per translation unit (in parallel), then one link step.  SEM_BUILD_DEFINES="-DSEM_ONLY_SIR" etc.
+    passes extra defines (development builds)."""
     if not force and not stale():
         return LIB
-    cmd = [nvcc_path()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
-    env = dict(os.environ)
-    # the image exports CC=/opt/gcc/bin/gcc; let nvcc use the system host compiler
-    res = subprocess.run(cmd + ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else cmd,
-                         capture_output=True, text=True, env=env)
-    log = res.stdout + res.stderr
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = nvcc_path()
+    ccbin = ["-ccbin", "/usr/bin/g++"] if os.path.exists("/usr/bin/g++") else []   # the image exports CC=/opt/gcc/bin/gcc
+    extra = os.environ.get("SEM_BUILD_DEFINES", "").split()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc] + NVCC_FLAGS + extra + ccbin + ["-c", os.path.join(CSRC, src), "-o", obj]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, " ".join(cmd) + "\n" + res.stdout + res.stderr, res.returncode
+
+    with ThreadPoolExecutor(len(SOURCES)) as ex:
+        done = list(ex.map(compile_one, SOURCES))
+    log = "\n".join(d[1] for d in done)
+    rc = max(d[2] for d in done)
+    if rc == 0:
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a"] + ccbin + ["-o", LIB] + [d[0] for d in done]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        log += "\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr
+        rc = res.returncode
     with open(os.path.join(HERE, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if rc != 0:
         sys.stderr.write(log)
         raise RuntimeError("nvcc failed building libsem_b200.so")
     if verbose:

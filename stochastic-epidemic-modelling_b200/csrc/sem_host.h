@@ -22,14 +22,12 @@ inline void set_error(const char *fmt, const char *a = "", const char *b = "") {
 inline int model_cols(int model, int G) { return model == SEM_MODEL_SIR ? 3 : model == SEM_MODEL_SEIR ? 4 : 3 * G; }
 inline int model_ntheta(int model, int G) { return model == SEM_MODEL_SIR ? 2 : model == SEM_MODEL_SEIR ? 3 : G * G + 1; }
 
-inline int sm_count() {
-    static int n_sm = 0;
-    if (!n_sm) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) n_sm = n;
-        else n_sm = 148;
-    }
-    return n_sm;
+inline int sm_count() {                                      // of the CURRENT device (cached per device)
+    static int n_sm[64] = {0};
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!n_sm[dev]) n_sm[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
+    return n_sm[dev];
 }
 
 }  // namespace sem

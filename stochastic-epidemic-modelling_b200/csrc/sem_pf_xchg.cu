@@ -1,0 +1,213 @@
+// sem_pf_xchg.cu -- one particle filter sharded over the GPUs of a node, exchange on the device.
+//
+// Every rank launches pf_persistent_x once per filter pass (cooperative launch: all of its CTAs are co-resident and may
+// spin on each other and on the peers).  The body is the single-GPU whole-filter kernel (sem_pf_dev.cuh,
+// pf_persistent_body<.., PUSH = true>): same SSA loops, same layouts, same weights; what changes is the resampling
+// step, which globalises pmcmc.py:183-199 over peer memory -- see the "peer-memory exchange" block of sem_pf_dev.cuh.
+// This file holds the kernel instantiations, the arena layout, CUDA IPC plumbing and the launch.
+#include "sem_pf_host.h"
+
+namespace sem {
+
+template <class Model, int ARITH>
+__global__ void __launch_bounds__(kMaxThreads) pf_persistent_x(const __grid_constant__ PfDev P, const __grid_constant__ XchgDev X) {
+    pf_persistent_body<Model, ARITH, true>(P, &X);
+}
+
+template <class Model>
+static const void *xchg_fn(int arith) {
+    return arith == SEM_ARITH_UNIFORMIZED32 ? (const void *)pf_persistent_x<Model, SEM_ARITH_UNIFORMIZED32>
+         : arith == SEM_ARITH_FAST32        ? (const void *)pf_persistent_x<Model, SEM_ARITH_FAST32>
+                                            : nullptr;
+}
+static const void *xchg_kernel(const sem_pf_config *cfg) {
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    switch (cfg->model) {
+        case SEM_MODEL_SIR: return xchg_fn<SirModel>(cfg->arith);
+#ifndef SEM_ONLY_SIR
+        case SEM_MODEL_SEIR: return xchg_fn<SeirModel>(cfg->arith);
+        default:
+            switch (G) {
+                case 1: return xchg_fn<SubModel<1>>(cfg->arith);
+                case 2: return xchg_fn<SubModel<2>>(cfg->arith);
+                case 3: return xchg_fn<SubModel<3>>(cfg->arith);
+                default: return xchg_fn<SubModel<4>>(cfg->arith);
+            }
+#else
+        default: return nullptr;
+#endif
+    }
+}
+
+// One rank's arena: control block (error flag, path-sampler mailbox), partial tables [3][NB], record buffers [2][N][RW],
+// packed iteration result.  Identical on every rank (same cfg, same device type).
+struct ArenaLayout { size_t err, mail, part, rec, iter, bytes; int NB, nb, RW, C; };
+
+static ArenaLayout arena_layout(const sem_pf_config *cfg, int world) {
+    ArenaLayout a;
+    const WsLayout w = ws_layout(cfg);
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    a.C = model_cols(cfg->model, G);
+    a.RW = (a.C + 1 + 3) & ~3;
+    a.nb = w.nb; a.NB = w.nb * world;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    a.err = take(64); a.mail = take(64);
+    a.part = take(3 * (size_t)a.NB * sizeof(double2));
+    a.rec = take(2 * (size_t)cfg->n_particles * a.RW * sizeof(int32_t));
+    a.iter = take((SEM_ITER_HEADER + (size_t)cfg->n_obs * a.C) * sizeof(double));
+    a.bytes = off;
+    return a;
+}
+
+struct XchgPlan { const void *fn; int threads, split_main, kper; size_t smem; };
+
+static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (world < 1 || world > SEM_MAX_RANKS) { set_error("world must be 1..8"); return SEM_ERR_INVALID; }
+    if (cfg->n_filters != 1) { set_error("the sharded filter runs one filter (n_filters = 1)"); return SEM_ERR_INVALID; }
+    if (cfg->resampler != SEM_RESAMPLE_SYSTEMATIC) { set_error("the sharded filter resamples systematically"); return SEM_ERR_INVALID; }
+    if (cfg->n_obs >= (1 << 20) - 1) { set_error("n_obs too large for the path-sampler token"); return SEM_ERR_INVALID; }
+    if ((long long)cfg->n_particles * world > 0x7fffffffLL) { set_error("global particle count exceeds int32"); return SEM_ERR_INVALID; }
+    pl.fn = xchg_kernel(cfg);
+    if (!pl.fn) { set_error("the device-side exchange runs arith fast32 / uniformized32"); return SEM_ERR_INVALID; }
+    const WsLayout w = ws_layout(cfg);
+    pl.threads = persistent_threads(cfg, w, &pl.split_main);
+    const int NB = w.nb * world;
+    pl.kper = (NB + pl.threads - 1) / pl.threads;
+    if (pl.kper > 4) { set_error("too many CTAs for the in-kernel combine (world * nb > 4 * threads)"); return SEM_ERR_INVALID; }
+    pl.smem = persistent_smem(cfg, NB, pl.threads, pl.split_main);
+    int dev = 0, coop = 0, per_sm = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    SEM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    if (!coop) { set_error("device lacks cooperative launch"); return SEM_ERR_INVALID; }
+    rc = persistent_prepare(pl.fn, pl.smem);
+    if (rc) return rc;
+    SEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.fn, pl.threads, pl.smem));
+    if ((long long)per_sm * sm_count() < (long long)w.nb) {
+        set_error("this rank's particles are not co-resident on one GPU: use the host-driven exchange (sem_shard_*)");
+        return SEM_ERR_INVALID;
+    }
+    return SEM_OK;
+}
+
+}  // namespace sem
+
+using namespace sem;
+
+extern "C" {
+
+size_t sem_xchg_bytes(const sem_pf_config *cfg, int32_t world) {
+    if (validate(cfg) || world < 1 || world > SEM_MAX_RANKS) return 0;
+    return arena_layout(cfg, world).bytes;
+}
+
+int sem_xchg_alloc(size_t bytes, void **arena, unsigned char *ipc_handle) {
+    if (!arena || !bytes) { set_error("bad arena request"); return SEM_ERR_INVALID; }
+    SEM_CUDA(cudaMalloc(arena, bytes));
+    if (ipc_handle) {
+        cudaIpcMemHandle_t h;
+        cudaError_t e = cudaIpcGetMemHandle(&h, *arena);
+        if (e != cudaSuccess) { cudaFree(*arena); *arena = nullptr; set_error("cudaIpcGetMemHandle: %s", cudaGetErrorString(e)); return SEM_ERR_CUDA; }
+        static_assert(sizeof(h) == 64, "CUDA IPC handle size");
+        memcpy(ipc_handle, &h, sizeof(h));
+    }
+    return SEM_OK;
+}
+
+int sem_xchg_open(const unsigned char *ipc_handle, void **peer_arena) {
+    if (!ipc_handle || !peer_arena) { set_error("null"); return SEM_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, ipc_handle, sizeof(h));
+    SEM_CUDA(cudaIpcOpenMemHandle(peer_arena, h, cudaIpcMemLazyEnablePeerAccess));
+    return SEM_OK;
+}
+
+int sem_xchg_close(void *peer_arena) {
+    if (peer_arena) SEM_CUDA(cudaIpcCloseMemHandle(peer_arena));
+    return SEM_OK;
+}
+
+int sem_xchg_free(void *arena) {
+    if (arena) SEM_CUDA(cudaFree(arena));
+    return SEM_OK;
+}
+
+int sem_peer_enable(int32_t device, int32_t peer_device) {
+    if (device == peer_device) return SEM_OK;
+    int prev = 0, can = 0;
+    SEM_CUDA(cudaGetDevice(&prev));
+    SEM_CUDA(cudaDeviceCanAccessPeer(&can, device, peer_device));
+    if (!can) { set_error("no peer access between the two devices"); return SEM_ERR_INVALID; }
+    SEM_CUDA(cudaSetDevice(device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { set_error("cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e)); return SEM_ERR_CUDA; }
+    cudaGetLastError();
+    return SEM_OK;
+}
+
+int sem_xchg_reset(const sem_pf_config *cfg, int32_t world, void *arena, void *stream) {
+    if (validate(cfg) || !arena || world < 1 || world > SEM_MAX_RANKS) { set_error("bad arena reset"); return SEM_ERR_INVALID; }
+    const ArenaLayout a = arena_layout(cfg, world);
+    char *base = (char *)arena;
+    cudaStream_t s = (cudaStream_t)stream;
+    SEM_CUDA(cudaMemsetAsync(base, 0, a.part, s));                                  // error flag, mailbox
+    SEM_CUDA(cudaMemsetAsync(base + a.part, 0xFF, a.iter - a.part, s));            // partial tables and records: all-ones = empty
+    SEM_CUDA(cudaMemsetAsync(base + a.iter, 0, a.bytes - a.iter, s));
+    return SEM_OK;
+}
+
+double *sem_xchg_iteration_result(const sem_pf_config *cfg, int32_t world, void *arena) {
+    if (validate(cfg) || !arena || world < 1 || world > SEM_MAX_RANKS) return nullptr;
+    return (double *)((char *)arena + arena_layout(cfg, world).iter);
+}
+
+int sem_pf_sharded_supported(const sem_pf_config *cfg, int32_t world) {
+    XchgPlan pl;
+    return xchg_plan(cfg, world, pl) == SEM_OK ? 1 : 0;
+}
+
+int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_xchg_desc *x, void *stream) {
+    if (!x) { set_error("null exchange descriptor"); return SEM_ERR_INVALID; }
+    XchgPlan pl;
+    int rc = xchg_plan(cfg, x->world, pl);
+    if (rc) return rc;
+    if (x->rank < 0 || x->rank >= x->world) { set_error("bad rank"); return SEM_ERR_INVALID; }
+    for (int r = 0; r < x->world; r++) if (!x->arena[r]) { set_error("arena of a rank is not mapped"); return SEM_ERR_INVALID; }
+    PfDev P; WsLayout w; bool replay;
+    rc = fill_dev(cfg, buf, P, w, replay);
+    if (rc) return rc;
+    if (replay) { set_error("the sharded filter runs in Philox mode"); return SEM_ERR_INVALID; }
+    const ArenaLayout a = arena_layout(cfg, x->world);
+    P.j0 = x->rank * cfg->n_particles;
+    P.split_main = pl.split_main;
+    XchgDev X;
+    memset(&X, 0, sizeof(X));
+    X.W = x->world; X.rank = x->rank; X.NB = a.NB; X.kper = pl.kper;
+    X.Ng = (long long)cfg->n_particles * x->world;
+    X.gen0 = x->generation;
+    X.tag = (x->launch_tag % 4095u) + 1u;
+    int dev = 0, khz = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    SEM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    X.timeout = (long long)((x->timeout_s > 0 ? x->timeout_s : 20.0) * 1e3 * (khz > 0 ? khz : 1965000));
+    for (int r = 0; r < x->world; r++) {
+        char *base = (char *)x->arena[r];
+        X.part[r] = (double2 *)(base + a.part); X.rec[r] = (int32_t *)(base + a.rec);
+        X.mail[r] = (unsigned long long *)(base + a.mail); X.iter[r] = (double *)(base + a.iter);
+    }
+    X.err = (int *)((char *)x->arena[x->rank] + a.err);
+    if (buf->iteration_result) {
+        if (buf->iteration_result != X.iter[x->rank]) { set_error("iteration_result must be sem_xchg_iteration_result(arena)"); return SEM_ERR_INVALID; }
+        P.iter_out = X.iter[x->rank];
+    }
+    void *args[] = {(void *)&P, (void *)&X};
+    SEM_CUDA(cudaLaunchCooperativeKernel(pl.fn, dim3(w.nb, 1), dim3(pl.threads), args, pl.smem, (cudaStream_t)stream));
+    x->generation = (x->generation + (uint32_t)(cfg->n_obs > 1 ? cfg->n_obs - 1 : 0)) % 6u;   // only its value mod 2 and mod 3 matters
+    x->launch_tag = X.tag;
+    return SEM_OK;
+}
+
+}  // extern "C"

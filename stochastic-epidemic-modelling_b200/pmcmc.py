@@ -135,13 +135,26 @@ def particle_path_sampler(hidden_process, ancestry_matrix, *, exact_genealogy=Fa
 
 def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_chains=1000, observations=False,
                   probs=.1, n_particles=1000, n_population=4820, mu=20, jobs=4, *, resampler="systematic", seed=None,
-                  arith="auto", exact_genealogy=False, return_log=False, progress=False, stats=None):
+                  arith="auto", exact_genealogy=False, return_log=False, progress=False, stats=None, sharded=False,
+                  group=None, exchange="auto"):
     """Particle marginal Metropolis-Hastings (pmcmc.py:251-408).
 
     Returns (thetas[n_chains,P], likelihoods[n_chains], sampled_trajs[T,n_chains,C]).  likelihoods are the linear
     zetas[-1] like the reference (log-likelihoods with return_log=True).  `stats`, if a dict, receives
     'filter_runs', 'acceptances', 'launches'.
+
+    sharded=True (every rank of an initialised torch.distributed group calls with the same arguments): ONE chain whose
+    filter of n_particles (global count) is sharded over the ranks with global systematic resampling (BASELINE config 5;
+    globalises pmcmc.py:183-199 and the path sampler of pmcmc.py:236-248).  The MH draws come from a generator seeded
+    once from rank 0, every rank receives the same likelihood and sampled trajectory from the device and takes the same
+    decisions, so there is no host collective per iteration; all ranks return the same arrays.  exchange = "device"
+    (peer-memory exchange inside one launch per rank), "host" (NCCL collectives per step, for shards too large to be
+    co-resident) or "auto".
     """
+    if sharded:
+        return _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chains, observations, probs,
+                                      n_particles, n_population, mu, seed=seed, arith=arith, exact_genealogy=exact_genealogy,
+                                      return_log=return_log, stats=stats, group=group, exchange=exchange)
     dev = engine.require_cuda()
     Y = np.asarray(Y, dtype=np.float64)
     model = _model_id(type_model)
@@ -216,6 +229,104 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
         if bar is not None:
             bar.update(1)
             bar.set_postfix_str(f"theta={thetas[i]}, logZ={loglik[i]:.3f}, acc={100 * counters['acceptances'] / (i + 1):.1f}%")
+    if isinstance(stats, dict):
+        stats.update(counters)
+    return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs
+
+
+def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chains, observations, probs, n_particles,
+                           n_population, mu, *, seed, arith, exact_genealogy, return_log, stats, group, exchange):
+    """particle_mcmc with the filter sharded over the ranks of `group` (see particle_mcmc)."""
+    import torch.distributed as dist
+    from . import sharded as sh
+    if not (dist.is_available() and dist.is_initialized()):
+        raise RuntimeError("particle_mcmc(sharded=True) needs an initialised torch.distributed process group")
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if n_particles % world:
+        raise ValueError("n_particles must be divisible by the number of ranks")
+    Y = np.asarray(Y, dtype=np.float64)
+    model = _model_id(type_model)
+    n_par = len(parameters)
+    T = Y.shape[0]
+    G = len(mu) if model >= 2 else 1
+    Cn = engine.model_dims(model, G)[0]
+    box = [engine.new_seed() if seed is None else int(seed), engine.new_seed()]
+    dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    seed, mh_seed = box
+    rng = np.random.RandomState(mh_seed % 2**32)             # the same MH draws on every rank
+    thetas = np.zeros((n_chains, n_par))
+    loglik = np.zeros(n_chains)
+    sampled_trajs = np.zeros((T, n_chains, Cn))
+    std = np.eye(n_par) if sigma is None else sigma
+    counters = dict(filter_runs=0, acceptances=1, launches=0, exchange=None)
+    th0 = _flatten_theta(model, _split(model, G, np.asarray(parameters, dtype=float), probs)[0])
+    kw = dict(G=G, observations=observations, probs=.5 if probs is None else probs, seed=seed, mu=np.atleast_1d(mu),
+              n_population=np.atleast_1d(n_population))
+    n_local = n_particles // world
+    if exchange == "auto":
+        exchange = "device" if sh.device_exchange_supported(model, n_local, T, world, arith=engine.resolve_arith(model, arith, theta=th0),
+                                                            **kw) else "host"
+    counters["exchange"] = exchange
+    pf = None
+    if exchange == "device":
+        pf = sh.PeerFilter(rank, world, model, Y, n_local, arith=arith, theta=th0, path_exact=exact_genealogy, **kw)
+        sh.connect_distributed(pf, group)
+
+    def run_filter(theta_vec, it):
+        theta2, probs2 = _split(model, G, theta_vec, probs)
+        th = _flatten_theta(model, theta2)
+        counters["filter_runs"] += 1
+        if pf is not None:
+            r = pf.iteration(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th))
+            counters["launches"] += 1
+            if int(r[1]) != 0:                               # same status on every rank: clean the arenas together
+                if int(r[1]) == engine._lib.ERR_PEER:
+                    raise engine._lib.SemError("sharded filter: a peer rank did not answer (SEM_ERR_PEER)")
+                pf.reset()
+                dist.barrier(group=group)
+                return None, None
+            return float(r[0]), r[engine.ITER_HEADER:].reshape(T, Cn).copy()
+        out = sh.run_distributed(Y, model, th, n_particles, group=group, filter_id=it, arith=arith, **dict(kw, probs=probs2))
+        counters["launches"] += out["shard"].launches
+        if out["collapsed"]:
+            return None, None
+        traj = sh.path_sample_distributed(out["shard"], seed, it, exact=exact_genealogy, group=group)
+        return float(out["log_zetas"][-1]), traj
+
+    def finish_theta(theta_vec):
+        if probs is None:
+            out_t = np.array(theta_vec, dtype=float)
+            out_t[-1] = max(min(out_t[-1], 1), 0)
+            return out_t
+        return theta_vec
+
+    try:
+        it = 0
+        while True:                                                               # pmcmc.py:276-310
+            theta_proposal = rng.multivariate_normal(np.array(parameters), h * std)
+            if np.sum(theta_proposal < 0) > 0:
+                continue
+            lz, traj = run_filter(theta_proposal, it)
+            it += 1
+            if lz is not None:
+                break
+        thetas[0] = finish_theta(theta_proposal); loglik[0] = lz; sampled_trajs[:, 0, :] = traj
+        for i in range(1, n_chains):                                              # pmcmc.py:325-403
+            if adaptive and i > 1e3:
+                std = np.cov(thetas[:i].T, ddof=0) + 1e-4 * np.eye(n_par)
+            theta_proposal = rng.multivariate_normal(thetas[i - 1], h * std)
+            lz = None
+            if not np.sum(theta_proposal < 0) > 0:
+                lz, traj = run_filter(theta_proposal, it)
+                it += 1
+            if lz is not None and np.log(rng.uniform()) < lz - loglik[i - 1]:
+                counters["acceptances"] += 1
+                thetas[i] = finish_theta(theta_proposal); loglik[i] = lz; sampled_trajs[:, i, :] = traj
+            else:
+                thetas[i] = thetas[i - 1]; loglik[i] = loglik[i - 1]; sampled_trajs[:, i, :] = sampled_trajs[:, i - 1, :]
+    finally:
+        if pf is not None:
+            pf.close()
     if isinstance(stats, dict):
         stats.update(counters)
     return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs

@@ -468,6 +468,97 @@ def test_sharded_filter_equals_single_gpu(sem, c_oracle, world, model, G, theta,
     assert np.array_equal(one.ancestry[0].cpu().numpy(), A)
 
 
+PEER_CASES = [
+    # world, model, G, theta, npop, mu, arith, n_local, block
+    (1, 0, 1, [.4, .2], [1000], [20], 4, 3000, 256),              # one rank: the exchange degenerates to push-resampling on one GPU
+    (2, 0, 1, [.4, .2], [1000], [20], 4, 2048, 256),              # uniformized32, sorted layout (8 chunks per CTA)
+    (3, 0, 1, [.4, .2], [1000], [20], 4, 1500, 300),              # ragged CTAs, sorted layout with helper legs (4W+2 chunks)
+    (4, 0, 1, [2.0, 1.0], [1000], [20], 3, 1100, 160),            # direct method, balanced layout (128 + 32)
+    (2, 1, 1, [.4, .3, .2], [1000], [20], 4, 2000, 256),          # SEIR (5-word records -> 8-word slots)
+    (2, 3, 2, [5, 2, 1, 3, .5], [415, 620], [15, 20], 3, 1024, 128),   # 2 subgroups, group-summed observations (config 5 shape)
+    (8, 0, 1, [.4, .2], [1000], [20], 4, 512, 128),               # 8 ranks, 4 CTAs each
+]
+
+
+@pytest.mark.parametrize("world,model,G,theta,npop,mu,arith,n_local,block", PEER_CASES)
+def test_peer_exchange_equals_single_gpu_and_oracle(sem, c_oracle, world, model, G, theta, npop, mu, arith, n_local, block):
+    """Device-side exchange (sem_pf_run_sharded: partials and child records through peer memory, one cooperative launch
+    per rank, the ranks' kernels running concurrently on this GPU): states, GLOBAL ancestor indices, log-likelihoods and
+    event counts equal the single-GPU filter of W n particles and the C oracle; the path sample over the shards equals
+    the single-GPU iteration result; two passes back to back (generations keep counting, no reset in between)."""
+    import torch
+    from sem_b200 import sharded
+    N, T = world * n_local, (10 if model == 0 else 7)
+    Y = _truth_Y(model, T, 5, .1, False, G=G)
+    th = np.array(theta, float)
+    outs = sharded.run_peer_local(Y, model, th, N, world, G=G, probs=.1, seed=4242, filter_id=5, mu=mu, n_population=npop,
+                                  arith=arith, block_particles=block, want_path=True, passes=2, timeout_s=10.0)
+    for k, out in enumerate(outs):
+        assert out["status"] == [0] * world, out["status"]
+        cfg = sem.engine.make_pf_config(model, N, T, G=G, probs=.1, resampler=1, arith=arith, seed=4242, filter_id0=5 + k, mu=mu,
+                                        n_population=npop, block_particles=block)
+        it = torch.empty((1, sem.engine.ITER_HEADER + T * cfg_cols(model, G)), dtype=torch.float64, device="cuda")
+        one = sem.engine.run_pf(cfg, Y, th, iter_out=it)
+        torch.cuda.synchronize()
+        assert np.array_equal(one.ancestry[0].cpu().numpy(), out["ancestry"])
+        assert np.array_equal(one.X_hist[0].cpu().numpy(), out["X_hist"])
+        for r in range(world):                                   # every rank holds the same likelihood, bit for bit
+            assert np.array_equal(out["log_zetas"][r], out["log_zetas"][0])
+        np.testing.assert_allclose(out["log_zetas"][0], one.log_zetas[0].cpu().numpy(), rtol=1e-12)
+        assert out["n_events"] == int(one.n_events[0])
+        ito = it[0].cpu().numpy()
+        for r in range(world):                                   # same chosen particle and trajectory on every rank
+            got = out["iteration"][r]
+            assert got[1] == 0 and got[3] == ito[3]
+            assert np.array_equal(got[sem.engine.ITER_HEADER:], ito[sem.engine.ITER_HEADER:])
+            np.testing.assert_allclose(got[0], ito[0], rtol=1e-12)
+        if k == 0:
+            ref = c_oracle.pf_run(model, Y, theta, False, .1, N, G=G, resampler=1, arith=arith, seed=4242, filter_id=5, mu=mu, npop=npop)
+            assert np.array_equal(out["ancestry"], ref["ancestry"])
+            assert np.array_equal(np.transpose(out["X_hist"], (0, 2, 1)), ref["X_hist"])
+            np.testing.assert_allclose(out["log_zetas"][0], ref["log_zetas"], rtol=1e-11)
+
+
+def cfg_cols(model, G):
+    return 3 if model == 0 else 4 if model == 1 else 3 * G
+
+
+def test_peer_exchange_collapse_and_reset(sem):
+    """A collapsing sharded filter ends on every rank with the same status (no hang), and after reset() the arenas serve
+    the next pass."""
+    from sem_b200 import sharded
+    T = 8
+    Y = _truth_Y(0, T, 5, .1, False)
+    outs = sharded.run_peer_local(Y, 0, np.array([0.01, 50.0]), 2 * 1024, 2, probs=.1, seed=3, mu=[20], n_population=[1000],
+                                  arith=3, block_particles=256, timeout_s=10.0)
+    st = outs[0]["status"]
+    assert st[0] == st[1] and st[0] > 0, st
+    outs = sharded.run_peer_local(Y, 0, np.array([2.0, 1.0]), 2 * 1024, 2, probs=.1, seed=3, mu=[20], n_population=[1000],
+                                  arith=3, block_particles=256, timeout_s=10.0)
+    assert outs[0]["status"] == [0, 0]
+
+
+def test_peer_exchange_degenerate_weights(sem, c_oracle):
+    """Weight degeneracy: a handful of particles own thousands of children each (the warp-cooperative record store) --
+    normal observations with a tiny noise ratio make almost every weight vanish."""
+    import torch
+    from sem_b200 import sharded
+    T, world, n_local = 6, 2, 2048
+    Y = _truth_Y(0, T, 5, .02, True)
+    th = np.array([2.0, 1.0])
+    out = sharded.run_peer_local(Y, 0, th, world * n_local, world, observations=True, probs=.02, seed=12, mu=[20],
+                                 n_population=[1000], arith=3, block_particles=256, timeout_s=10.0)[0]
+    cfg = sem.engine.make_pf_config(0, world * n_local, T, observations=True, probs=.02, resampler=1, arith=3, seed=12, mu=[20],
+                                    n_population=[1000], block_particles=256)
+    one = sem.engine.run_pf(cfg, Y, th)
+    torch.cuda.synchronize()
+    assert out["status"] == [int(one.status[0])] * world
+    if out["status"][0] == 0:
+        anc = one.ancestry[0].cpu().numpy()
+        assert np.array_equal(anc, out["ancestry"]) and np.array_equal(one.X_hist[0].cpu().numpy(), out["X_hist"])
+        assert max(np.bincount(anc[p]).max() for p in range(1, T)) > 64      # the case really is degenerate
+
+
 def test_predict_forward_daily_states(sem, c_oracle):
     """Forward-prediction fan-out (tests/pred_tmps.py:55-73): daily states of many simulations == the oracle's event
     logs sampled at the integer times."""
