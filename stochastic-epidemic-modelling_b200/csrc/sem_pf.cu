@@ -418,7 +418,7 @@ int sem_shard_propagate(const sem_pf_config *cfg, const sem_pf_buffers *buf, con
 
 #ifdef SEM_PHASES
 int sem_debug_phases(unsigned long long *host_out) {
-    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 16 * 256));
+    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 24 * 256));
     return SEM_OK;
 }
 int sem_debug_warps(unsigned long long *end_out, unsigned int *work_out) {

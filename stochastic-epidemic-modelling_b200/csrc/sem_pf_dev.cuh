@@ -111,8 +111,8 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
 }
 
 #ifdef SEM_PHASES
-static __device__ unsigned long long g_phase[16 * 256];
-#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 16 + (k)] = (unsigned long long)clock64(); } } while (0)
+static __device__ unsigned long long g_phase[24 * 256];
+#define PHASE(k) do { if (tid == 0 && b == 0 && p < 256) { g_phase[p * 24 + (k)] = (unsigned long long)clock64(); } } while (0)
 static __device__ unsigned long long g_warp_end[256 * 32];          // CTA 0: when each warp left the SSA loop, and its work
 static __device__ unsigned int g_warp_work[256 * 32];
 #define WARP_END(work) do { const unsigned int wk_ = __reduce_max_sync(0xffffffffu, (unsigned int)(work)); \
@@ -303,6 +303,16 @@ __device__ __forceinline__ long long first_slot_ge(const SlotMap &sm, double c) 
     return j;
 }
 
+// J(c) without divisions in the common case: the real-valued slot position x = c N / total - u0 is evaluated with a
+// Newton reciprocal; unless x lies within 1e-5 of an integer (error of x: a few ulp of N <= 2^31, i.e. < 1e-6) its
+// ceiling IS the exact answer of first_slot_ge, which is only called for the rare near-ties.  n_over_total = N * rcp(total).
+__device__ __forceinline__ long long first_slot_ge_quick(const SlotMap &sm, const double c, const double n_over_total) {
+    if (c >= sm.total) return sm.N;
+    const double xr = __fma_rn(c, n_over_total, -sm.u0), up = ceil(xr);
+    if (fabs(xr - rint(xr)) < 1e-5) return first_slot_ge(sm, c);
+    return up <= 0.0 ? 0 : (long long)up;
+}
+
 // ---------------------------------------------------------------------------------------------- peer-memory exchange
 // One filter sharded over the W GPUs of a node, every rank running pf_persistent_x (sem_pf_xchg.cu).  Rank r owns the
 // particles [r N, (r+1) N) and the global CTAs [r nb, (r+1) nb); resampling is global and systematic.  Two exchanges per
@@ -350,20 +360,27 @@ template <int C> struct RecWords { static constexpr int value = (C + 1 + 3) & ~3
 
 __device__ __forceinline__ void xchg_fail(const XchgDev &X) { *(volatile int *)X.err = 1; }
 
-// Publish this CTA's partial of generation `gen` to every rank (threads 0..W-1, one destination each).  The fence orders
-// this CTA's earlier resets (made visible to these threads by the CTA barriers in between) before the publication.
+// Publish this CTA's partial of generation `gen` to every rank: the first W lanes of the CTA's LAST warp, one destination
+// each.  The same lanes ran xchg_early_fence after this step's resets (records and partial table; made visible to them
+// by a CTA barrier): fence.sys ... store by one thread is the release that orders the resets before the publication.
+// The fence costs ~3 us on B200, so it is issued right after the resets -- the last warp is a second-leg helper that
+// waits for its hand-over (balanced / helper layouts) or carries the CTA's lightest chunk (sorted layout) -- and not
+// between the weights and the publication, where every CTA of every rank would wait for it.
+__device__ __forceinline__ bool xchg_is_publisher(const XchgDev &X, const int tid) {
+    return (tid >> 5) == (((int)blockDim.x - 1) >> 5) && (tid & 31) < X.W;
+}
+__device__ __forceinline__ void xchg_early_fence(const XchgDev &X, const int tid) {
+    if (xchg_is_publisher(X, tid)) __threadfence_system();
+}
 __device__ __forceinline__ void xchg_publish(const XchgDev &X, const unsigned gen, const int gb, const int tid, const double mb, const double sb) {
-    if (tid < X.W) {
-        __threadfence_system();
-        st_vol(X.part[tid] + (size_t)(gen % 3u) * X.NB + gb, mb, sb);
-    }
+    if (xchg_is_publisher(X, tid)) st_vol(X.part[tid & 31] + (size_t)(gen % 3u) * X.NB + gb, mb, sb);
 }
 
 // Wait for all NB partials of generation `gen` (the resampling barrier) and combine them: global max M, per-CTA
 // (exclusive prefix, scale) into shared memory, total.  Thread t combines the kper consecutive entries [t kper, ...).
 // Also resets this CTA's share of the table of generation gen + 2.  Called by every thread of the CTA.
 __device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsigned gen, const int b, const int nb, const int tid, double *sm,
-                                                  double *s_pfx, double *s_scale, double &M_out, double &total_out) {
+                                                  double *s_pfx, double *s_scale, double &M_out, double &total_out, const int p) {
     constexpr int KMAX = 4;
     const int nwarps = (blockDim.x + 31) >> 5, NB = X.NB, base = tid * X.kper;
     const double2 *tab = X.part[X.rank] + (size_t)(gen % 3u) * NB;
@@ -382,10 +399,12 @@ __device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsign
             }
         }
     }
+    PHASE(16);
     double mx = m[0];
 #pragma unroll
     for (int k = 1; k < KMAX; k++) mx = fmax(mx, m[k]);
     const double M = block_max(mx, sm, tid, nwarps);
+    PHASE(17);
     // every thread of this CTA has left its poll: all CTAs of all ranks have published generation gen, hence finished reading
     // generation gen - 1, whose table is the one generation gen + 2 will use
     if (tid < X.W) st_vol(X.part[X.rank] + (size_t)((gen + 2u) % 3u) * NB + tid * nb + b, __longlong_as_double(-1ll), __longlong_as_double(-1ll));
@@ -420,14 +439,15 @@ __device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X,
     smap.u0 = systematic_u0(P, p_next, fid); smap.Nd = (double)X.Ng; smap.total = total; smap.N = X.Ng;
     const double pf = s_pfx[gb], sc = s_scale[gb];
     const double cta_hi = (gb == X.NB - 1) ? total : s_pfx[gb + 1];
+    const double n_over_total = __dmul_rn(smap.Nd, rcp_nr(total));
     long long hi = 0;
     if (active) {
         const double up = (pidx == len - 1) ? cta_hi : fmin(__fma_rn(sc, incl, pf), cta_hi);
-        hi = first_slot_ge(smap, up);
+        hi = first_slot_ge_quick(smap, up, n_over_total);
         s_J[pidx] = (int)hi;
     }
     __shared__ int s_J0;
-    if (tid == 0) s_J0 = (int)first_slot_ge(smap, pf);
+    if (tid == (int)blockDim.x - 1) s_J0 = (int)first_slot_ge_quick(smap, pf, n_over_total);
     __syncthreads();
     long long lo = 0;
     if (active) lo = pidx == 0 ? s_J0 : s_J[pidx - 1];
@@ -645,7 +665,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         const int par = p & 1;
         const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
         double M, total;
-        if constexpr (PUSH) xchg_wait_combine(*Xp, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, M, total);
+        if constexpr (PUSH) xchg_wait_combine(*Xp, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, M, total, p);
         else combine_partials(P, f, par ^ 1, tid, sm, s_pfx, s_scale, M, total);
         const bool ok = (M > -CUDART_INF && M < CUDART_INF) && (total > 0.0);
         if (!ok) {
@@ -673,6 +693,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         PHASE(2);
         if constexpr (PUSH)                                  // resample, offspring form: one record per child, to the slot's owner
             xchg_offspring<Model>(P, *Xp, Xp->gen0 + (unsigned)(p - 1), p, fid, b, gb, tid, pidx, active, j, x, ls.incl, total, s_pfx, s_scale, s_J);
+        PHASE(18);
         long long pairs = 0;
         int32_t *Xr = Xf + (size_t)row * Model::C * N;
         Model m;
@@ -693,6 +714,12 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
             m.setup(P.theta + (size_t)f * P.ntheta, x);
             src.init(P.key, (uint32_t)(P.j0 + j), (uint32_t)p, stream_word(DOM_SSA, fid));
             PHASE(7);
+        }
+        if constexpr (PUSH) {                                // all resets of this step are done: fence them, off the critical path
+            if (!(kUnif && P.split_main < 0)) {              // (the sorted layout fences after the last barrier of its sort)
+                __syncthreads();
+                xchg_early_fence(*Xp, tid);
+            }
         }
         if constexpr (kUnif) {
             // The uniformized loop knows its amount of work BEFORE it runs: the candidate count K of the (first) batch is
@@ -752,6 +779,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
                 }
                 __syncthreads();
                 PHASE(15);
+                if constexpr (PUSH) xchg_early_fence(*Xp, tid);   // after the LAST CTA-wide barrier before the loop (nobody waits for it)
                 // Sorted chunk -> warp.  The main warps take the chunks in snake order over the schedulers.  When the
                 // chunks are 4 W + 1 or 4 W + 2 (P.split_main == -2) the last one or two are shared in TIME by two helper
                 // warps each, on different schedulers: warp 4W + g serves the first half of the batch's candidates
@@ -877,6 +905,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         }
         if (p < P.T - 1) {
             ls = weigh_local<Model, PUSH>(P, p, f, b, tid, active, j, x, sm, s_tab);
+            PHASE(19);
             if constexpr (PUSH) xchg_publish(*Xp, Xp->gen0 + (unsigned)p, gb, tid, ls.mb, ls.sb);
         }
         PHASE(5);

@@ -210,4 +210,11 @@ int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_
     return SEM_OK;
 }
 
+#ifdef SEM_PHASES
+int sem_debug_phases_x(unsigned long long *host_out) {
+    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 24 * 256));
+    return SEM_OK;
+}
+#endif
+
 }  // extern "C"

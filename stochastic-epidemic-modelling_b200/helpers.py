@@ -66,13 +66,16 @@ def effective_sample_size(x):
         return float(n)
     f = np.fft.rfft(xc, 2 * n)
     acf = np.fft.irfft(f * np.conj(f))[:n] / (var * n)
+    # Geyer's initial positive sequence: Gamma_m = rho_{2m} + rho_{2m+1}, m = 0, 1, ... summed while positive;
+    # integrated autocorrelation time tau = -1 + 2 sum Gamma_m  (rho_0 = 1)
     s = 0.0
-    for k in range(1, n - 1, 2):
+    for k in range(0, n - 1, 2):
         pair = acf[k] + acf[k + 1]
         if pair < 0:
             break
         s += pair
-    return float(n / (1 + 2 * s))
+    tau = max(2 * s - 1, 1e-12)
+    return float(min(n / tau, n))
 
 
 def acceptance_rate(thetas):

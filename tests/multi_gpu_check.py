@@ -44,6 +44,31 @@ def main():
         ref = co.pf_run(0, Y, [2.0, 1.0], False, .1, N, resampler=1, arith=cfg.arith, seed=777, filter_id=2, mu=[20], npop=[pop])
         assert np.array_equal(one.ancestry[0].cpu().numpy(), ref["ancestry"])
         print(f"sharded filter over {world} GPUs == single GPU == oracle: OK  logZ={out['log_zetas'][-1]:.6f}")
+    # the same filter with the exchange on the device (peer memory, one cooperative launch per rank and pass)
+    n_local, blk = 20_000, 160
+    for model, th, kw in [(0, np.array([.4, .2]), dict(mu=[20], n_population=[pop])),
+                          (0, np.array([2.0, 1.0]), dict(mu=[20], n_population=[pop]))]:
+        pf = None
+        for k in range(2):                                          # two passes through the same arenas (no reset in between)
+            o = sharded.run_peer_distributed(Y, model, th, n_local * world, probs=.1, seed=777, filter_id=2 + k, want_path=True, pf=pf,
+                                             block_particles=blk, **kw)
+            pf = o["shard"]
+            assert o["collapsed"] == 0, o["collapsed"]
+            cfg = sem_b200.engine.make_pf_config(model, n_local * world, T, probs=.1, resampler=1, arith=pf.cfg.arith, seed=777,
+                                                 filter_id0=2 + k, block_particles=blk, **kw)
+            it = torch.empty((1, sem_b200.engine.ITER_HEADER + T * 3), dtype=torch.float64, device="cuda")
+            one = sem_b200.engine.run_pf(cfg, Y, th, iter_out=it)
+            torch.cuda.synchronize()
+            lo = rank * n_local
+            assert torch.equal(one.X_hist[0][:, :, lo:lo + n_local], pf.X_hist), "device exchange: states differ from the single-GPU filter"
+            assert torch.equal(one.ancestry[0][:, lo:lo + n_local], pf.ancestry), "device exchange: ancestors differ"
+            np.testing.assert_allclose(o["log_zetas"], one.log_zetas[0].cpu().numpy(), rtol=1e-12)
+            ito = it[0].cpu().numpy()
+            assert o["iteration"][3] == ito[3] and np.array_equal(o["iteration"][4:], ito[4:]), "path sample over the shards differs"
+        dist.barrier()
+        pf.close()
+        if rank == 0:
+            print(f"device-side exchange over {world} GPUs (theta {th.tolist()}, arith {pf.cfg.arith}) == single GPU, incl. path sample: OK")
     # ABC across ranks
     obs = workloads.observe_normal(workloads.sir_truth((480, 20, 0), 10, 2.0, 1.0), .1, seed=7)
     st = {}

@@ -648,6 +648,141 @@ def test_pmcmc_posterior_vs_reference(sem):
     assert abs(acc_ref - acc_ours) < 0.12, (acc_ref, acc_ours)
 
 
+# ---- the DEFAULT path (arith="auto" -> uniformized32, systematic resampling) in the regime where auto selects it
+def test_logz_distribution_vs_reference_slow_growth(sem):
+    """Slow-growth regime (beta=.4, gamma=.2: growth 0.2 per interval, where engine.resolve_arith picks uniformized32):
+    320 runs of the unmodified reference particle_filter (tests/golden/make_golden_stats_slow.py) vs the CUDA filter with
+    the shipped defaults.  Both estimators are unbiased for the same likelihood: means within 4 se; with the reference's
+    multinomial resampling the whole law of log Z agrees (KS); the direct method agrees too."""
+    import torch
+    from scipy import stats
+    g = golden("stat_logz_sir_slow")
+    N, npop, mu = int(g["n_particles"]), int(g["n_population"]), float(g["mu"])
+    ref = g["zetas_last"]
+    assert sem.engine.resolve_arith(0, "auto", theta=g["theta"]) == sem.engine.ARITH["uniformized32"]
+    runs = 4000
+    for resampler, arith in [(1, "auto"), (0, "auto"), (1, 3), (0, 3), (0, 0)]:
+        a = sem.engine.resolve_arith(0, arith, theta=g["theta"])
+        cfg = sem.engine.make_pf_config(0, N, len(g["Y"]), n_filters=runs, probs=float(g["probs"]), resampler=resampler,
+                                        arith=a, seed=911 + 7 * resampler + a, mu=[mu], n_population=[npop])
+        res = sem.engine.run_pf(cfg, g["Y"], np.tile(g["theta"], (runs, 1)))
+        torch.cuda.synchronize()
+        assert int((res.status != 0).sum()) == 0
+        z = np.exp(res.log_zetas[:, -1].cpu().numpy())
+        se = np.sqrt(ref.var() / ref.size + z.var() / z.size)
+        assert abs(z.mean() - ref.mean()) < 4 * se, (resampler, arith, z.mean(), ref.mean(), se)
+        if resampler == 0:
+            assert stats.ks_2samp(np.log(z), np.log(ref)).pvalue > 1e-3, (arith, stats.ks_2samp(np.log(z), np.log(ref)))
+        else:
+            assert np.log(z).std() <= np.log(ref).std() * 1.1
+
+
+def test_pmcmc_posterior_vs_reference_slow_growth(sem):
+    """Posterior of (beta, gamma) from the drop-in particle_mcmc WITH ITS DEFAULTS (arith='auto' -> uniformized32,
+    systematic resampling) vs four chains of the unmodified reference particle_mcmc on the same data and settings:
+    posterior means and both endpoints of the 95 % HDI agree within Monte-Carlo error (spread between chains)."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "stat_pmcmc_sir_slow.npz")):
+        pytest.skip("reference PMCMC chains (slow growth) not generated")
+    g = golden("stat_pmcmc_sir_slow")
+    burn = 400
+    ref = g["thetas"][:, burn:]                                              # (chains, iterations, 2)
+    ours = []
+    for c in range(4):
+        np.random.seed(100 + c)
+        th, lik, _ = sem.particle_mcmc(g["Y"], sem.ModelType.SIR, list(g["parameters"]), float(g["h"]), n_chains=6000,
+                                       probs=float(g["probs"]), n_particles=int(g["n_particles"]),
+                                       n_population=int(g["n_population"]), mu=float(g["mu"]), seed=500 + c)
+        ours.append(th[burn:])
+    ours = np.stack(ours)
+    hdi = sem.helpers.hdi
+    for k in range(2):
+        stat_ref = np.array([[c[:, k].mean(), *hdi(c[:, k], .95)] for c in ref])       # per chain: mean, HDI low, HDI high
+        stat_our = np.array([[c[:, k].mean(), *hdi(c[:, k], .95)] for c in ours])
+        for q, name in enumerate(("mean", "hdi_lo", "hdi_hi")):
+            se = np.sqrt(stat_ref[:, q].var(ddof=1) / len(stat_ref) + stat_our[:, q].var(ddof=1) / len(stat_our))
+            diff = abs(stat_ref[:, q].mean() - stat_our[:, q].mean())
+            assert diff < 4.5 * se + 0.004, (k, name, stat_ref[:, q], stat_our[:, q], se)
+    r_hat = sem.helpers.gelman_rubin_test([c for c in ours])
+    assert np.all(np.asarray(r_hat) < 1.1), r_hat
+    acc_ref = np.mean([sem.helpers.acceptance_rate(c) for c in g["thetas"]])
+    acc_our = np.mean([sem.helpers.acceptance_rate(c) for c in ours])
+    assert acc_our > acc_ref - 0.05, (acc_ref, acc_our)        # systematic resampling: no noisier a likelihood, no fewer acceptances
+
+
+@pytest.mark.parametrize("x0", [(8000, 500, 1500), (9990, 3, 7), (3000, 1500, 5500)])
+def test_uniformized_end_state_law_vs_direct_method(sem, x0):
+    """Law of the state at the END of one observation interval, headline theta / population 1e4: 1.2e6 propagations of
+    one fixed state with the uniformized interval simulation (arith 4, the filters' default) vs the direct method in
+    the reference's operation order (arith 0) -- two-sample chi-square on the joint histogram of (infections,
+    recoveries); includes a start with I = 3, where extinction inside the interval matters."""
+    import torch
+    from scipy import stats
+    n = 1_200_000
+    out = {}
+    for arith in (0, 4):
+        r = sem.engine.simulate(0, np.array(x0), np.array([.4, .2]), 1.0, arith=arith, seed=99 + arith, n_sims=n)
+        torch.cuda.synchronize()
+        x = r["x"].cpu().numpy().astype(np.int64)
+        assert np.all(x.sum(1) == sum(x0)) and np.all(x >= 0)
+        out[arith] = np.stack([x0[0] - x[:, 0], x[:, 2] - x0[2]], 1)          # (infections, recoveries) in the interval
+    both = np.concatenate([out[0], out[4]])
+    w = [max(1, int(np.ceil(both[:, k].std() / 3))) for k in range(2)]         # ~ 1/3 sd wide cells
+    key = lambda d: (d[:, 0] // w[0]) * 100_000 + d[:, 1] // w[1]
+    cells, inv = np.unique(np.concatenate([key(out[0]), key(out[4])]), return_inverse=True)
+    a = np.bincount(inv[:n], minlength=len(cells)).astype(float)
+    b = np.bincount(inv[n:], minlength=len(cells)).astype(float)
+    big = (a + b) >= 40
+    a2 = np.append(a[big], a[~big].sum()); b2 = np.append(b[big], b[~big].sum())   # the sparse cells pooled into one
+    keep = (a2 + b2) > 0
+    chi2 = float((((a2 - b2) ** 2) / (a2 + b2))[keep].sum())
+    dof = int(keep.sum()) - 1
+    pval = stats.chi2.sf(chi2, dof)
+    assert dof >= 20 and pval > 1e-4, (x0, chi2, dof, pval)
+    for k in range(2):                                                         # and the marginal means, z-test
+        se = np.sqrt(out[0][:, k].var() / n + out[4][:, k].var() / n)
+        assert abs(out[0][:, k].mean() - out[4][:, k].mean()) < 4.5 * se + 1e-9, (x0, k)
+
+
+NAMED_SIZE_CASES = [
+    # name, model, G, theta, npop, mu, observations, probs, N, T, arith
+    ("headline_sir_1e5x101_uniformized32", 0, 1, [.4, .2], [10_000], [20], False, .1, 100_000, 101, 4),
+    ("config3_seir_pop1e4_T101", 1, 1, [.4, .1, .1], [10_000], [20], False, .1, 20_000, 101, 4),
+    ("config4i_sir_normal_pop1e4_T101", 0, 1, [.4, .2], [10_000], [20], True, .1, 20_000, 101, 4),
+    ("config5_shape_sub2_pop1e5_T15", 3, 2, [5, 2, 1, 3, .5], [40_000, 60_000], [600, 800], False, .1, 20_000, 15, 3),
+]
+
+
+@pytest.mark.parametrize("name,model,G,theta,npop,mu,observations,probs,N,T,arith", NAMED_SIZE_CASES, ids=[c[0] for c in NAMED_SIZE_CASES])
+def test_named_sizes_match_oracle_exactly(sem, c_oracle, name, model, G, theta, npop, mu, observations, probs, N, T, arith):
+    """BASELINE's named configurations at (or near) their named sizes, default arithmetic of each model family, whole-filter
+    kernel in its production layout (N = 1e5: sorted, 4W+2 chunks with helper legs): states, ancestors and event counts
+    equal the OpenMP oracle's bit for bit, log-likelihoods to 1e-11."""
+    import torch
+    import workloads
+    if model == 0:
+        truth = workloads.sir_truth((npop[0] - mu[0], mu[0], 0), T, *theta)
+    elif model == 1:
+        truth = workloads.seir_truth((npop[0] - mu[0], 0, mu[0], 0), T, *theta)
+    else:
+        y0 = [(npop[g] - mu[g], mu[g], 0) for g in range(G)]
+        truth = workloads.subgroups_truth(y0, T, np.array(theta[:G * G]).reshape(G, G), theta[-1]).reshape(T, G, 3).sum(1)
+    Y = workloads.observe_normal(truth, probs, seed=3) if observations else workloads.observe_binomial(truth, probs, seed=3)
+    assert sem.engine.resolve_arith(model, "auto", theta=theta) == arith          # the default of this model family and regime
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, observations=observations, probs=probs, resampler=1, arith=arith, seed=606,
+                                    mu=mu, n_population=npop)
+    r = sem.engine.run_pf(cfg, Y, np.array(theta, float))
+    o = c_oracle.pf_run(model, Y, theta, observations, probs, N, G=G, resampler=1, arith=arith, seed=606, mu=mu, npop=npop)
+    torch.cuda.synchronize()
+    assert int(r.status.cpu()[0]) == 0 == o["collapsed"]
+    assert r.launches == 1                                                        # the whole-filter kernel
+    assert np.array_equal(r.ancestry[0].cpu().numpy(), o["ancestry"])
+    assert np.array_equal(r.X_hist[0].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+    np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
+    assert int(r.n_events[0]) == o["n_events"]
+
+
 # ------------------------------------------------------------------ robustness / edge cases
 def test_many_ctas_global_prefix_path(sem, c_oracle):
     """More CTAs than fit the shared-memory prefix stage (nb > 4096) and than one finalize chunk: same answers."""

@@ -6,7 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 pkg = os.path.join(ROOT, "stochastic-epidemic-modelling_b200")
 dbg = os.environ.get("SEM_PHASES_LIB") or os.path.join(ROOT, "tools", "micro", "libsem_b200_phases.so")      # git-ignored, travels with the snapshot
-src = [os.path.join(pkg, "csrc", f) for f in ("sem_pf.cu", "sem_sim_abc.cu")]
+src = [os.path.join(pkg, "csrc", f) for f in ("sem_pf.cu", "sem_pf_xchg.cu", "sem_sim_abc.cu")]
 if "--build" in sys.argv or not os.path.exists(dbg):                       # (build it in the container: python tools/phase_probe.py --build)
     subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "--fmad=false", "-DSEM_PHASES",
                            "-DSEM_ONLY_SIR", "-Xcompiler", "-fPIC", "-shared", "-ccbin", "/usr/bin/g++", "-o", dbg] + src)
@@ -25,9 +25,9 @@ out = engine.alloc_pf_outputs(cfg)
 for _ in range(3):
     engine.run_pf(cfg, Y, np.array([.4, .2]), out=out)
 torch.cuda.synchronize()
-buf = np.zeros(16 * 256, dtype=np.uint64)
+buf = np.zeros(24 * 256, dtype=np.uint64)
 assert L.sem_debug_phases(buf.ctypes.data_as(C.c_void_p)) == 0
-ph = buf.reshape(256, 16)[1:100].astype(np.int64)
+ph = buf.reshape(256, 24)[1:100].astype(np.int64)
 # slots: 0 before grid.sync, 1 after, 2 after combine, 6 after ancestor search, 7 after gather+setup, 3 after SSA+store (own warp),
 # 4 after the CTA barrier, 8 after the thread's log-weight, 9 after the CTA max, 10 after exp + CTA scan, 5 after the stores.  SM cycle counter of CTA 0's SM (1.965 GHz).
 order = [0, 1, 2, 6, 7, 12, 13, 14, 15, 11, 3, 4, 8, 9, 10, 5]
@@ -47,7 +47,7 @@ for p in (1, 10, 28, 60, 95):
 we = np.zeros(256 * 32, dtype=np.uint64); ww = np.zeros(256 * 32, dtype=np.uint32)
 if hasattr(L, "sem_debug_warps") and L.sem_debug_warps(we.ctypes.data_as(C.c_void_p), ww.ctypes.data_as(C.c_void_p)) == 0:
     we = we.reshape(256, 32).astype(np.int64); ww = ww.reshape(256, 32)
-    buf2 = buf.reshape(256, 16).astype(np.int64)
+    buf2 = buf.reshape(256, 24).astype(np.int64)
     for p in (11, 29, 45, 61):
         t0 = buf2[p, 11]
         nw = int((we[p] > 0).sum())
@@ -55,3 +55,26 @@ if hasattr(L, "sem_debug_warps") and L.sem_debug_warps(we.ctypes.data_as(C.c_voi
         print(f"  step {p}: SSA phase of warp w (us after the exchange) / its largest K;  CTA barrier released at {(buf2[p, 4] - t0) / 1965.0:.2f}")
         for s4 in range(4):
             print("     sched", s4, " ".join(f"{rel[w]:7.2f}/{ww[p, w]:<5d}" for w in range(s4, nw, 4)))
+
+
+# ---- the sharded filter's kernel with one rank (push-form resampling through the record buffers)
+from sem_b200 import sharded
+pf = sharded.PeerFilter(0, 1, 0, Y, N, theta=np.array([.4, .2]), probs=.1, seed=1, mu=[20], n_population=[10000], want_handle=False)
+for i in range(3):
+    pf.run(np.array([.4, .2]), filter_id=i)
+torch.cuda.synchronize()
+assert pf.status == 0
+L.sem_debug_phases_x.argtypes = [C.c_void_p]
+assert L.sem_debug_phases_x(buf.ctypes.data_as(C.c_void_p)) == 0
+ph = buf.reshape(256, 24)[1:100].astype(np.int64)
+order = [0, 16, 17, 2, 18, 6, 7, 12, 13, 14, 15, 11, 3, 4, 8, 9, 10, 19, 5]
+names = ["wait for the partials", "CTA max", "scan + s_pfx + barrier", "offspring (J, records)", "take record", "setup", "batch setup (K draw)", "sort: range",
+         "sort: bins", "sort: scan + write", "sort: read", "SSA+store (warp 0)", "wait CTA", "weights (warp 0)", "CTA max", "exp + CTA scan", "(keep)", "fence + publish"]
+t = ph[:, order] / 1965.0
+d = np.diff(t, axis=1)
+print("pf_persistent_x, one rank; per-step mean us (CTA 0, thread 0):")
+for k, nm in enumerate(names):
+    print(f"  {nm:24s} mean {d[:, k].mean():8.2f}  min {d[:, k].min():8.2f}  max {d[:, k].max():8.2f}")
+step = (t[1:, 0] - t[:-1, 0])
+print("  step-to-step            mean %.2f  total %.2f ms" % (step.mean(), step.sum() / 1e3))
+pf.close()
