@@ -260,9 +260,9 @@ def main():
     ap.add_argument("--resampler", default="systematic")
     ap.add_argument("--arith", default="auto", help="auto = uniformized32 for SIR/SEIR filters, fast32 otherwise (and for ABC)")
     ap.add_argument("--block", type=int, default=0)
-    ap.add_argument("--exchange", default="auto", choices=["auto", "pull", "push"],
-                    help="N = 1 only: pull = whole-filter kernel with grid barrier + ancestor search (sem_pf_run); push = the "
-                         "sharded filter's kernel with one rank (resampling in offspring form through the record buffers)")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "pull"],
+                    help="N = 1 only: pull = force the whole-filter kernel with grid barrier + ancestor search (pf_persistent); "
+                         "auto = sem_pf_run's default (pf_persistent_x with one rank: resampling in offspring form)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded"],
@@ -307,13 +307,13 @@ def main():
     # ---------------------------------------------------------------- device-resident timing ("value")
     cfg = engine.make_pf_config(0, N, T, probs=w["probs"], observations=w["observations"], resampler=args.resampler,
                                 arith=args.arith, seed=1234, filter_id0=rank * 4096, mu=[w["mu"]],
-                                n_population=[w["n_population"]], block_particles=args.block)
+                                n_population=[w["n_population"]], block_particles=args.block, grid_barrier=args.exchange == "pull")
     out = engine.alloc_pf_outputs(cfg, dev)
     Yd = torch.from_numpy(Y).to(dev)
     thd = torch.from_numpy(theta).to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
     stream = torch.cuda.current_stream()
-    sharded_mode = world > 1 or args.exchange == "push"
+    sharded_mode = world > 1
     peer = None
     if sharded_mode:                                                      # one filter of world x N particles over the ranks
         from sem_b200 import sharded as shd
@@ -437,7 +437,8 @@ def main():
         i_alg = I_ALG_BY_ARITH.get(args.arith, I_ALG_DECLARED)
         launches = res.launches
         traffic = DRAM_TRAFFIC_PER_PASS.get(args.arith) if (N == workloads.HEADLINE["n_particles"] and launches == 1) else None
-        kname = "pf_persistent_x" if sharded_mode else ("pf_persistent" if launches == 1 else "pf_step")
+        kname = "pf_persistent_x" if (sharded_mode or (launches == 1 and args.exchange != "pull" and args.resampler == "systematic")) else \
+            ("pf_persistent" if launches == 1 else "pf_step")
         roofline = {"bound": "issue", "kernel": kname + f"<SirModel, {args.arith}>",
                     "achieved": events_per_s * i_alg / 1e9, "peak": issue_peak / 1e9, "unit": "Gthread-inst/s",
                     "frac": events_per_s * i_alg / issue_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
@@ -466,7 +467,8 @@ def main():
                        "parallelism": (f"one filter of {world}x{N} particles sharded over {world} GPUs: global systematic resampling, "
                                        "CTA weight partials + child records exchanged through peer memory inside one cooperative "
                                        "launch per rank (no NCCL call, no host work per step)") if world > 1 else
-                                      ("1 GPU, push-form resampling (sharded kernel, one rank)" if sharded_mode else "1 GPU")},
+                                      ("1 GPU, whole-filter kernel with grid barrier + ancestor search" if args.exchange == "pull" else
+                                       "1 GPU, whole-filter kernel, resampling in offspring form (the sharded filter's kernel with one rank)")},
             "independent_chains": independent,
             "pmcmc_iters_per_s": world * K / (dev_ms_max / 1e3), "events_per_s": events_per_s * world,
             "log_likelihood": logz, "gpu_launches": K * res.launches, "clocks": clocks,

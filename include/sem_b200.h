@@ -90,8 +90,11 @@ typedef struct sem_pf_config {
     int32_t n_filters;      /* independent filters (chains / thetas) run side by side, >= 1 */
     int32_t block_particles;/* particles per CTA, 0 = choose from N and the SM count */
     int32_t store_history;  /* 1: write all T rows of X_hist/ancestry; 0: keep only two rows (ping-pong) */
-    int32_t reserved;       /* 1: force one launch per step (default 0: one cooperative launch for the whole filter
-                               when all CTAs are co-resident; results are bit-identical) */
+    int32_t reserved;       /* launch mode.  0 (default): one cooperative launch for the whole filter when all CTAs are
+                               co-resident -- with systematic resampling and one filter the kernel resamples in offspring
+                               form through record buffers in the workspace (pf_persistent_x with one rank), otherwise
+                               with a grid barrier + ancestor search per step (pf_persistent); 1: force one launch per
+                               step; 2: force the grid-barrier kernel.  Results are bit-identical in all modes. */
     double probs;           /* p_obs (binomial) or noise ratio (normal), pmcmc.py:128 */
     double dt;              /* observation interval, the reference uses 1 (pmcmc.py:205) */
     uint64_t seed;          /* Philox key */

@@ -51,12 +51,16 @@ def abc_rejection(observed_data, no_of_samples, threshold, priors, *, seed=None,
     obs = np.asarray(observed_data, dtype=np.float64)
     T = obs.shape[0]
     prior4 = [priors["beta"][0], priors["beta"][1], priors["gamma"][0], priors["gamma"][1]]
-    seed = engine.new_seed() if seed is None else seed
     run_batch = run_batch or _device_batch
     run_traj = run_traj or _device_trajectories
     dist = torch.distributed if (torch.distributed.is_available() and torch.distributed.is_initialized()) else None
     world = dist.get_world_size() if dist else 1
     rank = dist.get_rank() if dist else 0
+    seed = engine.new_seed() if seed is None else seed
+    if dist and world > 1:                                            # ONE Philox key for all ranks: trial ids are global, and every
+        box = [seed]                                                  # rank re-simulates the accepted ids (rank 0's seed wins)
+        dist.broadcast_object_list(box, src=0)
+        seed = box[0]
     batch = batch or max(1 << 16, 64 * no_of_samples)
     next_id, trials, events = 0, 0, 0
     acc_ids, acc_theta, acc_dist = [], [], []

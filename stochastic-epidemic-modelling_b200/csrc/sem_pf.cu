@@ -335,6 +335,12 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
     int rc = fill_dev(cfg, buf, P, w, replay);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!replay && use_persistent(cfg, w, replay)) {         // systematic resampling, one filter: the exchange kernel with one rank
+        bool launched = false;                               // (resampling in offspring form, no grid barrier, no ancestor search)
+        rc = xchg_run_single(cfg, P, w, (char *)buf->workspace + w.xarena, s, &launched);
+        if (rc) return rc;
+        if (launched) return SEM_OK;
+    }
     if (use_persistent(cfg, w, replay)) {                    // one launch, nothing else (the kernel initialises its outputs)
         void *args[] = {(void *)&P};
         const dim3 grid(w.nb, cfg->n_filters), block(persistent_threads(cfg, w, &P.split_main));

@@ -370,7 +370,10 @@ __device__ __forceinline__ bool xchg_is_publisher(const XchgDev &X, const int ti
     return (tid >> 5) == (((int)blockDim.x - 1) >> 5) && (tid & 31) < X.W;
 }
 __device__ __forceinline__ void xchg_early_fence(const XchgDev &X, const int tid) {
-    if (xchg_is_publisher(X, tid)) __threadfence_system();
+    if (xchg_is_publisher(X, tid)) {
+        if (X.W == 1) __threadfence();                       // one rank: every access comes from this GPU
+        else __threadfence_system();
+    }
 }
 __device__ __forceinline__ void xchg_publish(const XchgDev &X, const unsigned gen, const int gb, const int tid, const double mb, const double sb) {
     if (xchg_is_publisher(X, tid)) st_vol(X.part[tid & 31] + (size_t)(gen % 3u) * X.NB + gb, mb, sb);

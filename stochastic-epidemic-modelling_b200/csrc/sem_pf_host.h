@@ -38,7 +38,7 @@ static int validate(const sem_pf_config *c) {
     return SEM_OK;
 }
 
-struct WsLayout { size_t L[2], pfx[2], scale[2], total[2], part, counter, wtab, bytes; int nb, ppb, wt_n; };
+struct WsLayout { size_t L[2], pfx[2], scale[2], total[2], part, counter, wtab, xarena, xarena_bytes, bytes; int nb, ppb, wt_n; };
 
 // total population = the largest count a compartment (or a group sum) can hold; 0 = no table (unknown, or > 1 GiB)
 static int weight_table_n(const sem_pf_config *c) {
@@ -54,6 +54,39 @@ static int weight_table_n(const sem_pf_config *c) {
     const double bytes = (double)(c->n_obs - 1) * c->n_obs_cols * (tot + 1) * sizeof(double);
     return bytes <= 268435456.0 ? (int)tot : 0;
 }
+static WsLayout ws_layout(const sem_pf_config *c);
+
+// One rank's arena: control block (error flag, path-sampler mailbox), partial tables [3][NB], record buffers [2][N][RW],
+// packed iteration result.  Identical on every rank (same cfg, same device type).
+struct ArenaLayout { size_t err, mail, part, rec, iter, bytes; int NB, nb, RW, C; };
+
+static ArenaLayout arena_layout_nb(const sem_pf_config *cfg, int world, int nb_rank) {
+    ArenaLayout a;
+    struct { int nb; } w{nb_rank};
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    a.C = model_cols(cfg->model, G);
+    a.RW = (a.C + 1 + 3) & ~3;
+    a.nb = w.nb; a.NB = w.nb * world;
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    a.err = take(64); a.mail = take(64);
+    a.part = take(3 * (size_t)a.NB * sizeof(double2));
+    a.rec = take(2 * (size_t)cfg->n_particles * a.RW * sizeof(int32_t));
+    a.iter = take((SEM_ITER_HEADER + (size_t)cfg->n_obs * a.C) * sizeof(double));
+    a.bytes = off;
+    return a;
+}
+
+
+// push-form resampling (the sharded filter's kernel with one rank, sem_pf_xchg.cu) is also the single-GPU whole-filter
+// kernel of sem_pf_run when these hold; its arena then lives in the caller's workspace and is re-marked per launch
+static bool push_eligible(const sem_pf_config *c) {
+    static int env_off = -1;
+    if (env_off < 0) { const char *e = getenv("SEM_NO_PUSH"); env_off = (e && e[0] == '1') ? 1 : 0; }
+    return !env_off && c->n_filters == 1 && c->resampler == SEM_RESAMPLE_SYSTEMATIC && c->reserved == 0 && c->n_obs >= 2 &&
+           (c->arith == SEM_ARITH_FAST32 || c->arith == SEM_ARITH_UNIFORMIZED32);
+}
+
 static WsLayout ws_layout(const sem_pf_config *c) {
     WsLayout w;
     w.ppb = choose_ppb(c);
@@ -69,9 +102,17 @@ static WsLayout ws_layout(const sem_pf_config *c) {
     w.counter = take(F * sizeof(unsigned int));
     w.wt_n = weight_table_n(c);
     w.wtab = take(w.wt_n ? (size_t)(c->n_obs - 1) * c->n_obs_cols * ((size_t)w.wt_n + 1) * sizeof(double) : 0);
+    w.xarena_bytes = push_eligible(c) ? arena_layout_nb(c, 1, w.nb).bytes : 0;
+    w.xarena = take(w.xarena_bytes);
     w.bytes = off;
     return w;
 }
+static ArenaLayout arena_layout(const sem_pf_config *cfg, int world) { return arena_layout_nb(cfg, world, ws_layout(cfg).nb); }
+
+// sem_pf_xchg.cu: launch the one-rank exchange kernel on an arena inside the workspace (launched = false: not available
+// for this configuration / device, the caller takes the grid-barrier kernel)
+int xchg_run_single(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, void *arena, cudaStream_t s, bool *launched);
+bool xchg_single_available(const sem_pf_config *cfg);
 
 static int hist_rows(const sem_pf_config *c) { return c->store_history ? c->n_obs : (c->n_obs < 2 ? c->n_obs : 2); }
 

@@ -39,27 +39,6 @@ static const void *xchg_kernel(const sem_pf_config *cfg) {
     }
 }
 
-// One rank's arena: control block (error flag, path-sampler mailbox), partial tables [3][NB], record buffers [2][N][RW],
-// packed iteration result.  Identical on every rank (same cfg, same device type).
-struct ArenaLayout { size_t err, mail, part, rec, iter, bytes; int NB, nb, RW, C; };
-
-static ArenaLayout arena_layout(const sem_pf_config *cfg, int world) {
-    ArenaLayout a;
-    const WsLayout w = ws_layout(cfg);
-    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
-    a.C = model_cols(cfg->model, G);
-    a.RW = (a.C + 1 + 3) & ~3;
-    a.nb = w.nb; a.NB = w.nb * world;
-    size_t off = 0;
-    auto take = [&](size_t bytes) { size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
-    a.err = take(64); a.mail = take(64);
-    a.part = take(3 * (size_t)a.NB * sizeof(double2));
-    a.rec = take(2 * (size_t)cfg->n_particles * a.RW * sizeof(int32_t));
-    a.iter = take((SEM_ITER_HEADER + (size_t)cfg->n_obs * a.C) * sizeof(double));
-    a.bytes = off;
-    return a;
-}
-
 struct XchgPlan { const void *fn; int threads, split_main, kper; size_t smem; };
 
 static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
@@ -89,6 +68,64 @@ static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
         set_error("this rank's particles are not co-resident on one GPU: use the host-driven exchange (sem_shard_*)");
         return SEM_ERR_INVALID;
     }
+    return SEM_OK;
+}
+
+// Fill the exchange descriptor of one launch and launch the kernel.  arenas[r] = rank r's arena in this address space.
+static int xchg_launch(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, const XchgPlan &pl, const ArenaLayout &a, int world, int rank,
+                       void *const *arenas, uint32_t generation, uint32_t tag, double timeout_s, bool want_iter, cudaStream_t s) {
+    P.j0 = rank * cfg->n_particles;
+    P.split_main = pl.split_main;
+    XchgDev X;
+    memset(&X, 0, sizeof(X));
+    X.W = world; X.rank = rank; X.NB = a.NB; X.kper = pl.kper;
+    X.Ng = (long long)cfg->n_particles * world;
+    X.gen0 = generation;
+    X.tag = tag;
+    int dev = 0, khz = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    SEM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    X.timeout = (long long)((timeout_s > 0 ? timeout_s : 20.0) * 1e3 * (khz > 0 ? khz : 1965000));
+    for (int r = 0; r < world; r++) {
+        char *base = (char *)arenas[r];
+        X.part[r] = (double2 *)(base + a.part); X.rec[r] = (int32_t *)(base + a.rec);
+        X.mail[r] = (unsigned long long *)(base + a.mail); X.iter[r] = (double *)(base + a.iter);
+    }
+    X.err = (int *)((char *)arenas[rank] + a.err);
+    if (world == 1 && P.iter_out) X.iter[0] = P.iter_out;    // one rank: the caller's own result buffer
+    else P.iter_out = want_iter ? X.iter[rank] : nullptr;
+    void *args[] = {(void *)&P, (void *)&X};
+    SEM_CUDA(cudaLaunchCooperativeKernel(pl.fn, dim3(w.nb, 1), dim3(pl.threads), args, pl.smem, s));
+    return SEM_OK;
+}
+
+static int arena_mark_empty(const ArenaLayout &a, void *arena, cudaStream_t s) {
+    char *base = (char *)arena;
+    SEM_CUDA(cudaMemsetAsync(base, 0, a.part, s));                                  // error flag, mailbox
+    SEM_CUDA(cudaMemsetAsync(base + a.part, 0xFF, a.iter - a.part, s));            // partial tables and records: all-ones = empty
+    return SEM_OK;
+}
+
+bool xchg_single_available(const sem_pf_config *cfg) {
+    XchgPlan pl;
+    if (!push_eligible(cfg)) return false;
+    const bool ok = xchg_plan(cfg, 1, pl) == SEM_OK;
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+
+int xchg_run_single(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, void *arena, cudaStream_t s, bool *launched) {
+    *launched = false;
+    XchgPlan pl;
+    if (!push_eligible(cfg) || !w.xarena_bytes) return SEM_OK;
+    if (xchg_plan(cfg, 1, pl) != SEM_OK) { cudaGetLastError(); return SEM_OK; }
+    const ArenaLayout a = arena_layout(cfg, 1);
+    int rc = arena_mark_empty(a, arena, s);                  // the workspace is scratch: empty marks per launch (a few MB of memset)
+    if (rc) return rc;
+    void *arenas[1] = {arena};
+    rc = xchg_launch(cfg, P, w, pl, a, 1, 0, arenas, 0u, 1u, 0.0, P.iter_out != nullptr, s);
+    if (rc) return rc;
+    *launched = true;
     return SEM_OK;
 }
 
@@ -151,11 +188,9 @@ int sem_peer_enable(int32_t device, int32_t peer_device) {
 int sem_xchg_reset(const sem_pf_config *cfg, int32_t world, void *arena, void *stream) {
     if (validate(cfg) || !arena || world < 1 || world > SEM_MAX_RANKS) { set_error("bad arena reset"); return SEM_ERR_INVALID; }
     const ArenaLayout a = arena_layout(cfg, world);
-    char *base = (char *)arena;
-    cudaStream_t s = (cudaStream_t)stream;
-    SEM_CUDA(cudaMemsetAsync(base, 0, a.part, s));                                  // error flag, mailbox
-    SEM_CUDA(cudaMemsetAsync(base + a.part, 0xFF, a.iter - a.part, s));            // partial tables and records: all-ones = empty
-    SEM_CUDA(cudaMemsetAsync(base + a.iter, 0, a.bytes - a.iter, s));
+    int rc = arena_mark_empty(a, arena, (cudaStream_t)stream);
+    if (rc) return rc;
+    SEM_CUDA(cudaMemsetAsync((char *)arena + a.iter, 0, a.bytes - a.iter, (cudaStream_t)stream));
     return SEM_OK;
 }
 
@@ -181,32 +216,15 @@ int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_
     if (rc) return rc;
     if (replay) { set_error("the sharded filter runs in Philox mode"); return SEM_ERR_INVALID; }
     const ArenaLayout a = arena_layout(cfg, x->world);
-    P.j0 = x->rank * cfg->n_particles;
-    P.split_main = pl.split_main;
-    XchgDev X;
-    memset(&X, 0, sizeof(X));
-    X.W = x->world; X.rank = x->rank; X.NB = a.NB; X.kper = pl.kper;
-    X.Ng = (long long)cfg->n_particles * x->world;
-    X.gen0 = x->generation;
-    X.tag = (x->launch_tag % 4095u) + 1u;
-    int dev = 0, khz = 0;
-    SEM_CUDA(cudaGetDevice(&dev));
-    SEM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
-    X.timeout = (long long)((x->timeout_s > 0 ? x->timeout_s : 20.0) * 1e3 * (khz > 0 ? khz : 1965000));
-    for (int r = 0; r < x->world; r++) {
-        char *base = (char *)x->arena[r];
-        X.part[r] = (double2 *)(base + a.part); X.rec[r] = (int32_t *)(base + a.rec);
-        X.mail[r] = (unsigned long long *)(base + a.mail); X.iter[r] = (double *)(base + a.iter);
+    if (buf->iteration_result && buf->iteration_result != (double *)((char *)x->arena[x->rank] + a.iter)) {
+        set_error("iteration_result must be sem_xchg_iteration_result(arena)"); return SEM_ERR_INVALID;
     }
-    X.err = (int *)((char *)x->arena[x->rank] + a.err);
-    if (buf->iteration_result) {
-        if (buf->iteration_result != X.iter[x->rank]) { set_error("iteration_result must be sem_xchg_iteration_result(arena)"); return SEM_ERR_INVALID; }
-        P.iter_out = X.iter[x->rank];
-    }
-    void *args[] = {(void *)&P, (void *)&X};
-    SEM_CUDA(cudaLaunchCooperativeKernel(pl.fn, dim3(w.nb, 1), dim3(pl.threads), args, pl.smem, (cudaStream_t)stream));
+    const uint32_t tag = (x->launch_tag % 4095u) + 1u;
+    rc = xchg_launch(cfg, P, w, pl, a, x->world, x->rank, x->arena, x->generation, tag, x->timeout_s, buf->iteration_result != nullptr,
+                     (cudaStream_t)stream);
+    if (rc) return rc;
     x->generation = (x->generation + (uint32_t)(cfg->n_obs > 1 ? cfg->n_obs - 1 : 0)) % 6u;   // only its value mod 2 and mod 3 matters
-    x->launch_tag = X.tag;
+    x->launch_tag = tag;
     return SEM_OK;
 }
 

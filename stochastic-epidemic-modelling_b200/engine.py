@@ -112,12 +112,12 @@ class PfResult:
 
 def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, resampler="systematic", arith="auto",
                    seed=0, filter_id0=0, mu=None, n_population=None, dt=1.0, store_history=True, block_particles=0,
-                   launch_per_step=False, path_exact=False):
+                   launch_per_step=False, path_exact=False, grid_barrier=False, theta=None):
     Cn, P, Cobs = model_dims(model, G)
     cfg = _lib.PfConfig(model=model, obs_kind=int(bool(observations)), resampler=RESAMPLERS.get(resampler, resampler),
-                        arith=resolve_arith(model, arith), n_particles=int(N), n_obs=int(T), n_groups=int(G),
+                        arith=resolve_arith(model, arith, theta=theta), n_particles=int(N), n_obs=int(T), n_groups=int(G),
                         n_obs_cols=Cobs, n_filters=int(n_filters), block_particles=int(block_particles),
-                        store_history=int(bool(store_history)), reserved=int(bool(launch_per_step)), probs=float(probs),
+                        store_history=int(bool(store_history)), reserved=1 if launch_per_step else 2 if grid_barrier else 0, probs=float(probs),
                         dt=float(dt), path_exact=int(bool(path_exact)),
                         seed=int(seed) & (2**64 - 1), filter_id0=int(filter_id0) & 0xFFFFFF)
     if mu is not None:

@@ -269,8 +269,7 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
     counters["exchange"] = exchange
     pf = None
     if exchange == "device":
-        pf = sh.PeerFilter(rank, world, model, Y, n_local, arith=arith, theta=th0, path_exact=exact_genealogy, **kw)
-        sh.connect_distributed(pf, group)
+        pf = sh.cached_peer_filter(group, rank, world, model, Y, n_local, arith=arith, theta=th0, path_exact=exact_genealogy, **kw)
 
     def run_filter(theta_vec, it):
         theta2, probs2 = _split(model, G, theta_vec, probs)
@@ -300,7 +299,7 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
             return out_t
         return theta_vec
 
-    try:
+    if True:
         it = 0
         while True:                                                               # pmcmc.py:276-310
             theta_proposal = rng.multivariate_normal(np.array(parameters), h * std)
@@ -324,9 +323,6 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
                 thetas[i] = finish_theta(theta_proposal); loglik[i] = lz; sampled_trajs[:, i, :] = traj
             else:
                 thetas[i] = thetas[i - 1]; loglik[i] = loglik[i - 1]; sampled_trajs[:, i, :] = sampled_trajs[:, i - 1, :]
-    finally:
-        if pf is not None:
-            pf.close()
     if isinstance(stats, dict):
         stats.update(counters)
     return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs

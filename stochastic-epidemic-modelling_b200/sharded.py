@@ -436,6 +436,43 @@ class PeerFilter:
         return int(self.out[4].cpu()[0])
 
 
+_PEER_CACHE = {}
+
+
+def cached_peer_filter(group, rank, world, model, Y, n_local, *, G=1, observations=False, probs=.1, arith="auto", theta=None, seed=0,
+                       mu=None, n_population=None, path_exact=False):
+    """A connected PeerFilter for this configuration, kept across calls (particle_mcmc(sharded=True) called repeatedly does
+    not pay cudaMalloc + CUDA IPC mapping + a barrier each time).  Every rank must call with the same arguments."""
+    Y = np.ascontiguousarray(Y, dtype=np.float64)
+    key = (id(group), rank, world, model, Y.shape, int(n_local), G, bool(observations), bool(path_exact),
+           tuple(np.atleast_1d(mu).tolist()), tuple(np.atleast_1d(n_population).tolist()), torch.cuda.current_device())
+    pf = _PEER_CACHE.get(key)
+    if pf is None:
+        pf = PeerFilter(rank, world, model, Y, n_local, G=G, observations=observations, probs=probs, arith=arith, theta=theta,
+                        seed=seed, mu=mu, n_population=n_population, path_exact=path_exact)
+        connect_distributed(pf, group)
+        _PEER_CACHE[key] = pf
+    else:
+        pf.Y.copy_(torch.from_numpy(Y))
+        pf.cfg.seed = int(seed) & (2**64 - 1)
+        pf.cfg.probs = float(probs)
+        pf.cfg.arith = engine.resolve_arith(model, arith, theta=theta)
+    return pf
+
+
+def _close_cached():
+    for pf in list(_PEER_CACHE.values()):
+        try:
+            pf.close()
+        except Exception:
+            pass
+    _PEER_CACHE.clear()
+
+
+import atexit  # noqa: E402
+atexit.register(_close_cached)
+
+
 def connect_distributed(pf, group=None):
     """Exchange the CUDA IPC handles of the arenas over torch.distributed (once) and map the peers."""
     import torch.distributed as dist

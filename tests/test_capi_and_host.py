@@ -152,6 +152,83 @@ def test_abc_sharding_world2_gloo(tmp_path, c_oracle):
     assert np.array_equal(r0["traj"][:, :, 1:], ref["traj"][acc].astype(float))
 
 
+WORKER_NOSEED = WORKER.replace("seed=7, batch=600", "seed=None, batch=600").replace(
+    'ids=st["accepted_ids"])', 'ids=st["accepted_ids"], seed=np.array([st["seed"]], dtype=np.uint64))').replace(
+    "import sem_b200", "np.random.seed(1000 + int(sys.argv[3]))\nimport sem_b200")
+
+
+def test_abc_sharding_world2_gloo_default_seed(tmp_path, c_oracle):
+    """seed=None under torch.distributed: the ranks' numpy generators differ, rank 0's Philox seed is broadcast, so both
+    ranks key the global trial ids with ONE seed and return the same accepted (theta, trajectory) set, which is the
+    single-process answer for that seed."""
+    port = str(33500 + os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER_NOSEED)
+    out = str(tmp_path / "res")
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    assert int(r0["seed"][0]) == int(r1["seed"][0])
+    assert np.array_equal(r0["ids"], r1["ids"]) and np.array_equal(r0["theta"], r1["theta"]) and np.array_equal(r0["traj"], r1["traj"])
+    obs = golden("abc_sir_small")["observed"]
+    ref = c_oracle.abc_trials(obs, 6000, 45.0, (0, 5, 0, 5), arith=1, seed=int(r0["seed"][0]), trial0=0)
+    acc = np.nonzero(ref["distance"] <= 45.0)[0][:4]
+    assert np.array_equal(r0["ids"], acc) and np.array_equal(r0["theta"], ref["theta"][acc])
+    assert np.array_equal(r0["traj"][:, :, 1:], ref["traj"][acc].astype(float))
+
+
+PATH_WORKER = r"""
+import os, sys, types, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+import sem_b200
+from sem_b200 import sharded
+rank = int(sys.argv[3])
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%s" % sys.argv[2], rank=rank, world_size=2)
+g = np.load(sys.argv[4] + ".in.npz")
+X, A = g["X"], g["A"]                                   # (T,C,N) states, (T,N) GLOBAL parent indices
+N = X.shape[2]
+lo, cnt = sharded.shard_bounds(N, 2)[rank]
+sh = types.SimpleNamespace(n_global=N, X_hist=torch.from_numpy(X[:, :, lo:lo + cnt].copy()), ancestry=torch.from_numpy(A[:, lo:lo + cnt].copy()))
+out = {}
+for exact in (False, True):
+    for fid in (0, 3, 11):
+        out["t_%d_%d" % (exact, fid)] = sharded.path_sample_distributed(sh, 0xBEEF1234, fid, exact=exact)
+np.savez(sys.argv[4] + ".%d.npz" % rank, **out)
+dist.destroy_process_group()
+"""
+
+
+def test_path_sampler_over_shards_world2_gloo(tmp_path, c_oracle):
+    """particle_path_sampler over a sharded history (pmcmc.py:236-248 globalised): the lineage chase with one broadcast
+    per time equals the oracle's path sample on the concatenated history, with the reference's off-by-one indexing and
+    with the exact genealogy; both ranks return the same trajectory; the final particle is the kernels' Philox pick."""
+    from sem_b200 import sharded
+    rng = np.random.RandomState(4)
+    T, C, N = 9, 3, 37
+    X = rng.randint(0, 1000, (T, C, N)).astype(np.int32)
+    A = rng.randint(0, N, (T, N)).astype(np.int32)
+    A[0] = 0
+    out = str(tmp_path / "res")
+    np.savez(out + ".in.npz", X=X, A=A)
+    port = str(35500 + os.getpid() % 2000)
+    script = tmp_path / "worker.py"
+    script.write_text(PATH_WORKER)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r), out]) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    r0, r1 = np.load(out + ".0.npz"), np.load(out + ".1.npz")
+    for exact in (False, True):
+        for fid in (0, 3, 11):
+            k = "t_%d_%d" % (exact, fid)
+            assert np.array_equal(r0[k], r1[k])
+            chosen = sharded.path_pick(0xBEEF1234, fid, N)
+            u, _ = c_oracle.philox_uniform_pair(0xBEEF1234, 0, 0, 0, 4, fid)
+            assert chosen == min(int(u * N), N - 1)
+            ref = c_oracle.path_sample(np.ascontiguousarray(np.transpose(X, (0, 2, 1))), A, chosen, exact=exact)
+            assert np.array_equal(r0[k], ref.astype(float)), (exact, fid)
+
+
 # ------------------------------------------------------------------ sharded filter: host-side logic
 def test_sharded_host_arithmetic(c_oracle):
     from sem_b200 import sharded

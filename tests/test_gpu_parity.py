@@ -849,14 +849,18 @@ def test_single_cooperative_launch_equals_launch_per_step(sem, model, G, theta, 
     Y = _truth_Y(model, T, 5, .1, False, G=G)
     for F, N, hist in [(1, 3000, True), (3, 700, True), (1, 5000, False)]:
         outs = []
-        for per_step in (False, True):
+        for per_step, grid_barrier in ((False, False), (True, False), (False, True)):   # default (offspring form for F = 1), per step, grid barrier
             cfg = sem.engine.make_pf_config(model, N, T, G=G, n_filters=F, probs=.1, resampler=1, arith=arith, seed=6, filter_id0=2,
-                                            mu=mu, n_population=npop, store_history=hist, launch_per_step=per_step)
+                                            mu=mu, n_population=npop, store_history=hist, launch_per_step=per_step, grid_barrier=grid_barrier)
             r = sem.engine.run_pf(cfg, Y, np.tile(np.array(theta, float), (F, 1)))
             torch.cuda.synchronize()
             outs.append((r.launches, r.X_hist.cpu().numpy(), r.ancestry.cpu().numpy(), r.log_zetas.cpu().numpy(), r.n_events.cpu().numpy(),
                          r.status.cpu().numpy()))
-        assert outs[0][0] == 1 and outs[1][0] == T + 1                        # T steps + the weight-table kernel
+        assert outs[0][0] == 1 and outs[1][0] in (T, T + 1) and outs[2][0] == 1      # T steps (+ the weight-table kernel)
+        for k in (3, 5):                                                       # grid-barrier kernel == default kernel, everything
+            assert np.array_equal(outs[2][k], outs[0][k])
+        if hist and not outs[0][5].any():
+            assert np.array_equal(outs[2][1], outs[0][1]) and np.array_equal(outs[2][2], outs[0][2]) and np.array_equal(outs[2][4], outs[0][4])
         assert np.array_equal(outs[0][5], outs[1][5])                          # status (0, or the step of the collapse)
         for f in range(F):
             upto = int(outs[0][5][f]) or T                                     # rows before a collapse are defined, later ones are not

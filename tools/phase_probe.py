@@ -20,7 +20,7 @@ _lib._lib = None
 L = _lib.load()
 Y = workloads.headline_Y()
 N = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 100000
-cfg = engine.make_pf_config(0, N, 101, probs=.1, seed=1, mu=[20], n_population=[10000])
+cfg = engine.make_pf_config(0, N, 101, probs=.1, seed=1, mu=[20], n_population=[10000], grid_barrier=True)   # pf_persistent
 out = engine.alloc_pf_outputs(cfg)
 for _ in range(3):
     engine.run_pf(cfg, Y, np.array([.4, .2]), out=out)
