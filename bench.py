@@ -50,6 +50,19 @@ LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
 DRAM_TRAFFIC_PER_PASS = {"uniformized32": 0.62848e6 + 149.0688e6, "fast32": 883.968e3 + 143.988224e6}
 
 
+def workload_config(w, N, T, theta, world, resampler="systematic", arith="uniformized32", exchange="auto"):
+    """The `config` object of the JSON line -- the same for the GPU arm and the reference arm (which times a bounded
+    sample of this workload; the sample is described in its cpu_baseline.sample)."""
+    return {"workload": w["name"], "model": "SIR", "n_particles": N, "n_obs": T, "population": w["n_population"],
+            "theta": [float(v) for v in theta], "obs_model": "binomial p=0.1", "resampler": resampler, "arith": arith,
+            "l2": "flushed between timed iterations (256 MiB write)", "n_particles_global": world * N,
+            "parallelism": (f"one filter of {world}x{N} particles sharded over {world} GPUs: global systematic resampling, "
+                            "CTA weight partials + child records exchanged through peer memory inside one cooperative "
+                            "launch per rank (no NCCL call, no host work per step)") if world > 1 else
+                           ("1 GPU, whole-filter kernel with grid barrier + ancestor search" if exchange == "pull" else
+                            "1 GPU, whole-filter kernel, resampling in offspring form (the sharded filter's kernel with one rank)")}
+
+
 def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -94,7 +107,15 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(Y, w, n_particles, threads, seed=1):
+def host_threads():
+    # every host thread the process may use, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def cpu_port(Y, w, n_particles, threads, seed=1):
     """C restatement of the reference (oracle/sem_oracle.c) on the host cores: bounded sample of the workload."""
     from oracle import c_oracle as co
     co.build()
@@ -110,38 +131,78 @@ def cpu_baseline(Y, w, n_particles, threads, seed=1):
                 events_per_s=o["n_events"] / dt, seconds=dt)
 
 
+def cpu_reference(Y, w, n_particles, jobs, seed=0):
+    """The UNMODIFIED Python reference (oracle/_ref, copied there by oracle/make_ref.py): pmcmc.particle_filter
+    (pmcmc.py:123) on a bounded sample of the workload -- fewer particles, every observation interval, same data, same
+    theta.  jobs=1: one core (deterministic); jobs=-1: the reference's own per-particle process pool on all host cores."""
+    from oracle import ref_run
+    if jobs != 1:                                             # loky workers import gillespie_algo by name
+        os.environ["PYTHONPATH"] = ref_run.REF + os.pathsep + os.environ.get("PYTHONPATH", "")
+    r = ref_run.time_particle_filter(Y, list(w["theta"]), w["observations"], w["probs"], n_particles, w["n_population"], w["mu"],
+                                     jobs=jobs, seed=seed)
+    cores = 1 if jobs == 1 else host_threads()
+    return dict(value=r["particle_steps"] / r["seconds"], unit="particle-steps/s", cores=cores, kind="reference",
+                sample=f"unmodified reference pmcmc.particle_filter(jobs={jobs}): {n_particles} particles x {Y.shape[0] - 1} observation "
+                       f"intervals of the same workload in {r['seconds']:.1f} s" + (" (filter collapsed)" if r["collapsed"] else ""),
+                seconds=r["seconds"], log_likelihood=r["log_z"])
+
+
+def cpu_baseline(Y, w):
+    """cpu_baseline of the GPU arm's line: the Python reference on ONE core (bounded sample, ~20 s), with the C port's
+    figure beside it; the C port alone when oracle/_ref did not travel."""
+    from oracle import ref_run
+    port = cpu_port(Y, w, 5000, 1)
+    port.pop("seconds")
+    if not ref_run.available():
+        port["note"] = "oracle/_ref absent: Python reference not timed here (BASELINE.md: ~220 particle-steps/s/core)"
+        return port
+    cb = cpu_reference(Y, w, 50, 1)
+    cb.pop("seconds")
+    cb["c_port_1_thread"] = port
+    return cb
+
+
 def run_reference_arm(args):
+    """--impl reference: the reference's own CPU implementation on this box's host cores, all of them (jobs=-1 is the
+    reference's process pool, one task per particle per step, pmcmc.py:201-220).  One step = one particle_filter call on a
+    bounded sample: 64 particles (not the 1e5 of the GPU arm: the reference needs ~12 h per pass at that size; its cost is
+    linear in the particle count) x all 100 observation intervals of the same data.  Falls back to the C port when
+    oracle/_ref is absent."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    from oracle import ref_run
     w = workloads.HEADLINE
     Y = workloads.headline_Y()
-    n_sample = 10_000
     T = Y.shape[0]
-    # every host thread the process may use, stated explicitly: torchrun exports OMP_NUM_THREADS=1 to its workers
-    try:
-        threads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        threads = os.cpu_count() or 1
+    threads = host_threads()
+    use_ref = ref_run.available()
+    n_sample = 64 if use_ref else 10_000
+    run = (lambda n, sd: cpu_reference(Y, w, n, -1, seed=sd)) if use_ref else (lambda n, sd: cpu_port(Y, w, n, threads, seed=sd))
     for i in range(args.warmup):
-        cpu_baseline(Y, w, 1000, threads, seed=100 + i)
+        run(16 if use_ref else 1000, 100 + i)
     t_tot, last = 0.0, None
     for i in range(args.steps):
-        last = cpu_baseline(Y, w, n_sample, threads, seed=i)
+        last = run(n_sample, i)
         t_tot += last["seconds"]
     value = args.steps * n_sample * (T - 1) / t_tot
-    cb = dict(value=value, unit="particle-steps/s", cores=last["cores"], kind="port",
-              sample=f"each step = {n_sample} particles x {T - 1} observation intervals of the {w['name']} workload "
-                     "(C restatement of the Python reference, all host threads)")
+    cb = dict(value=value, unit="particle-steps/s", cores=last["cores"], kind=last["kind"],
+              sample=f"each step = {n_sample} particles x {T - 1} observation intervals of the {w['name']} workload, "
+                     + ("unmodified Python reference, pmcmc.particle_filter(jobs=-1) = its own process pool over all host cores"
+                        if use_ref else "C restatement of the Python reference, all host threads"))
+    if use_ref:
+        port = cpu_port(Y, w, 10_000, threads)
+        port.pop("seconds")
+        cb["c_port_all_threads"] = port
     print(json.dumps({
         "impl": "reference", "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": w["name"], "sample_particles": n_sample, "n_obs": T, "population": w["n_population"]},
+        "config": workload_config(w, w["n_particles"], T, w["theta"], args.gpus),
         "cpu_baseline": cb,
         "e2e": {"value": value, "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference is pure Python (cannot run on the GPU box); its measured rate in the build container is "
-                "~220 particle-steps/s/core (BASELINE.md); this arm is its C port, ~500x faster per core",
+        "note": "same workload (data, theta, population, horizon, metric) as the GPU arm; the timed steps run a bounded sample "
+                f"of {n_sample} particles because the reference's cost is linear in the particle count (about 12 h per pass at 1e5)",
     }))
 
 
@@ -460,25 +521,14 @@ def main():
             "metric": "particle-steps/s", "value": value, "unit": "particle-steps/s", "n_gpus": world, "steps": K,
             "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": w["name"], "model": "SIR", "n_particles": N, "n_obs": T, "population": w["n_population"],
-                       "theta": list(theta), "obs_model": "binomial p=0.1", "resampler": args.resampler, "arith": args.arith,
-                       "l2": "flushed between timed iterations (256 MiB write)",
-                       "n_particles_global": world * N,
-                       "parallelism": (f"one filter of {world}x{N} particles sharded over {world} GPUs: global systematic resampling, "
-                                       "CTA weight partials + child records exchanged through peer memory inside one cooperative "
-                                       "launch per rank (no NCCL call, no host work per step)") if world > 1 else
-                                      ("1 GPU, whole-filter kernel with grid barrier + ancestor search" if args.exchange == "pull" else
-                                       "1 GPU, whole-filter kernel, resampling in offspring form (the sharded filter's kernel with one rank)")},
+            "config": workload_config(w, N, T, theta, world, args.resampler, args.arith, args.exchange),
             "independent_chains": independent,
             "pmcmc_iters_per_s": world * K / (dev_ms_max / 1e3), "events_per_s": events_per_s * world,
             "log_likelihood": logz, "gpu_launches": K * res.launches, "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "e2e": e2e, "wall_s_timed_region": t_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(Y, w, 5000, 1)
-            cb.pop("seconds")
-            cb["python_reference_measured_in_build_container"] = "~220 particle-steps/s/core (BASELINE.md section 2)"
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_baseline(Y, w)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

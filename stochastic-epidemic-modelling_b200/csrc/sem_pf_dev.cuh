@@ -150,14 +150,60 @@ __device__ __forceinline__ LocalScan weigh_local(const PfDev &P, const int p, co
     return LocalScan{incl, mb, sb};
 }
 
-// Combine the CTA partials of parity `par` into (M, total) and per-CTA (prefix, scale) written to pfx_out/scale_out
-// (shared or global memory).  Called by every thread of a CTA.
+// Combine nb CTA partials (m_i, s_i) into the global max M, per-CTA (exclusive prefix, scale = exp(m_i - M)) and the total.
+// ONE summation order whatever the CTA size: entries are scanned in groups of 32 (warp scan), the 32 group totals of a
+// block of 1024 entries by another warp scan, blocks of 1024 chained by a running carry -- so the whole-filter kernels,
+// the launch-per-step path and the sharded filter produce bit-identical cdfs for the same partials.  load(i, m, s) reads
+// entry i (global or shared memory); pfx_out / scale_out may be shared or global memory.  Called by every thread of a CTA.
+template <class Load>
+__device__ __forceinline__ void combine_canonical(const int nb, const int tid, double *sm, Load load, double *pfx_out,
+                                                  double *scale_out, double &M_out, double &total_out) {
+    const int nwarps = (blockDim.x + 31) >> 5, warp = tid >> 5, lane = tid & 31;
+    double M = -CUDART_INF;
+    for (int i = tid; i < nb; i += blockDim.x) { double m, s; load(i, m, s); M = fmax(M, m); }
+    M = block_max(M, sm, tid, nwarps);
+    const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
+    double carry = 0.0;
+    for (int base = 0; base < nb; base += 1024) {
+        __syncthreads();                                     // sm[] is reused (block_max above, the previous block's totals)
+        for (int gi = warp; gi < 32; gi += nwarps) {         // group gi of this block: one warp, one entry per lane
+            const int i = base + gi * 32 + lane;
+            double sc = 0.0, val = 0.0;
+            if (i < nb && finiteM) {
+                double m, sb;
+                load(i, m, sb);
+                sc = (m > -CUDART_INF) ? exp(m - M) : 0.0;
+                val = sc * sb;
+            }
+            const double v = warp_incl_scan_d(val, lane);
+            if (i < nb) { pfx_out[i] = v; scale_out[i] = sc; }   // (inclusive within the group, completed below)
+            if (lane == 31) sm[gi] = v;
+        }
+        __syncthreads();
+        const double ws = warp_incl_scan_d(sm[lane], lane);  // inclusive scan of the 32 group totals
+        for (int gi = warp; gi < 32; gi += nwarps) {
+            const int i = base + gi * 32 + lane;
+            const double off = __shfl_sync(0xffffffffu, ws, gi > 0 ? gi - 1 : 0);
+            if (i < nb) {
+                double m, sb;
+                load(i, m, sb);
+                const double sc = scale_out[i], val = finiteM ? sc * sb : 0.0, v = pfx_out[i];
+                pfx_out[i] = carry + ((gi > 0 ? v + off : v) - val);
+            }
+        }
+        carry = carry + __shfl_sync(0xffffffffu, ws, 31);
+    }
+    M_out = M; total_out = carry;
+}
+
+// Combine the CTA partials of parity `par` (global memory) into (M, total) and per-CTA (prefix, scale) written to
+// pfx_out/scale_out (shared or global memory).  Called by every thread of a CTA.
 __device__ __forceinline__ void combine_partials(const PfDev &P, const int f, const int par, const int tid, double *sm,
                                                  double *pfx_out, double *scale_out, double &M_out, double &total_out) {
     const int nwarps = (blockDim.x + 31) >> 5;
     const double2 *part = P.part + ((size_t)par * P.n_filters + f) * P.nb;
-    if (P.nb <= (int)blockDim.x) {                           // one partial per thread: a single L2 round trip
-        double2 ps = make_double2(-CUDART_INF, 0.0);
+    if (P.nb <= (int)blockDim.x) {                           // one partial per thread: a single L2 round trip (same arithmetic
+        double2 ps = make_double2(-CUDART_INF, 0.0);         // as combine_canonical: warp scans + a scan of the warp totals)
         if (tid < P.nb) ps = __ldcg(&part[tid]);
         const double M = block_max(ps.x, sm, tid, nwarps);
         const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
@@ -168,25 +214,8 @@ __device__ __forceinline__ void combine_partials(const PfDev &P, const int f, co
         M_out = M; total_out = 0.0 + tot;
         return;
     }
-    double M = -CUDART_INF;
-    for (int i = tid; i < P.nb; i += blockDim.x) M = fmax(M, __ldcg(&part[i].x));
-    M = block_max(M, sm, tid, nwarps);
-    double carry = 0.0;
-    const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
-    for (int i0 = 0; i0 < P.nb; i0 += blockDim.x) {
-        const int i = i0 + tid;
-        double sc = 0.0, val = 0.0;
-        if (i < P.nb && finiteM) {
-            const double mi = __ldcg(&part[i].x), si = __ldcg(&part[i].y);
-            sc = (mi > -CUDART_INF) ? exp(mi - M) : 0.0;
-            val = sc * si;
-        }
-        double chunk;
-        const double incl2 = block_incl_scan(val, sm, tid, nwarps, &chunk);
-        if (i < P.nb) { pfx_out[i] = carry + (incl2 - val); scale_out[i] = sc; }
-        carry += chunk;
-    }
-    M_out = M; total_out = carry;
+    combine_canonical(P.nb, tid, sm, [&](int i, double &m, double &s) { const double2 v = __ldcg(&part[i]); m = v.x; s = v.y; },
+                      pfx_out, scale_out, M_out, total_out);
 }
 
 // Weigh the CTA's particles against Y[p], CTA-local scan, and (last CTA to arrive) the step's global combine.
@@ -380,52 +409,43 @@ __device__ __forceinline__ void xchg_publish(const XchgDev &X, const unsigned ge
 }
 
 // Wait for all NB partials of generation `gen` (the resampling barrier) and combine them: global max M, per-CTA
-// (exclusive prefix, scale) into shared memory, total.  Thread t combines the kper consecutive entries [t kper, ...).
-// Also resets this CTA's share of the table of generation gen + 2.  Called by every thread of the CTA.
+// (exclusive prefix, scale) into shared memory, total.  Thread t polls the entries t, t + blockDim, ... and stages them
+// in shared memory (stage[0..NB) = m, stage[NB..2NB) = s); the combine is combine_partials' arithmetic.  Also resets this
+// CTA's share of the table of generation gen + 2.  Called by every thread of the CTA.
 __device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsigned gen, const int b, const int nb, const int tid, double *sm,
-                                                  double *s_pfx, double *s_scale, double &M_out, double &total_out, const int p) {
-    constexpr int KMAX = 4;
-    const int nwarps = (blockDim.x + 31) >> 5, NB = X.NB, base = tid * X.kper;
+                                                  double *s_pfx, double *s_scale, double *stage, double &M_out, double &total_out, const int p) {
+    const int nwarps = (blockDim.x + 31) >> 5, NB = X.NB;
     const double2 *tab = X.part[X.rank] + (size_t)(gen % 3u) * NB;
-    double m[KMAX], s[KMAX];
     const long long t0 = clock64();
     unsigned spins = 0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-        m[k] = -CUDART_INF; s[k] = 0.0;
-        if (k < X.kper && base + k < NB) {
-            for (;;) {
-                unsigned long long a, c;
-                ld_vol(tab + base + k, a, c);
-                if (a != kPartSentinel && c != kPartSentinel) { m[k] = __longlong_as_double((long long)a); s[k] = __longlong_as_double((long long)c); break; }
-                if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X); break; }
-            }
+    double m0 = -CUDART_INF, s0 = 0.0;
+    for (int i = tid; i < NB; i += blockDim.x) {
+        double m = -CUDART_INF, sv = 0.0;
+        for (;;) {
+            unsigned long long a, c;
+            ld_vol(tab + i, a, c);
+            if (a != kPartSentinel && c != kPartSentinel) { m = __longlong_as_double((long long)a); sv = __longlong_as_double((long long)c); break; }
+            if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X); break; }
         }
+        stage[i] = m; stage[NB + i] = sv;
+        if (i == tid) { m0 = m; s0 = sv; }
     }
     PHASE(16);
-    double mx = m[0];
-#pragma unroll
-    for (int k = 1; k < KMAX; k++) mx = fmax(mx, m[k]);
-    const double M = block_max(mx, sm, tid, nwarps);
-    PHASE(17);
-    // every thread of this CTA has left its poll: all CTAs of all ranks have published generation gen, hence finished reading
-    // generation gen - 1, whose table is the one generation gen + 2 will use
-    if (tid < X.W) st_vol(X.part[X.rank] + (size_t)((gen + 2u) % 3u) * NB + tid * nb + b, __longlong_as_double(-1ll), __longlong_as_double(-1ll));
-    const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
-    double sc[KMAX], pre[KMAX], run = 0.0;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++) {
-        sc[k] = (finiteM && m[k] > -CUDART_INF) ? exp(m[k] - M) : 0.0;
-        pre[k] = run;
-        run += sc[k] * s[k];
+    if (NB <= (int)blockDim.x) {                             // one partial per thread, straight from the registers
+        const double M = block_max(m0, sm, tid, nwarps);
+        const bool finiteM = (M > -CUDART_INF && M < CUDART_INF);
+        const double sc = (tid < NB && finiteM && m0 > -CUDART_INF) ? exp(m0 - M) : 0.0, val = sc * s0;
+        double tot;
+        const double incl = block_incl_scan(val, sm, tid, nwarps, &tot);
+        if (tid < NB) { s_pfx[tid] = 0.0 + (incl - val); s_scale[tid] = sc; }
+        M_out = M; total_out = 0.0 + tot;
+    } else {
+        combine_canonical(NB, tid, sm, [&](int i, double &m, double &sv) { m = stage[i]; sv = stage[NB + i]; }, s_pfx, s_scale, M_out, total_out);
     }
-    double tot;
-    const double incl = block_incl_scan(run, sm, tid, nwarps, &tot);
-    const double excl = incl - run;
-#pragma unroll
-    for (int k = 0; k < KMAX; k++)
-        if (k < X.kper && base + k < NB) { s_pfx[base + k] = excl + pre[k]; s_scale[base + k] = sc[k]; }
-    M_out = M; total_out = 0.0 + tot;
+    PHASE(17);
+    // every thread of this CTA has left its poll (CTA barriers above): all CTAs of all ranks have published generation gen,
+    // hence finished reading generation gen - 1, whose table is the one generation gen + 2 will use
+    if (tid < X.W) st_vol(X.part[X.rank] + (size_t)((gen + 2u) % 3u) * NB + tid * nb + b, __longlong_as_double(-1ll), __longlong_as_double(-1ll));
 }
 
 // Children of the CTA's particles (global systematic resampling in offspring form): particle i of global CTA gb owns the
@@ -585,6 +605,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) double s_dyn[];          // pfx[nb], scale[nb] of the previous step (+ the sorted layout's exchange area)
     const int nbt = PUSH ? Xp->NB : P.nb;                    // CTAs of the whole filter
+    const int soff = PUSH ? 4 * nbt : 2 * nbt;               // doubles before the sorted layout's area (PUSH: + the staged partials)
     double *s_pfx = s_dyn, *s_scale = s_dyn + nbt;
     __shared__ int s_J[PUSH ? kMaxThreads : 1];
     __shared__ double sm[32];
@@ -668,7 +689,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         const int par = p & 1;
         const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
         double M, total;
-        if constexpr (PUSH) xchg_wait_combine(*Xp, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, M, total, p);
+        if constexpr (PUSH) xchg_wait_combine(*Xp, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, s_dyn + 2 * nbt, M, total, p);
         else combine_partials(P, f, par ^ 1, tid, sm, s_pfx, s_scale, M, total);
         const bool ok = (M > -CUDART_INF && M < CUDART_INF) && (total > 0.0);
         if (!ok) {
@@ -682,7 +703,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         }
         if constexpr (kUnif) {                               // sorted layout: clear the bins and the range of K
             if (P.split_main < 0) {
-                uint32_t *bins = (uint32_t *)(s_dyn + 2 * nbt + 2 * blockDim.x) + (2 * Model::C + 3) * blockDim.x;
+                uint32_t *bins = (uint32_t *)(s_dyn + soff + 2 * blockDim.x) + (2 * Model::C + 3) * blockDim.x;
                 for (int i = tid; i < 130; i += blockDim.x) bins[i] = i == 129 ? 0xffffffffu : 0u;
             }
         }
@@ -747,7 +768,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
             PHASE(12);
             if (sorted) {
                 const int NT = blockDim.x;
-                double *x_h = s_dyn + 2 * nbt, *x_B = x_h + NT;
+                double *x_h = s_dyn + soff, *x_B = x_h + NT;
                 int32_t *x_x = (int32_t *)(x_B + NT), *x_ret = x_x + Model::C * NT;
                 uint32_t *x_K = (uint32_t *)(x_ret + Model::C * NT), *x_aux = x_K + NT;
                 int32_t *x_home = (int32_t *)(x_aux + NT);
@@ -847,7 +868,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
             WARP_END(run ? ust.last : 0u);
             if (sorted && home >= 0 && leg != 1) {           // back to the home thread (read after the barrier below)
                 const int NT = blockDim.x;
-                int32_t *x_ret = (int32_t *)(s_dyn + 2 * nbt + 2 * NT) + Model::C * NT;
+                int32_t *x_ret = (int32_t *)(s_dyn + soff + 2 * NT) + Model::C * NT;
 #pragma unroll
                 for (int c = 0; c < Model::C; c++) x_ret[c * NT + home] = (int32_t)x[c];
             }
@@ -897,7 +918,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
         if constexpr (kUnif) {
             if (active && via_smem) {
-                const int32_t *x_ret = (const int32_t *)(s_dyn + 2 * nbt + 2 * blockDim.x) + Model::C * blockDim.x;
+                const int32_t *x_ret = (const int32_t *)(s_dyn + soff + 2 * blockDim.x) + Model::C * blockDim.x;
 #pragma unroll
                 for (int c = 0; c < Model::C; c++) {
                     const int32_t v = x_ret[c * blockDim.x + pidx];

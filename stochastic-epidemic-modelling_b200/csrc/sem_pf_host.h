@@ -179,8 +179,8 @@ static int persistent_threads(const sem_pf_config *cfg, const WsLayout &w, int *
 
 // dynamic shared memory of the whole-filter kernel: pfx / scale of the CTAs, plus the sorted layout's exchange area
 // (h, B, state out, state back, K, aux counter, home index per thread, 128 bins + range)
-static size_t persistent_smem(const sem_pf_config *cfg, int nb_filter, int threads, int split_main) {
-    size_t b = 2 * (size_t)nb_filter * sizeof(double);      // nb_filter: CTAs of the whole filter (all ranks of a sharded one)
+static size_t persistent_smem(const sem_pf_config *cfg, int nb_filter, int threads, int split_main, bool push = false) {
+    size_t b = (push ? 4 : 2) * (size_t)nb_filter * sizeof(double);   // nb_filter: CTAs of the whole filter (all ranks of a sharded one)
     if (split_main < 0) {
         const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
         b += (size_t)threads * (2 * sizeof(double) + (2 * C + 3) * sizeof(int32_t)) + 132 * sizeof(uint32_t);

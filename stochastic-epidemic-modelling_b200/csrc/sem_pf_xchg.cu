@@ -55,8 +55,8 @@ static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
     pl.threads = persistent_threads(cfg, w, &pl.split_main);
     const int NB = w.nb * world;
     pl.kper = (NB + pl.threads - 1) / pl.threads;
-    if (pl.kper > 4) { set_error("too many CTAs for the in-kernel combine (world * nb > 4 * threads)"); return SEM_ERR_INVALID; }
-    pl.smem = persistent_smem(cfg, NB, pl.threads, pl.split_main);
+    if (NB > 4096) { set_error("too many CTAs for the in-kernel combine (world * nb > 4096)"); return SEM_ERR_INVALID; }
+    pl.smem = persistent_smem(cfg, NB, pl.threads, pl.split_main, true);
     int dev = 0, coop = 0, per_sm = 0;
     SEM_CUDA(cudaGetDevice(&dev));
     SEM_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
@@ -82,9 +82,11 @@ static int xchg_launch(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, co
     X.Ng = (long long)cfg->n_particles * world;
     X.gen0 = generation;
     X.tag = tag;
-    int dev = 0, khz = 0;
+    int dev = 0;
     SEM_CUDA(cudaGetDevice(&dev));
-    SEM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, dev));
+    static int khz_of[64] = {0};                             // (cudaDevAttrClockRate is a slow query: once per device)
+    if (dev >= 0 && dev < 64 && !khz_of[dev]) { int k = 0; SEM_CUDA(cudaDeviceGetAttribute(&k, cudaDevAttrClockRate, dev)); khz_of[dev] = k > 0 ? k : 1965000; }
+    const int khz = (dev >= 0 && dev < 64) ? khz_of[dev] : 1965000;
     X.timeout = (long long)((timeout_s > 0 ? timeout_s : 20.0) * 1e3 * (khz > 0 ? khz : 1965000));
     for (int r = 0; r < world; r++) {
         char *base = (char *)arenas[r];
