@@ -36,18 +36,28 @@ if ROOT not in sys.path:
 
 import workloads  # noqa: E402
 
-# Thread-instructions per SSA event (SIR, fp64), the per-unit figure of the issue roofline.  SURVEY 8(d) declared a
-# budget of 128 "to be replaced by ncu smsp__inst_executed / events once the kernel exists"; these are the measured
-# values: smsp__inst_executed.sum x thread_inst_per_inst / n_events over the whole-filter kernel
-# (profiles/r01c_pf_persistent_final.txt: 4.4271e9 x 26.49 / 1.598e9; profiles/r01_pf_step_peak.txt for "fast").
-# uniformized32, sorted layout (profiles/r01e_pf_persistent_uniformized32_sorted.txt): 3.2797e9 x 29.34 / 1.5888e9 fired
-# events (the balanced layout of round 1d read 3.911e9 x 25.10 / 1.588e9 = 61.8: 16 % more warp instructions, emptier warps).
-I_ALG_BY_ARITH = {"uniformized32": 60.6, "fast32": 73.4, "fast": 106.0}
+# Roofline inputs.  SURVEY 8(d) declared a budget of 128 thread-instructions per SSA event "to be replaced by ncu
+# smsp__inst_executed / events once the kernel exists".  The measured per-kernel figures (executed thread-instructions per
+# event, DRAM bytes per launch) are NOT pasted here: they are read from profiles/r02_kernel_profile.json, which
+# tools/profile_kernels.py (under ncu) + tools/make_kernel_profile.py write together with the sha256 of the library they
+# were measured on.  If the library loaded now is a different build, the measured roofline is withheld (frac = null,
+# "stale_profile") and only the declared-budget figure is printed.
 I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
 LANES = 148 * 4 * 32   # issue lanes: SMs x schedulers x warp width
-# dram__bytes_read.sum + dram__bytes_write.sum of one whole-filter launch (ncu --set full, same profile)
-DRAM_TRAFFIC_PER_PASS = {"uniformized32": 0.62848e6 + 149.0688e6, "fast32": 883.968e3 + 143.988224e6}
+KERNEL_PROFILE = os.path.join(ROOT, "profiles", "r02_kernel_profile.json")
+
+
+def kernel_profile(tag):
+    """(record, stale) of a profiled kernel; record None when the profile file is missing."""
+    import hashlib
+    try:
+        prof = json.load(open(KERNEL_PROFILE))
+        from sem_b200 import _lib
+        sha = hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()
+        return prof["kernels"].get(tag), prof["lib_sha256"] != sha
+    except Exception:
+        return None, True
 
 
 def workload_config(w, N, T, theta, world, resampler="systematic", arith="uniformized32", exchange="auto"):
@@ -311,6 +321,59 @@ def run_sharded(args):
     dist.destroy_process_group()
 
 
+def run_config5(args):
+    """BASELINE config 5 AS DEFINED (tests/test_pmcmc_sir_subgrps2.py:13-41 scaled to pop 1e6): particle_mcmc on the 2-subgroup
+    SIR with group-summed binomial observations, ONE filter of --particles (default 1e7) particles sharded over all ranks with
+    global systematic resampling and the path sample over the shards, for a few MH iterations.  A rank's 1.25e6 particles
+    are not co-resident on a GPU, so the exchange is the host-driven one (NCCL all-gather + all-to-all-v per step; a step is
+    ~1 s of SSA).  Wall clock around the public call, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    import sem_b200
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev, init_method=None if "MASTER_ADDR" in os.environ else "tcp://127.0.0.1:29534",
+                            rank=rank, world_size=world)
+    pop = args.population if args.population != 100_000 else 1_000_000
+    npop = [int(.4 * pop), pop - int(.4 * pop)]                       # [400000, 600000] at pop 1e6
+    mu = [int(.015 * npop[0]), int(8000 / 600000 * npop[1])]          # [6000, 8000]
+    theta = np.array([5, 2, 1, 3, .5])
+    T = 15
+    y0 = [(npop[0] - mu[0], mu[0], 0), (npop[1] - mu[1], mu[1], 0)]
+    truth = workloads.subgroups_truth(y0, T, theta[:4].reshape(2, 2), theta[4]).reshape(T, 2, 3).sum(1)
+    Y = workloads.observe_binomial(truth, .1, seed=0)
+    N = args.particles or 10_000_000
+    n_it = max(2, min(args.steps, 4))
+    st = {}
+    torch.cuda.synchronize(); dist.barrier()
+    t0 = time.perf_counter()
+    thetas, lik, trajs = sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR_SUBGROUPS2, list(theta), 1e-8, n_chains=n_it, probs=.1,
+                                                n_particles=N, n_population=npop, mu=mu, seed=2026, sharded=True, return_log=True, stats=st)
+    torch.cuda.synchronize()
+    dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    sec = float(dt.cpu()[0])
+    same = torch.tensor(np.concatenate([lik, trajs.reshape(-1)]), device=dev)
+    ref = same.clone()
+    dist.broadcast(ref, src=0)
+    agree = torch.tensor([float(torch.equal(same, ref))], device=dev)
+    dist.all_reduce(agree, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        runs = st["filter_runs"]
+        print(json.dumps({"metric": "particle-steps/s", "value": runs * N * (T - 1) / sec, "unit": "particle-steps/s", "n_gpus": world,
+                          "steps": runs, "warmup": 0, "ms_per_step": 1e3 * sec / runs, "higher_is_better": True, "scaling": "strong",
+                          "dtype": "f64", "data": "synthetic",
+                          "config": {"workload": f"config5_pmcmc_sir_subgroups2_pop{pop}_N{N}_T{T}", "n_population": npop, "mu": mu,
+                                     "theta": theta.tolist(), "exchange": st["exchange"], "api": "sem_b200.particle_mcmc(sharded=True)",
+                                     "parallelism": f"one filter of {N} particles sharded over {world} GPUs, global systematic resampling, "
+                                                    "path sample over the shards"},
+                          "filter_runs": runs, "seconds_per_likelihood": sec / runs, "log_likelihoods": [float(v) for v in lik],
+                          "acceptances": st["acceptances"], "all_ranks_agree": bool(agree.cpu()[0] == 1.0),
+                          "sampled_trajectory_last": trajs[:, -1, :].tolist(), "gpu_launches": st["launches"]}))
+    dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -326,7 +389,7 @@ def main():
                          "auto = sem_pf_run's default (pf_persistent_x with one rank: resampling in offspring form)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded"],
+    ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded", "config5"],
                     help="pf = the BASELINE metric workload (default); abc = ABC rejection trials (config 2); sharded = one "
                          "particle-sharded filter over all ranks (config 5 shape); the last two are extra measurements")
     ap.add_argument("--population", type=int, default=100_000, help="total population of the sharded workload")
@@ -336,7 +399,9 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
     from sem_b200 import engine as _engine            # report the resolved interval simulation, not "auto"
-    args.arith = _engine.ARITH_NAMES[_engine.resolve_arith({"pf": 0, "abc": None, "sharded": 3}[args.workload], args.arith)]
+    args.arith = _engine.ARITH_NAMES[_engine.resolve_arith({"pf": 0, "abc": None, "sharded": 3, "config5": 3}[args.workload], args.arith)]
+    if args.workload == "config5":
+        return run_config5(args)
     if args.workload == "abc":
         return run_abc(args)
     if args.workload == "sharded":
@@ -495,23 +560,35 @@ def main():
         events_per_s = float(events_all.cpu()[0]) / world / (per_gpu_ms / 1e3)          # per GPU
         events_last = float(events_all.cpu()[0]) / world
         issue_peak = LANES * f_sm
-        i_alg = I_ALG_BY_ARITH.get(args.arith, I_ALG_DECLARED)
         launches = res.launches
-        traffic = DRAM_TRAFFIC_PER_PASS.get(args.arith) if (N == workloads.HEADLINE["n_particles"] and launches == 1) else None
+        default_path = (args.arith == "uniformized32" and args.resampler == "systematic" and N == workloads.HEADLINE["n_particles"]
+                        and launches == 1)
+        rec, stale = kernel_profile("headline_sir_grid_barrier" if args.exchange == "pull" and world == 1 else "headline_sir") \
+            if default_path else (None, True)
+        measured = rec is not None and not stale
+        i_alg = rec["thread_inst_per_event"] if measured else None
+        traffic = rec["dram_bytes"] if measured else None
         kname = "pf_persistent_x" if (sharded_mode or (launches == 1 and args.exchange != "pull" and args.resampler == "systematic")) else \
             ("pf_persistent" if launches == 1 else "pf_step")
         roofline = {"bound": "issue", "kernel": kname + f"<SirModel, {args.arith}>",
-                    "achieved": events_per_s * i_alg / 1e9, "peak": issue_peak / 1e9, "unit": "Gthread-inst/s",
-                    "frac": events_per_s * i_alg / issue_peak, "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
+                    "achieved": events_per_s * i_alg / 1e9 if measured else None, "peak": issue_peak / 1e9, "unit": "Gthread-inst/s",
+                    "frac": events_per_s * i_alg / issue_peak if measured else None,
+                    "traffic": traffic, "traffic_unit": "DRAM bytes per launch (ncu)",
                     "events_per_s": events_per_s,
                     "events_per_particle_step": events_last / (N * (T - 1)), "I_alg": i_alg,
-                    "I_alg_source": "ncu: executed thread-instructions per SSA event over the whole-filter kernel (profiles/)",
+                    "I_alg_source": ("profiles/r02_kernel_profile.json: ncu smsp__thread_inst_executed.sum / SSA events of one launch of this "
+                                     "kernel, library sha256 matches the one loaded") if measured else
+                                    ("withheld: " + ("no profile of this configuration" if rec is None else
+                                                     "stale_profile (profiles/r02_kernel_profile.json was measured on another build of the library)")),
+                    "stale_profile": bool(rec is not None and stale),
+                    "issue_active_pct_ncu": rec["issue_active_pct"] if measured else None,
+                    "active_lanes_per_inst_ncu": rec["lanes_per_inst"] if measured else None,
                     "frac_with_declared_I_alg_128": events_per_s * I_ALG_DECLARED / issue_peak,
                     "sm_mhz_used": f_sm / 1e6, "launches_per_pass": launches, "avg_launch_us": 1e3 * per_gpu_ms / launches,
                     "note": "SSA propagate is bound by SM instruction issue, not HBM (SURVEY 8(d)); peak = 148 SMs x 4 "
-                            "schedulers x 32 lanes x SM clock sampled during the run; sm_100a issues the IMAD.WIDE of "
-                            "Philox once per ~4 cycles, so the reachable fraction for this mix is ~0.65 (DESIGN.md); "
-                            "events = fired SSA events (uniformized modes) or uniform pairs drawn (direct modes)"}
+                            "schedulers x 32 lanes x SM clock sampled during the run; frac = issue-active x active lanes / 32; sm_100a "
+                            "issues the IMAD.WIDE of Philox once per ~4 cycles, so the reachable fraction for this mix is ~0.65 "
+                            "(DESIGN.md); events = fired SSA events (uniformized modes) or uniform pairs drawn (direct modes)"}
         hbm_ach = N * (T - 1) * B_ALG / (per_gpu_ms / 1e3) / 1e9
         roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "traffic": traffic, "peak_source": how, "bytes_per_launch": N * (T - 1) * B_ALG / launches,
