@@ -465,7 +465,7 @@ static int64_t ssa_run_unif(const so_model *m, double *x, double max_time, so_st
 
 /* Uniformized interval with 32-bit candidates (arith 4; specification: the comment above ssa_unif32_leg in
  * csrc/sem_common.cuh).  Candidate c of the particle-step = word (c & 3) of Philox call c >> 2 of the SSA stream,
- * u = w / 2^32; bound B = max(a0(x), a0(x + drift * t_rem)) * (c0 + c1 / sqrt(a0 t_rem + 1)); K and the gammas of the
+ * compared with the fixed-point thresholds 2^32 (r_0 + .. + r_j) / B; bound B = max(a0(x), a0(x + drift * t_rem)) * (c0 + c1 / sqrt(a0 t_rem + 1)); K and the gammas of the
  * restart time come from the DOM_AUX stream (52-bit pairs) as in ssa_run_unif; no direct-method tail. */
 static void model_drift(const so_model *m, const double *x, const double *r, double t, double *xp) {
     if (m->model == M_SIR) {
@@ -485,12 +485,122 @@ static void model_drift(const so_model *m, const double *x, const double *r, dou
     }
 }
 
+/* Candidate-count tables (specification: "candidate-count tables" in csrc/sem_common.cuh, construction as in
+ * csrc/sem_host.h): the mean B h of a batch is rounded up to the next double with six mantissa bits (641 grid means in
+ * [4, 4096]); K is drawn from the alias table (Vose) of Poisson(grid mean) over mu +- 10 sigma with one pair of 52-bit
+ * uniforms of the DOM_AUX stream.  Means above 4096 keep poisson_draw_u. */
+#define KTAB_COUNT 641
+typedef struct { double prob; int32_t alias; } ktab_entry;
+static ktab_entry *g_kt_e = NULL;
+static int32_t g_kt_meta[KTAB_COUNT][3];                   /* first entry, entries, first count */
+
+static double ktab_grid_mean(int id) {
+    uint64_t bits = (uint64_t)(((uint32_t)(0x40100000u >> 14) + (uint32_t)id) << 14) << 32;
+    double mu; memcpy(&mu, &bits, 8);
+    return mu;
+}
+
+static void ktab_build(void) {
+    size_t cap = 0, used = 0;
+    for (int id = 0; id < KTAB_COUNT; id++) { double mu = ktab_grid_mean(id); cap += (size_t)(20.0 * sqrt(mu)) + 24; }
+    ktab_entry *e = (ktab_entry *)malloc(cap * sizeof(ktab_entry));
+    double *p = (double *)malloc(4096 * sizeof(double)), *q = (double *)malloc(4096 * sizeof(double));
+    int *small = (int *)malloc(8192 * sizeof(int)), *large = (int *)malloc(4096 * sizeof(int));
+    for (int id = 0; id < KTAB_COUNT; id++) {
+        const double mu = ktab_grid_mean(id), sd = sqrt(mu);
+        long long k_lo = (long long)floor(mu - 10.0 * sd) - 4, k_hi = (long long)ceil(mu + 10.0 * sd) + 12;
+        if (k_lo < 0) k_lo = 0;
+        const int n = (int)(k_hi - k_lo + 1);
+        const long long mode = (long long)floor(mu);
+        p[mode - k_lo] = exp((double)mode * log(mu) - mu - lgamma((double)mode + 1.0));
+        for (long long k = mode; k < k_hi; k++) p[k + 1 - k_lo] = p[k - k_lo] * mu / (double)(k + 1);
+        for (long long k = mode; k > k_lo; k--) p[k - 1 - k_lo] = p[k - k_lo] * (double)k / mu;
+        double sum = 0.0;
+        for (int i = 0; i < n; i++) sum += p[i];
+        int ns = 0, nl = 0, si = 0, li = 0;
+        for (int i = 0; i < n; i++) {
+            q[i] = p[i] * (double)n / sum;
+            if (q[i] < 1.0) small[ns++] = i; else large[nl++] = i;
+            e[used + i].prob = 1.0; e[used + i].alias = i;
+        }
+        while (si < ns && li < nl) {
+            const int a = small[si++], g = large[li];
+            e[used + a].prob = q[a]; e[used + a].alias = g;
+            q[g] = (q[g] + q[a]) - 1.0;
+            if (q[g] < 1.0) { small[ns++] = g; li++; }
+        }
+        g_kt_meta[id][0] = (int32_t)used; g_kt_meta[id][1] = n; g_kt_meta[id][2] = (int32_t)k_lo;
+        used += (size_t)n;
+    }
+    free(p); free(q); free(small); free(large);
+    g_kt_e = e;
+}
+
+static double ktab_round_up(double mu, int *id) {
+    uint64_t bits; memcpy(&bits, &mu, 8);
+    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+    if (!(mu > 4.0)) { *id = 0; return 4.0; }
+    const int on_grid = (hi & 0x3FFFu) == 0u && lo == 0u;
+    *id = (int)((hi >> 14) - (0x40100000u >> 14)) + (on_grid ? 0 : 1);
+    return ktab_grid_mean(*id);
+}
+
+static uint32_t ktab_draw(so_stream *aux, int id) {
+    if (!g_kt_e) {
+#pragma omp critical(sem_ktab)
+        { if (!g_kt_e) ktab_build(); }
+    }
+    double u1, u2;
+    stream_pair(aux, &u1, &u2);
+    const int n = g_kt_meta[id][1];
+    int col = (int)(u1 * (double)n);
+    if (col > n - 1) col = n - 1;
+    const ktab_entry *e = g_kt_e + g_kt_meta[id][0] + col;
+    return (uint32_t)(g_kt_meta[id][2] + (u2 < e->prob ? col : e->alias));
+}
+
+/* K of one batch (test hook) */
+uint32_t so_ktab_philox(double mu, uint64_t seed, uint32_t c1, uint32_t c2, uint32_t domain, uint32_t fid, double *grid_mean) {
+    so_stream s;
+    philox_stream(&s, seed, c1, c2, domain, fid);
+    int id;
+    const double g = ktab_round_up(mu, &id);
+    if (grid_mean) *grid_mean = g;
+    return ktab_draw(&s, id);
+}
+
+/* Fixed-point thresholds of the candidate test (Model::thresholds in csrc/sem_common.cuh): T[j] = 2^52 + round(s (r_0 +
+ * ... + r_j)), chained fused multiply-adds in the reaction order of model_rates_fast, s = 2^32 / B.  The low word of
+ * T[j] is the integer the 32-bit candidate word is compared with. */
+#define MAGIC52 4503599627370496.0
+#define MAGIC52_HI 0x43300000u
+static inline uint32_t lo32(double d) { uint64_t b; memcpy(&b, &d, 8); return (uint32_t)b; }
+static inline uint32_t hi32(double d) { uint64_t b; memcpy(&b, &d, 8); return (uint32_t)(b >> 32); }
+
+static void model_thresholds(const so_model *m, const double *x, double invN, double s, double *T) {
+    const double *th = m->th;
+    if (m->model == M_SIR) {
+        T[0] = fma(x[1], ((th[0] * invN) * s) * x[0], MAGIC52);
+        T[1] = fma(th[1] * s, x[1], T[0]);
+    } else if (m->model == M_SEIR) {
+        T[0] = fma(x[2], ((th[0] * invN) * s) * x[0], MAGIC52);
+        T[1] = fma(th[1] * s, x[1], T[0]);
+        T[2] = fma(th[2] * s, x[2], T[1]);
+    } else {
+        int G = m->G, k = 0; double gs = th[G * G] * s, acc = MAGIC52;
+        for (int a = 0; a < G; a++) {
+            for (int b = 0; b < G; b++) { acc = fma(x[3 * a + 1], ((th[a * G + b] * invN) * s) * x[3 * b], acc); T[k++] = acc; }
+            acc = fma(gs, x[3 * a + 1], acc); T[k++] = acc;
+        }
+    }
+}
+
 static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_stream *s) {
     const double c0 = 1.0, c1 = 2.0, gmax = 1.25;             /* SEM_U32_C0 / SEM_U32_C1 / SEM_U32_GMAX */
     so_stream aux = *s;
     aux.k = 0; aux.c3 = (s->c3 & 0xFFFFFFu) | ((uint32_t)DOM_AUX << 24);
     const int R = m->R;
-    double r[SO_MAX_R], rp[SO_MAX_R], xp[SO_MAX_C], N = model_popsize(m, x), invN = 1.0 / N, t_rem = max_time;
+    double r[SO_MAX_R], rp[SO_MAX_R], xp[SO_MAX_C], T[SO_MAX_R], N = model_popsize(m, x), invN = 1.0 / N, t_rem = max_time;
     int64_t fired = 0;
     uint32_t cand = 0;
     while (model_alive(m, x)) {
@@ -505,24 +615,28 @@ static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_
         if (amax > cap) { h = t_rem * ((cap - a0) / (a0p - a0)); amax = cap; }     /* fast growth: a shorter batch */
         double expect = a0 * h;
         double B = amax * (c0 + c1 / sqrt(expect + 1.0));
-        double Kd = poisson_draw_u(&aux, B * h);
-        uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+        double mu = B * h;
+        uint32_t K;
+        if (mu <= 4096.0) { int id; mu = ktab_round_up(mu, &id); K = ktab_draw(&aux, id); }
+        else { double Kd = poisson_draw_u(&aux, mu); K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u; }
         uint32_t first = cand, last = cand + K;
         int violated = 0, absorbed = 0;
+        const double sc = (4294967296.0 * h) / mu;             /* 2^32 / B for the bound B = mu / h actually used */
+        model_thresholds(m, x, invN, sc, T);
         while (cand < last) {
             uint32_t ctr[4] = {cand >> 2, s->c1, s->c2, s->c3}, w[4];
             so_philox4x32(ctr, s->key, w);
-            double u = (double)w[cand & 3u] * (1.0 / 4294967296.0);
+            const uint32_t wq = w[cand & 3u];
             cand++;
-            double v = fma(u + 1.0, B, -B);                    /* u*B with one rounding, as the kernel's fma(d,B,-B) */
-            if (v < a0) {
-                double acc = r[0]; int j = (acc <= v);
-                for (int i = 1; i < R - 1; i++) { acc = acc + r[i]; j += (acc <= v); }
+            if (wq < lo32(T[R - 1])) {                         /* a real event: reaction j */
+                int j = 0;
+                for (int i = 0; i < R - 1; i++) j += (wq >= lo32(T[i]));
                 model_apply(m, x, j);
                 fired++;
-                model_rates_fast(m, x, invN, r);
-                a0 = 0; for (int i = 0; i < R; i++) a0 = a0 + r[i];
-                if (!(a0 > 0 && a0 <= B)) { violated = a0 > B; absorbed = !violated; break; }
+                model_thresholds(m, x, invN, sc, T);
+                if (!(hi32(T[R - 1]) == MAGIC52_HI && lo32(T[R - 1]) != 0u)) {
+                    violated = hi32(T[R - 1]) != MAGIC52_HI; absorbed = !violated; break;
+                }
             }
         }
         if (!violated) {                                       /* the batch covered its h exactly */

@@ -11,8 +11,10 @@
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/sem_b200.h"
+#include "sem_host.h"
 
 namespace sem {
 
@@ -316,10 +318,78 @@ __device__ __noinline__ double poisson_draw_u(Src &src, double mu, const double2
     }
 }
 
+// ------------------------------------------------------------------------------------------ candidate-count tables
+// The candidate count of a uniformized batch is K ~ Poisson(B h), and the bound B is OURS to choose (any B above the
+// propensity is valid): the mean is rounded UP to the next double with six mantissa bits (<= 1.6 % more candidates, 0.6 %
+// on average) so that it falls on a grid of 641 values in [4, 4096], each with a precomputed alias table (Walker / Vose)
+// of its Poisson law over mu +- 10 sigma (truncated mass < 1e-20, renormalised; built on the host in fp64, sem_host.h).
+// A draw is one Philox call, one 16-byte metadata load and one 16-byte entry load -- no rejection loop, no logarithms,
+// no divergence: 0.5 us instead of 3.4 us per step of the headline filter.  Means above 4096 keep the PTRS sampler.
+struct KTabEntry { double prob; int32_t alias, pad; };      // accept column i with probability prob, else take alias
+struct KTab { const KTabEntry *e; const int4 *meta; };      // meta[id] = (first entry, entries, first count, 0)
+static __device__ KTab g_ktab;                              // bound per translation unit and device (ktab_bind)
+constexpr double kKTabMaxMean = 4096.0;
+constexpr int kKTabShift = 14, kKTabBase = 0x40100000 >> kKTabShift, kKTabCount = ((0x40B00000 >> kKTabShift) - kKTabBase) + 1;
+
+// smallest grid mean >= mu (mu <= 4096): returns the grid mean, id = its table
+__host__ __device__ inline double ktab_round_up(const double mu, int &id) {
+#ifdef __CUDA_ARCH__
+    const uint32_t hi = (uint32_t)__double2hiint(mu), lo = (uint32_t)__double2loint(mu);
+#else
+    uint64_t bits; memcpy(&bits, &mu, 8);
+    const uint32_t hi = (uint32_t)(bits >> 32), lo = (uint32_t)bits;
+#endif
+    if (!(mu > 4.0)) { id = 0; return 4.0; }
+    const uint32_t t = hi >> kKTabShift;
+    const bool on_grid = (hi & ((1u << kKTabShift) - 1u)) == 0u && lo == 0u;
+    id = (int)(t - (uint32_t)kKTabBase) + (on_grid ? 0 : 1);
+#ifdef __CUDA_ARCH__
+    return __hiloint2double((int)(((uint32_t)kKTabBase + (uint32_t)id) << kKTabShift), 0);
+#else
+    const uint64_t ob = (uint64_t)(((uint32_t)kKTabBase + (uint32_t)id) << kKTabShift) << 32;
+    double out; memcpy(&out, &ob, 8);
+    return out;
+#endif
+}
+
+// Point this translation unit's g_ktab at the current device's tables (once per unit and device); called by the host
+// entry points before a kernel that may run uniformized intervals.
+static int ktab_bind() {
+    static bool bound[64] = {false};
+    static std::mutex mu;
+    int dev = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return SEM_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(mu);
+    if (bound[dev]) return SEM_OK;
+    const void *e = nullptr, *m = nullptr;
+    const int rc = ktab_device(&e, &m);
+    if (rc) return rc;
+    KTab kt; kt.e = (const KTabEntry *)e; kt.meta = (const int4 *)m;
+    SEM_CUDA(cudaMemcpyToSymbol(g_ktab, &kt, sizeof(KTab)));
+    bound[dev] = true;
+    return SEM_OK;
+}
+
+template <class Src>
+__device__ __forceinline__ uint32_t ktab_draw(Src &aux, const int id) {
+    const int4 mt = __ldg(&g_ktab.meta[id]);
+    double u1, u2;
+    aux.next(u1, u2);
+    const int col = min((int)__dmul_rn(u1, (double)mt.y), mt.y - 1);
+    const KTabEntry *ep = g_ktab.e + (size_t)mt.x + col;
+    const int4 raw = __ldg(reinterpret_cast<const int4 *>(ep));
+    const double prob = __hiloint2double(raw.y, raw.x);
+    return (uint32_t)(mt.z + (u2 < prob ? col : raw.z));
+}
+
 // ------------------------------------------------------------------------------------------ models
 // State is kept as fp64 integers in registers (exact up to 2^53); converted to int32 at observation boundaries.
 // rates<ARITH>() fills r[] in the reference's reaction order; REF divides by N per event like
 // gillespie_algo.py:38, FAST multiplies by the hoisted beta/N.
+
+constexpr double kMagic52 = 4503599627370496.0;          // 2^52: a double 2^52 + n (0 <= n < 2^32) holds n in its low word
+constexpr uint32_t kMagic52Hi = 0x43300000u;
 
 struct SirModel {
     static constexpr int C = 3, R = 2, NTHETA = 2, G = 1;
@@ -345,6 +415,22 @@ struct SirModel {
         if (TRACK_R) x[2] = x[2] + (inf ? 0.0 : 1.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[2] = N - x[0] - x[1]; }
+    // Fixed-point thresholds of the uniformized candidate test (ssa_unif32_leg): T[j] = 2^52 + round(s (r_0 + .. + r_j)),
+    // reaction order of rates(); the low word of T[j] is the integer a 32-bit candidate word is compared with.
+    struct Scaled { double bNs, gs; };
+    __device__ __forceinline__ void scale(Scaled &sc, const double s) const { sc.bNs = __dmul_rn(bN, s); sc.gs = __dmul_rn(gamma, s); }
+    __device__ __forceinline__ void thresholds(const Scaled &sc, const double *x, double *T) const {
+        T[0] = __fma_rn(x[1], __dmul_rn(sc.bNs, x[0]), kMagic52);
+        T[1] = __fma_rn(sc.gs, x[1], T[0]);
+    }
+    // apply reaction j if `hit` (a select of the +-1 / 0 increment, no branch): same arithmetic as apply()
+    template <bool TRACK_R = true>
+    __device__ __forceinline__ void apply_if(double *x, const bool hit, const int j) const {
+        const bool inf = hit && j == 0;
+        x[0] = x[0] + (inf ? -1.0 : 0.0);
+        x[1] = x[1] + (hit ? (inf ? 1.0 : -1.0) : 0.0);
+        if (TRACK_R) x[2] = x[2] + ((hit && !inf) ? 1.0 : 0.0);
+    }
     // state after the expected net change over a time t (Euler step of the mean-field drift, clamped at 0): the
     // uniformized interval uses it to anticipate growth of the total propensity
     __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
@@ -379,6 +465,23 @@ struct SeirModel {
         if (TRACK_R) x[3] = x[3] + ((j == 2) ? 1.0 : 0.0);
     }
     __device__ __forceinline__ void fix_removed(double *x) const { x[3] = N - x[0] - x[1] - x[2]; }
+    struct Scaled { double bNs, as, gs; };
+    __device__ __forceinline__ void scale(Scaled &sc, const double s) const {
+        sc.bNs = __dmul_rn(bN, s); sc.as = __dmul_rn(alpha, s); sc.gs = __dmul_rn(gamma, s);
+    }
+    __device__ __forceinline__ void thresholds(const Scaled &sc, const double *x, double *T) const {
+        T[0] = __fma_rn(x[2], __dmul_rn(sc.bNs, x[0]), kMagic52);
+        T[1] = __fma_rn(sc.as, x[1], T[0]);
+        T[2] = __fma_rn(sc.gs, x[2], T[1]);
+    }
+    template <bool TRACK_R = true>
+    __device__ __forceinline__ void apply_if(double *x, const bool hit, const int j) const {
+        const bool r0 = hit && j == 0, r1 = hit && j == 1, r2 = hit && j == 2;
+        x[0] = x[0] + (r0 ? -1.0 : 0.0);
+        x[1] = x[1] + (r0 ? 1.0 : (r1 ? -1.0 : 0.0));
+        x[2] = x[2] + (r1 ? 1.0 : (r2 ? -1.0 : 0.0));
+        if (TRACK_R) x[3] = x[3] + (r2 ? 1.0 : 0.0);
+    }
     __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
         const double f0 = __dmul_rn(r[0], t), f1 = __dmul_rn(r[1], t), f2 = __dmul_rn(r[2], t);
         xp[0] = fmax(__dsub_rn(x[0], f0), 0.0);
@@ -444,6 +547,24 @@ struct SubModel {
 #pragma unroll
         for (int g = 0; g < G; g++) x[3 * g + 2] = Ng[g] - x[3 * g] - x[3 * g + 1];
     }
+    struct Scaled { double bNs[G_ * G_], gs; };
+    __device__ __forceinline__ void scale(Scaled &sc, const double s) const {
+#pragma unroll
+        for (int i = 0; i < G * G; i++) sc.bNs[i] = __dmul_rn(bN[i], s);
+        sc.gs = __dmul_rn(gamma, s);
+    }
+    __device__ __forceinline__ void thresholds(const Scaled &sc, const double *x, double *T) const {
+        double acc = kMagic52;
+#pragma unroll
+        for (int a = 0; a < G; a++) {
+#pragma unroll
+            for (int b = 0; b < G; b++) { acc = __fma_rn(x[3 * a + 1], __dmul_rn(sc.bNs[a * G + b], x[3 * b]), acc); T[a * (G + 1) + b] = acc; }
+            acc = __fma_rn(sc.gs, x[3 * a + 1], acc);
+            T[a * (G + 1) + G] = acc;
+        }
+    }
+    template <bool TRACK_R = true>
+    __device__ __forceinline__ void apply_if(double *x, const bool hit, const int j) const { if (hit) apply<TRACK_R>(x, j); }
     __device__ __forceinline__ void drift(const double *x, const double *r, double t, double *xp) const {
 #pragma unroll
         for (int b = 0; b < G; b++) {
@@ -841,10 +962,10 @@ __device__ __forceinline__ long long ssa_run_unif(const Model &m, double *x, dou
 #define SEM_U32_C1 2.0
 #define SEM_U32_GMAX 1.25          /* largest anticipated growth of the total propensity within one batch */
 #endif
-struct Unif32State { double t_rem, h, B; uint32_t cand, first, last, aux_k; int in_batch; };
+struct Unif32State { double t_rem, h, s; uint32_t cand, first, last, aux_k; int in_batch; };   // s = 2^32 / B (B = bound of the batch)
 
 __device__ __forceinline__ void unif32_begin(Unif32State &st, double max_time) {
-    st.t_rem = max_time; st.h = max_time; st.B = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
+    st.t_rem = max_time; st.h = max_time; st.s = 0.0; st.cand = 0; st.first = 0; st.last = 0; st.aux_k = 0; st.in_batch = 0;
 }
 
 // First-batch / next-batch setup of the uniformized loop: bound B, covered time h, candidate count K ~ Poisson(B h).
@@ -867,9 +988,18 @@ __device__ __forceinline__ bool unif32_batch_setup(const Model &m, const double 
         amax = cap;
     }
     const double expect = __dmul_rn(a0, st.h);
-    st.B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
-    const double Kd = poisson_draw_u(aux, __dmul_rn(st.B, st.h), tab);
-    const uint32_t K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+    const double B = __dmul_rn(amax, __dadd_rn(SEM_U32_C0, __ddiv_rn(SEM_U32_C1, sqrt(__dadd_rn(expect, 1.0)))));
+    double mu = __dmul_rn(B, st.h);                               // mean candidate count; rounded up to the tables' grid
+    uint32_t K;
+    if (mu <= kKTabMaxMean) {
+        int id;
+        mu = ktab_round_up(mu, id);
+        K = ktab_draw(aux, id);
+    } else {
+        const double Kd = poisson_draw_u(aux, mu, tab);
+        K = Kd < 2.0e9 ? (uint32_t)Kd : 2000000000u;
+    }
+    st.s = __ddiv_rn(__dmul_rn(4294967296.0, st.h), mu);          // 2^32 / B for the bound B = mu / h actually used
     st.first = st.cand; st.last = st.cand + K; st.in_batch = 1;
     return true;
 }
@@ -888,6 +1018,70 @@ __device__ __forceinline__ double event_tally(const double *x) {
     return t;
 }
 
+// One candidate of the thinned stream against the fixed-point thresholds T (see Model::thresholds): the 32-bit word w is
+// a real event iff w < lo32(T[R-1]) -- probability round(2^32 a0 / B) / 2^32 -- namely reaction j = #{i < R-1 : w >=
+// lo32(T[i])}; integer compares on the low words, no conversion of the word, no fp64 compare.  After a fired event the
+// thresholds are recomputed and the batch stops unless 0 < n(a0) < 2^32, i.e. unless the high word of T[R-1] is still
+// that of 2^52 (the bound holds; n = 2^32 exactly counts as a violation, which is conservative and therefore exact) and
+// its low word is non-zero (not absorbed).
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ void unif32_candidate(const Model &m, const typename Model::Scaled &sc, double *x, double *T,
+                                                 const uint32_t w, const bool live, bool &stop) {
+    int j = 0;
+#pragma unroll
+    for (int i = 0; i < Model::R - 1; i++) j += (w >= (uint32_t)__double2loint(T[i])) ? 1 : 0;
+    const bool hit = live && w < (uint32_t)__double2loint(T[Model::R - 1]);
+    m.template apply_if<TRACK_R>(x, hit, j);
+    m.thresholds(sc, x, T);
+    const bool ok = (uint32_t)__double2hiint(T[Model::R - 1]) == kMagic52Hi && __double2loint(T[Model::R - 1]) != 0;
+    stop = stop || (hit && !ok);
+}
+
+// Serve the candidates [cand, last) of a batch, four per Philox call (candidate c = word c & 3 of call c >> 2), until the
+// batch stops.  A full group is straight-line code (live = not stopped yet); the first group after a restart or a
+// hand-over and the last group of a batch take the general path (words before cand were served already).
+template <class Model, bool TRACK_R>
+__device__ __forceinline__ void unif32_serve(const Model &m, const typename Model::Scaled &sc, double *x, double *T,
+                                             PairSource<false> &loc, uint32_t &cand, const uint32_t last, bool &stop) {
+#ifdef SEM_PIPE_PHILOX
+    loc.k = cand >> 2;
+    uint4 w = loc.raw();
+#endif
+    while (cand < last && !stop) {
+#ifdef SEM_PIPE_PHILOX
+        const uint4 wn = loc.raw();                                    // the next group's words, behind this group's candidates
+#else
+        loc.k = cand >> 2;
+        const uint4 w = loc.raw();
+#endif
+        if ((cand & 3u) == 0u && last - cand >= 4u) {
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const bool live = !stop;
+                cand += live ? 1u : 0u;
+                unif32_candidate<Model, TRACK_R>(m, sc, x, T, words[q], live, stop);
+            }
+        } else {
+            const uint32_t base = cand & ~3u;
+#pragma unroll 1
+            for (uint32_t q = 0; q < 4u; q++) {
+                const uint32_t c = base + q;
+                const bool live = !stop && c >= cand && c < last;
+                const uint32_t wq = q == 0u ? w.x : q == 1u ? w.y : q == 2u ? w.z : w.w;
+                unif32_candidate<Model, TRACK_R>(m, sc, x, T, wq, live, stop);
+                cand += live ? 1u : 0u;
+            }
+        }
+#ifdef SEM_PIPE_PHILOX
+        w = wn;                                                        // (whenever the loop goes on, the next group is call k + 1)
+#endif
+    }
+#ifdef SEM_PIPE_PHILOX
+    loc.k = (cand + 3u) >> 2;                                          // calls consumed, as without the look-ahead
+#endif
+}
+
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32State &st, long long &fired_total, const bool handoff,
                                                PairSource<false> &src, PairSource<false> &aux, const double2 *tab) {
@@ -896,42 +1090,24 @@ __device__ __forceinline__ bool ssa_unif32_leg(const Model &m, double *x, Unif32
     bool finished = true;
     const double tally0 = event_tally<Model>(x);
     for (;;) {
-        double r[Model::R], a0;
-        if (!st.in_batch) {
+        if (!st.in_batch) {                                            // (else: resumed -- second leg, or set up by the caller)
+            double r[Model::R], a0;
             if (!unif32_batch_setup(m, x, st, aux, r, a0, tab)) break;
-        } else {
-            a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);            // resumed (second leg, or set up by the caller)
         }
-        const double B = st.B;
+        typename Model::Scaled sc;
+        m.scale(sc, st.s);                                             // candidate words against 2^32 r / B
+        double T[Model::R];
+        m.thresholds(sc, x, T);
         // a first leg serves the first half of the batch's candidates only: the loop is the same, its bound differs
         const uint32_t last = handoff ? st.first + ((st.last - st.first) >> 1) : st.last;
         uint32_t cand = st.cand;
         bool stop = false;
-        while (cand < last && !stop) {
-            loc.k = cand >> 2;
-            const uint4 w = loc.raw();
-            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
-            const uint32_t base = cand & ~3u;
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-                const uint32_t c = base + q;
-                const bool live = !stop && c >= cand && c < last;      // (c >= cand: words already served before a restart)
-                const double v = __fma_rn(word_to_d12(words[q]), B, -B);   // u * B
-                const bool hit = live && v < a0;
-                double acc = r[0];
-                int j = (acc <= v) ? 1 : 0;
-#pragma unroll
-                for (int i = 1; i < Model::R - 1; i++) { acc = __dadd_rn(acc, r[i]); j += (acc <= v) ? 1 : 0; }
-                if (hit) m.template apply<TRACK_R>(x, j);
-                a0 = ssa_total<Model, SEM_ARITH_FAST>(m, x, r);
-                stop = stop || (hit && !(a0 > 0 && a0 <= B));          // absorbed (a0 = 0) or bound violated
-                cand += live ? 1u : 0u;
-            }
-        }
+        unif32_serve<Model, TRACK_R>(m, sc, x, T, loc, cand, last, stop);
         st.cand = cand;
         if (!stop && cand < st.last) { finished = false; break; }      // hand-over point reached (first leg only)
         st.in_batch = 0;
-        if (!(stop && a0 > B)) {                                       // not violated: the batch covered its h exactly
+        const bool violated = stop && (uint32_t)__double2hiint(T[Model::R - 1]) != kMagic52Hi;
+        if (!violated) {                                               // the batch covered its h exactly
             if (stop || !(st.h < st.t_rem)) break;                     // absorbed, or h was the rest of the interval
             st.t_rem = __dsub_rn(st.t_rem, st.h);
             continue;

@@ -796,7 +796,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
                                t2 = __shfl_sync(0xffffffffu, e2, sl), t3 = __shfl_sync(0xffffffffu, e3, sl);
                 const int pos = (int)((sk == 0 ? t0 : sk == 1 ? t1 : sk == 2 ? t2 : t3) + rank);
                 x_K[pos] = K; x_home[pos] = home < 0 ? -1 : (home | (run ? 0x40000000 : 0)); x_h[pos] = ust.h;   // (K = 0 may still have to run: a batch that covers only part of the interval)
-                x_B[pos] = ust.B; x_aux[pos] = ust.aux_k;
+                x_B[pos] = ust.s; x_aux[pos] = ust.aux_k;
                 if (has) {
 #pragma unroll
                     for (int c = 0; c < Model::C; c++) x_x[c * NT + pos] = (int32_t)x[c];
@@ -809,11 +809,24 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
                 // warps each, on different schedulers: warp 4W + g serves the first half of the batch's candidates
                 // and hands the continuation over, warp 4W + 2 + g finishes the interval -- W + 1/2 rounds per scheduler
                 // instead of W + 1 on two of them.
+                // Heavier chunks go to HIGHER warp ids: the scheduler's arbiter serves the highest eligible warp id first, so
+                // the warp with the longest dependent chain (the CTA's critical path) runs at its own pace from the start
+                // and the lighter warps fill the issue slots it leaves -- instead of all warps sharing the scheduler
+                // equally and the heaviest one finishing alone, latency-bound, after the others.  (Without helper warps
+                // the last warp keeps the lightest chunk: it issues the exchange's fence.)
                 const int nw = NT >> 5, main_w = P.split_main == -2 ? nw - 4 : nw;
+                const int nrev = (P.split_main == -2 || !PUSH) ? main_w : main_w - 1;
+#ifdef SEM_DEAL_NATURAL
+#define SEM_WR(w_) (w_)
+#else
+#define SEM_WR(w_) (nrev - 1 - (w_))
+#endif
                 int chunk;
-                if (warp < main_w) {
-                    const int rnd = warp >> 2, r_last = (main_w - 1) >> 2;
-                    chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (warp & 3) : 3 - (warp & 3));
+                if (warp < nrev) {
+                    const int wr = SEM_WR(warp), rnd = wr >> 2, r_last = (nrev - 1) >> 2;
+                    chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (wr & 3) : 3 - (wr & 3));   // (the last round is in natural order)
+                } else if (warp < main_w) {
+                    chunk = main_w - 1;
                 } else {
                     hg = (warp - main_w) & 1;
                     leg = (warp - main_w) < 2 ? 1 : 2;
@@ -831,7 +844,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
                         for (int c = 0; c < Model::C; c++) x[c] = s_cx[hg][lane][c];
                         if (!s_cfin[hg][lane]) {
                             run = true;
-                            ust.t_rem = s_ct[hg][lane]; ust.B = s_cB[hg][lane]; ust.h = s_ch[hg][lane];
+                            ust.t_rem = s_ct[hg][lane]; ust.s = s_cB[hg][lane]; ust.h = s_ch[hg][lane];
                             ust.cand = s_ck[hg][lane]; ust.first = s_cu[hg][lane][0]; ust.last = s_cu[hg][lane][1]; ust.aux_k = s_cu[hg][lane][2];
                         }
                     }
@@ -841,7 +854,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
 #pragma unroll
                         for (int c = 0; c < Model::C; c++) x[c] = (double)x_x[c * NT + slot];
                     }
-                    if (run) { ust.h = x_h[slot]; ust.B = x_B[slot]; ust.last = x_K[slot]; ust.aux_k = x_aux[slot]; }
+                    if (run) { ust.h = x_h[slot]; ust.s = x_B[slot]; ust.last = x_K[slot]; ust.aux_k = x_aux[slot]; }
                 }
             }
             if (sorted && run) m.setup(P.theta + (size_t)f * P.ntheta, x);
@@ -859,7 +872,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
             if (leg == 1) {                                  // hand over
 #pragma unroll
                 for (int c = 0; c < Model::C; c++) s_cx[hg][lane][c] = x[c];
-                s_ct[hg][lane] = ust.t_rem; s_cB[hg][lane] = ust.B; s_ch[hg][lane] = ust.h;
+                s_ct[hg][lane] = ust.t_rem; s_cB[hg][lane] = ust.s; s_ch[hg][lane] = ust.h;
                 s_ck[hg][lane] = ust.cand; s_cu[hg][lane][0] = ust.first; s_cu[hg][lane][1] = ust.last; s_cu[hg][lane][2] = ust.aux_k;
                 s_cfin[hg][lane] = fin ? 1 : 0;
                 __threadfence_block();

@@ -123,6 +123,7 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
         set_error("null buffer"); return SEM_ERR_INVALID;
     }
     replay = buf->replay_ssa_u != nullptr;
+    if (cfg->arith == SEM_ARITH_UNIFORMIZED32 && (rc = ktab_bind()) != SEM_OK) return rc;   // candidate-count tables of this device
     if (replay && (!buf->replay_resample_u || !buf->replay_ssa_off || !buf->X0)) { set_error("replay needs resample_u, ssa_off and X0"); return SEM_ERR_INVALID; }
     const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
     w = ws_layout(cfg);

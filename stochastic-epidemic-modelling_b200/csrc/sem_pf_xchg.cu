@@ -74,6 +74,10 @@ static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
 // Fill the exchange descriptor of one launch and launch the kernel.  arenas[r] = rank r's arena in this address space.
 static int xchg_launch(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, const XchgPlan &pl, const ArenaLayout &a, int world, int rank,
                        void *const *arenas, uint32_t generation, uint32_t tag, double timeout_s, bool want_iter, cudaStream_t s) {
+    if (cfg->arith == SEM_ARITH_UNIFORMIZED32) {             // this translation unit's view of the candidate-count tables
+        const int rcb = ktab_bind();
+        if (rcb) return rcb;
+    }
     P.j0 = rank * cfg->n_particles;
     P.split_main = pl.split_main;
     XchgDev X;

@@ -299,6 +299,7 @@ int sem_ssa_simulate(const sem_sim_config *cfg, const int32_t *x0, const double 
     P.x0 = x0; P.theta = theta; P.replay_u = replay_u; P.replay_off = (const long long *)replay_off;
     P.x_out = x_out; P.states = states; P.n_rows = (long long *)n_rows; P.times = times;
     const bool replay = replay_u != nullptr;
+    if (cfg->arith == SEM_ARITH_UNIFORMIZED32 && !replay) { const int rc = ktab_bind(); if (rc) return rc; }
     cudaStream_t s = (cudaStream_t)stream;
     switch (cfg->model) {
         case SEM_MODEL_SIR: launch_sim<SirModel>(P, cfg->arith, replay, s); break;
