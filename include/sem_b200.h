@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define SEM_ABI_VERSION 1
+#define SEM_ABI_VERSION 2
 #define SEM_MAX_GROUPS 4
 
 /* pmcmc.py:116-120 ModelType */
@@ -126,6 +126,10 @@ typedef struct sem_pf_buffers {
      * ancestry chased backwards) and packs, per filter, device double[SEM_ITER_HEADER + T*C] =
      * { log_zetas[T-1], status, n_events, chosen final particle, trajectory[T][C] } for a single D2H copy. */
     double *iteration_result;
+    /* Observation parameter per filter (device [n_filters]; binomial p / normal sd factor), or NULL = cfg->probs for
+     * every filter.  With theta per filter this lets one launch evaluate a BATCH of Metropolis-Hastings proposals that
+     * also differ in the estimated p_obs (pmcmc.py:283-296 / 339-352). */
+    const double *probs_per_filter;
 } sem_pf_buffers;
 #define SEM_ITER_HEADER 4
 
@@ -143,6 +147,8 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
 int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *theta, const int32_t *X0,
                     double *log_zetas_out, double *zetas_out, double *hidden_process_out, double *ancestry_out,
                     uint64_t *n_events_out);
+/* sem_pf_run_host keeps one grow-only device workspace per device between calls; this returns the memory. */
+int sem_host_workspace_release(void);
 
 /* ------------------------------------------------------------------------------------------------
  * Particle-sharded filter (one filter too large for one GPU): every rank owns a contiguous slice

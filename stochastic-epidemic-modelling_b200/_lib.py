@@ -18,7 +18,7 @@ ERR_PEER = -5
 SEM_MAX_RANKS = 8
 
 EXPORTS = [
-    "sem_abi_version", "sem_last_error", "sem_device_info",
+    "sem_abi_version", "sem_last_error", "sem_device_info", "sem_host_workspace_release",
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
     "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
     "sem_ssa_simulate", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
@@ -44,6 +44,7 @@ class PfBuffers(C.Structure):
         ("replay_resample_u", C.c_void_p), ("replay_ssa_u", C.c_void_p), ("replay_ssa_off", C.c_void_p),
         ("X_hist", C.c_void_p), ("ancestry", C.c_void_p), ("log_zetas", C.c_void_p), ("status", C.c_void_p),
         ("n_events", C.c_void_p), ("workspace", C.c_void_p), ("iteration_result", C.c_void_p),
+        ("probs_per_filter", C.c_void_p),
     ]
 
 
@@ -151,7 +152,7 @@ def load():
     L.sem_test_fast_math.restype = C.c_int
     L.sem_test_fast_math.argtypes = [C.c_void_p] * 4 + [C.c_int64]
     L.sem_test_poisson.argtypes = [C.c_double, C.c_uint64, C.c_uint32, C.c_uint32, C.c_void_p, C.c_int64]
-    if L.sem_abi_version() != 1:
+    if L.sem_abi_version() != 2:
         raise SemError("libsem_b200.so ABI version mismatch")
     _lib = L
     return L

@@ -1039,21 +1039,15 @@ __device__ __forceinline__ void unif32_candidate(const Model &m, const typename 
 
 // Serve the candidates [cand, last) of a batch, four per Philox call (candidate c = word c & 3 of call c >> 2), until the
 // batch stops.  A full group is straight-line code (live = not stopped yet); the first group after a restart or a
-// hand-over and the last group of a batch take the general path (words before cand were served already).
+// hand-over and the last group of a batch take the general path (words before cand were served already).  (Computing the
+// next group's Philox words behind this group's candidates was measured: the lone-warp latency of a group stays 540
+// cycles -- ptxas does not interleave the two chains -- and the filter gets 6 % slower; tools/micro/cand_loop.cu.)
 template <class Model, bool TRACK_R>
 __device__ __forceinline__ void unif32_serve(const Model &m, const typename Model::Scaled &sc, double *x, double *T,
                                              PairSource<false> &loc, uint32_t &cand, const uint32_t last, bool &stop) {
-#ifdef SEM_PIPE_PHILOX
-    loc.k = cand >> 2;
-    uint4 w = loc.raw();
-#endif
     while (cand < last && !stop) {
-#ifdef SEM_PIPE_PHILOX
-        const uint4 wn = loc.raw();                                    // the next group's words, behind this group's candidates
-#else
         loc.k = cand >> 2;
         const uint4 w = loc.raw();
-#endif
         if ((cand & 3u) == 0u && last - cand >= 4u) {
             const uint32_t words[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
@@ -1073,13 +1067,7 @@ __device__ __forceinline__ void unif32_serve(const Model &m, const typename Mode
                 cand += live ? 1u : 0u;
             }
         }
-#ifdef SEM_PIPE_PHILOX
-        w = wn;                                                        // (whenever the loop goes on, the next group is call k + 1)
-#endif
     }
-#ifdef SEM_PIPE_PHILOX
-    loc.k = (cand + 3u) >> 2;                                          // calls consumed, as without the look-ahead
-#endif
 }
 
 template <class Model, bool TRACK_R>

@@ -452,6 +452,10 @@ int sem_hist_to_f64(const int32_t *X_hist, int32_t T, int32_t N, int32_t C, doub
     return SEM_OK;
 }
 
+static void *g_host_ws[64] = {nullptr};                     // sem_pf_run_host's workspace, per device
+static size_t g_host_ws_bytes[64] = {0};
+static std::mutex g_host_ws_mu[64];
+
 int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *theta, const int32_t *X0,
                     double *log_zetas_out, double *zetas_out, double *hidden_out, double *ancestry_out, uint64_t *n_events_out) {
     int rc = validate(cfg);
@@ -467,7 +471,19 @@ int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *the
     size_t oY = 0, oth = oY + al(nY * 8), oX0 = oth + al(nth * 8), oH = oX0 + al(X0 ? (size_t)C * N * 4 : 0), oA = oH + al(nh * 4),
            oZ = oA + al(na * 4), oS = oZ + al((size_t)T * 8), oE = oS + 256, oW = oE + 256, oF = oW + al(wsb),
            tot = oF + al(((hidden_out ? nh : 0) > (ancestry_out ? na : 0) ? (hidden_out ? nh : 0) : (ancestry_out ? na : 0)) * 8);
-    SEM_CUDA(cudaMalloc(&d, tot));
+    // One grow-only device workspace per device, reused across calls (a PMCMC loop calls this once per iteration; the
+    // cudaMalloc / cudaFree pair of a 160 MB block costs more than the headline filter itself).  Calls on the same device
+    // are serialised by the lock; sem_host_workspace_release() returns the memory.
+    int dev = 0;
+    SEM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { set_error("device index out of range"); return SEM_ERR_INVALID; }
+    std::lock_guard<std::mutex> lock(g_host_ws_mu[dev]);
+    if (g_host_ws_bytes[dev] < tot) {
+        if (g_host_ws[dev]) { cudaFree(g_host_ws[dev]); g_host_ws[dev] = nullptr; g_host_ws_bytes[dev] = 0; }
+        SEM_CUDA(cudaMalloc(&g_host_ws[dev], tot));
+        g_host_ws_bytes[dev] = tot;
+    }
+    d = (char *)g_host_ws[dev];
     cudaStream_t s = 0;
     rc = SEM_OK;
     auto fail = [&](cudaError_t e, const char *what) { if (e != cudaSuccess && rc == SEM_OK) { set_error("%s: %s", what, cudaGetErrorString(e)); rc = SEM_ERR_CUDA; } };
@@ -501,9 +517,23 @@ int sem_pf_run_host(const sem_pf_config *cfg, const double *Y, const double *the
             for (int i = T - 1; i >= 0; i--) zetas_out[i] = exp(src[i]);
         }
     }
-    cudaFree(d);
     if (rc != SEM_OK) return rc;
     return status;
+}
+
+int sem_host_workspace_release(void) {
+    for (int dev = 0; dev < 64; dev++) {
+        std::lock_guard<std::mutex> lock(g_host_ws_mu[dev]);
+        if (g_host_ws[dev]) {
+            int cur = 0;
+            SEM_CUDA(cudaGetDevice(&cur));
+            SEM_CUDA(cudaSetDevice(dev));
+            cudaFree(g_host_ws[dev]);
+            SEM_CUDA(cudaSetDevice(cur));
+            g_host_ws[dev] = nullptr; g_host_ws_bytes[dev] = 0;
+        }
+    }
+    return SEM_OK;
 }
 
 }  // extern "C"

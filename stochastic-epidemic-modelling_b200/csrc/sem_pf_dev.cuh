@@ -18,6 +18,7 @@ struct PfDev {
     uint32_t filter_id0;
     double mu[SEM_MAX_GROUPS], npop[SEM_MAX_GROUPS];
     const double *Y, *theta;
+    const double *probs_f;     // [F] observation parameter per filter, or null = probs for every filter
     const int32_t *X0;
     const double *res_u, *ssa_u;
     const long long *ssa_off;
@@ -70,8 +71,8 @@ __device__ __forceinline__ double block_incl_scan(double v, double *sm, int tid,
 }
 
 // log-weight of one observed column given the compartment count (pmcmc.py:179,181)
-__device__ __forceinline__ double column_logw(const PfDev &P, double y, double xc, const double2 *tab) {
-    return (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf_obs(binom_obs(y, tab), xc, P.probs, tab) : norm_logpdf(y, xc, P.probs, tab);
+__device__ __forceinline__ double column_logw(const PfDev &P, double y, double xc, const double2 *tab, const double probs) {
+    return (P.obs_kind == SEM_OBS_BINOMIAL) ? binom_logpmf_obs(binom_obs(y, tab), xc, probs, tab) : norm_logpdf(y, xc, probs, tab);
 }
 
 // The weight of a column depends on the particle only through an integer count in [0, total population], and Y is
@@ -83,12 +84,13 @@ __device__ __forceinline__ void weight_table_fill(const PfDev &P, size_t first, 
     for (size_t i = first; i < total; i += stride) {
         const size_t pc = i / per_col;
         const double y = P.Y[pc];                            // Y[p][c], p = pc / Cobs
-        P.wtab[i] = (y != y) ? 0.0 : column_logw(P, y, (double)(i - pc * per_col), tab);
+        P.wtab[i] = (y != y) ? 0.0 : column_logw(P, y, (double)(i - pc * per_col), tab, P.probs);   // (no table with per-filter parameters)
     }
 }
 
 template <class Model>
-__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double *wrow, const double2 *tab) {
+__device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double *wrow, const double2 *tab,
+                                                const double probs) {
     double lw = CUDART_INF;
 #pragma unroll
     for (int c = 0; c < Model::C; c++) {
@@ -103,7 +105,7 @@ __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x,
             if (y != y) continue;                            // extension: a NaN entry of Y marks an unobserved column
             double l;
             if (wrow && xc >= 0.0 && xc <= (double)P.wt_n) l = wrow[(size_t)c * (P.wt_n + 1) + (int)xc];
-            else l = column_logw(P, y, xc, tab);
+            else l = column_logw(P, y, xc, tab, probs);
             lw = (l < lw || l != l) ? l : lw;                // min over columns; NaN sticks
         }
     }
@@ -117,9 +119,13 @@ static __device__ unsigned long long g_warp_end[256 * 32];          // CTA 0: wh
 static __device__ unsigned int g_warp_work[256 * 32];
 #define WARP_END(work) do { const unsigned int wk_ = __reduce_max_sync(0xffffffffu, (unsigned int)(work)); \
     if ((tid & 31) == 0 && b == 0 && p < 256) { g_warp_end[p * 32 + (tid >> 5)] = (unsigned long long)clock64(); g_warp_work[p * 32 + (tid >> 5)] = wk_; } } while (0)
+static __device__ unsigned long long g_cta_t[2 * 128 * 160];          // per step and CTA: globaltimer (ns) after the SSA phase / at the publication
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define CTA_T(k) do { if (tid == 0 && p < 128 && b < 160) g_cta_t[((k) * 128 + p) * 160 + b] = gtimer(); } while (0)
 #else
 #define PHASE(k)
 #define WARP_END(work)
+#define CTA_T(k)
 #endif
 
 // Weigh the CTA's particles against Y[p] and CTA-local scan: writes L[par] and the CTA partial (m_b, s_b) -- or, for the
@@ -132,7 +138,8 @@ __device__ __forceinline__ LocalScan weigh_local(const PfDev &P, const int p, co
     const int N = P.N, par = p & 1;
     double lw = -CUDART_INF;
     if (active) {
-        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, P.wtab ? P.wtab + (size_t)p * P.Cobs * (P.wt_n + 1) : nullptr, tab);
+        lw = particle_logw<Model>(P, x, P.Y + (size_t)p * P.Cobs, P.wtab ? P.wtab + (size_t)p * P.Cobs * (P.wt_n + 1) : nullptr, tab,
+                                  P.probs_f ? __ldg(&P.probs_f[f]) : P.probs);
         if (lw != lw) lw = CUDART_INF;                       // NaN -> +inf marker => collapse in the combine
     }
     PHASE(8);
@@ -367,7 +374,8 @@ struct XchgDev {
     int32_t *rec[SEM_MAX_RANKS];    // [2][N][RW]
     unsigned long long *mail[SEM_MAX_RANKS];   // path-sampler token, one slot per rank
     double *iter[SEM_MAX_RANKS];    // [SEM_ITER_HEADER + T*C] packed result of the iteration, one copy per rank (or null)
-    int *err;                       // this rank's error flag
+    int *err;                       // this rank's error flag (1 = a peer did not answer)
+    size_t filter_stride;           // one rank, several filters (grid y): filter f uses the arena at f * filter_stride bytes
 };
 
 __device__ __forceinline__ void st_vol(double2 *p, double a, double b) {
@@ -387,7 +395,9 @@ __device__ __forceinline__ int4 ld_vol(const int32_t *p) {
 constexpr unsigned long long kPartSentinel = ~0ull;
 template <int C> struct RecWords { static constexpr int value = (C + 1 + 3) & ~3; };
 
-__device__ __forceinline__ void xchg_fail(const XchgDev &X) { *(volatile int *)X.err = 1; }
+template <class T> __device__ __forceinline__ T *xsh(T *p, const size_t fsh) { return (T *)((char *)p + fsh); }   // pointer into filter f's arena
+__device__ __forceinline__ void xchg_fail(const XchgDev &X, const size_t fsh) { *(volatile int *)xsh(X.err, fsh) = 1; }
+__device__ __forceinline__ bool xchg_failed(const XchgDev &X, const size_t fsh) { return *(volatile int *)xsh(X.err, fsh) == 1; }   // (an arena marked empty holds all-ones)
 
 // Publish this CTA's partial of generation `gen` to every rank: the first W lanes of the CTA's LAST warp, one destination
 // each.  The same lanes ran xchg_early_fence after this step's resets (records and partial table; made visible to them
@@ -404,18 +414,18 @@ __device__ __forceinline__ void xchg_early_fence(const XchgDev &X, const int tid
         else __threadfence_system();
     }
 }
-__device__ __forceinline__ void xchg_publish(const XchgDev &X, const unsigned gen, const int gb, const int tid, const double mb, const double sb) {
-    if (xchg_is_publisher(X, tid)) st_vol(X.part[tid & 31] + (size_t)(gen % 3u) * X.NB + gb, mb, sb);
+__device__ __forceinline__ void xchg_publish(const XchgDev &X, const size_t fsh, const unsigned gen, const int gb, const int tid, const double mb, const double sb) {
+    if (xchg_is_publisher(X, tid)) st_vol(xsh(X.part[tid & 31], fsh) + (size_t)(gen % 3u) * X.NB + gb, mb, sb);
 }
 
 // Wait for all NB partials of generation `gen` (the resampling barrier) and combine them: global max M, per-CTA
 // (exclusive prefix, scale) into shared memory, total.  Thread t polls the entries t, t + blockDim, ... and stages them
 // in shared memory (stage[0..NB) = m, stage[NB..2NB) = s); the combine is combine_partials' arithmetic.  Also resets this
 // CTA's share of the table of generation gen + 2.  Called by every thread of the CTA.
-__device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsigned gen, const int b, const int nb, const int tid, double *sm,
+__device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const size_t fsh, const unsigned gen, const int b, const int nb, const int tid, double *sm,
                                                   double *s_pfx, double *s_scale, double *stage, double &M_out, double &total_out, const int p) {
     const int nwarps = (blockDim.x + 31) >> 5, NB = X.NB;
-    const double2 *tab = X.part[X.rank] + (size_t)(gen % 3u) * NB;
+    const double2 *tab = xsh(X.part[X.rank], fsh) + (size_t)(gen % 3u) * NB;
     const long long t0 = clock64();
     unsigned spins = 0;
     double m0 = -CUDART_INF, s0 = 0.0;
@@ -425,7 +435,7 @@ __device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsign
             unsigned long long a, c;
             ld_vol(tab + i, a, c);
             if (a != kPartSentinel && c != kPartSentinel) { m = __longlong_as_double((long long)a); sv = __longlong_as_double((long long)c); break; }
-            if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X); break; }
+            if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X, fsh); break; }
         }
         stage[i] = m; stage[NB + i] = sv;
         if (i == tid) { m0 = m; s0 = sv; }
@@ -445,14 +455,14 @@ __device__ __forceinline__ void xchg_wait_combine(const XchgDev &X, const unsign
     PHASE(17);
     // every thread of this CTA has left its poll (CTA barriers above): all CTAs of all ranks have published generation gen,
     // hence finished reading generation gen - 1, whose table is the one generation gen + 2 will use
-    if (tid < X.W) st_vol(X.part[X.rank] + (size_t)((gen + 2u) % 3u) * NB + tid * nb + b, __longlong_as_double(-1ll), __longlong_as_double(-1ll));
+    if (tid < X.W) st_vol(xsh(X.part[X.rank], fsh) + (size_t)((gen + 2u) % 3u) * NB + tid * nb + b, __longlong_as_double(-1ll), __longlong_as_double(-1ll));
 }
 
 // Children of the CTA's particles (global systematic resampling in offspring form): particle i of global CTA gb owns the
 // slots [J(lower_i), J(upper_i)), upper_i = min(pf + sc L_i, prefix of the next CTA) and lower_i = upper_{i-1} -- exactly
 // the particle the search of select_ancestor finds for those slots.  One record per child goes to the owner of the slot.
 template <class Model>
-__device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X, const unsigned gen, const int p_next, const uint32_t fid,
+__device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X, const size_t fsh, const unsigned gen, const int p_next, const uint32_t fid,
                                                const int b, const int gb, const int tid, const int pidx, const bool active,
                                                const int j, const double *x, const double incl, const double total,
                                                const double *s_pfx, const double *s_scale, int *s_J) {
@@ -482,7 +492,7 @@ __device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X,
     const size_t half = (size_t)((gen + 1u) & 1u) * N * RW;
     auto put = [&](const long long ch, const int (&rec)[RW]) {
         const int r = (int)(ch / N);
-        int32_t *dst = X.rec[r] + half + (size_t)(ch - (long long)r * N) * RW;
+        int32_t *dst = xsh(X.rec[r], fsh) + half + (size_t)(ch - (long long)r * N) * RW;
 #pragma unroll
         for (int q = 0; q < RW; q += 4) st_vol(dst + q, rec[q], rec[q + 1], rec[q + 2], rec[q + 3]);
     };
@@ -503,9 +513,9 @@ __device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X,
 
 // The child's side: wait for the record of local slot j in generation `gen`, reset it, return state and parent index.
 template <class Model>
-__device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X, const unsigned gen, const int j, double *x) {
+__device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X, const size_t fsh, const unsigned gen, const int j, double *x) {
     constexpr int C = Model::C, RW = RecWords<C>::value;
-    int32_t *src = X.rec[X.rank] + ((size_t)(gen & 1u) * P.N + j) * RW;
+    int32_t *src = xsh(X.rec[X.rank], fsh) + ((size_t)(gen & 1u) * P.N + j) * RW;
     int w[RW];
     const long long t0 = clock64();
     unsigned spins = 0;
@@ -519,7 +529,7 @@ __device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X
         }
         if (ok) break;
         if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) {
-            xchg_fail(X);
+            xchg_fail(X, fsh);
 #pragma unroll
             for (int c = 0; c < RW; c++) w[c] = 0;               // an extinct particle: the launch ends quickly, status SEM_ERR_PEER
             break;
@@ -538,19 +548,20 @@ __device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X
 // reads into EVERY rank's packed iteration result, so all ranks end with the same trajectory and can run the MH accept
 // step redundantly (no host collective per iteration).
 template <int C>
-__device__ void xchg_iteration_epilogue(const PfDev &P, const XchgDev &X) {
+__device__ void xchg_iteration_epilogue(const PfDev &P, const XchgDev &X, const int f, const size_t fsh) {
     const int T = P.T, N = P.N, W = X.W, me = X.rank;
-    double *out = P.iter_out;
-    const int status = *(volatile int32_t *)&P.status[0];
-    out[0] = __ldcg(&P.log_zetas[T - 1]);
+    const size_t ish = (size_t)f * (SEM_ITER_HEADER + (size_t)T * C);    // this filter's block of the packed results (one rank)
+    double *out = P.iter_out + ish;
+    const int status = *(volatile int32_t *)&P.status[f];
+    out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
     out[1] = (double)status;
-    out[2] = P.n_events ? (double)__ldcg(&P.n_events[0]) : 0.0;
+    out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
     if (status != 0) { out[3] = -1.0; return; }
-    const uint4 wd = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, P.filter_id0), P.key);
+    const uint4 wd = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, P.filter_id0 + f), P.key);
     long long idx = min((long long)((bits_to_d12(wd.x, wd.y) - 1.0) * (double)X.Ng), X.Ng - 1);   // np.random.randint(0, N) (pmcmc.py:241)
     out[3] = (double)idx;
     const unsigned long long tag = (unsigned long long)X.tag << 52, kDone = 0xFFFFFull;
-    volatile unsigned long long *mail = X.mail[me];
+    volatile unsigned long long *mail = xsh(X.mail[me], fsh);
     int cur = T - 1;
     bool hold = (int)(idx / N) == me;
     const long long t0 = clock64();
@@ -561,7 +572,7 @@ __device__ void xchg_iteration_epilogue(const PfDev &P, const XchgDev &X) {
             for (;;) {
                 tok = *mail;
                 if ((tok >> 52) == X.tag) break;
-                if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X); return; }
+                if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X, fsh); return; }
             }
             *mail = 0ull;
             const unsigned long long pp = (tok >> 32) & kDone;
@@ -571,15 +582,15 @@ __device__ void xchg_iteration_epilogue(const PfDev &P, const XchgDev &X) {
         const int loc = (int)(idx - (long long)me * N);
 #pragma unroll
         for (int c = 0; c < C; c++) {
-            const double v = (double)__ldcg(&P.X_hist[((size_t)cur * C + c) * N + loc]);
-            for (int r = 0; r < W; r++) *(volatile double *)&X.iter[r][SEM_ITER_HEADER + (size_t)cur * C + c] = v;
+            const double v = (double)__ldcg(&P.X_hist[(((size_t)f * P.hist_rows + cur) * C + c) * N + loc]);
+            for (int r = 0; r < W; r++) *(volatile double *)&X.iter[r][ish + SEM_ITER_HEADER + (size_t)cur * C + c] = v;
         }
         if (cur == 0) {
             __threadfence_system();
             for (int r = 0; r < W; r++) if (r != me) *(volatile unsigned long long *)X.mail[r] = tag | (kDone << 32);
             return;
         }
-        idx = __ldcg(&P.ancestry[(size_t)(P.path_exact ? cur : cur - 1) * N + loc]);     // reference indexes row p
+        idx = __ldcg(&P.ancestry[((size_t)f * P.hist_rows + (P.path_exact ? cur : cur - 1)) * N + loc]);     // reference indexes row p
         cur -= 1;
         const int owner = (int)(idx / N);
         if (owner != me) {
@@ -603,6 +614,10 @@ template <class Model, int ARITH, bool PUSH>
 __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev *Xp) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    // One rank may run several filters side by side (grid y; a batch of Metropolis-Hastings proposals): filter f has its
+    // own arena, fsh bytes further on, so the filters never wait for each other -- the only grid-wide barriers are the
+    // two outside the step loop.  (P and *Xp stay kernel parameters: constant-bank operands, no registers.)
+    const size_t fsh = (PUSH && gridDim.y > 1) ? (size_t)blockIdx.y * Xp->filter_stride : 0;
     extern __shared__ __align__(16) double s_dyn[];          // pfx[nb], scale[nb] of the previous step (+ the sorted layout's exchange area)
     const int nbt = PUSH ? Xp->NB : P.nb;                    // CTAs of the whole filter
     const int soff = PUSH ? 4 * nbt : 2 * nbt;               // doubles before the sorted layout's area (PUSH: + the staged partials)
@@ -676,7 +691,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
     const int gb = PUSH ? Xp->rank * P.nb + b : b;           // this CTA in the whole filter
     if (P.T > 1) {
         ls = weigh_local<Model, PUSH>(P, 0, f, b, tid, active, j, x, sm, s_tab);
-        if constexpr (PUSH) xchg_publish(*Xp, Xp->gen0, gb, tid, ls.mb, ls.sb);
+        if constexpr (PUSH) xchg_publish(*Xp, fsh, Xp->gen0, gb, tid, ls.mb, ls.sb);
     }
     bool dead = false;
     double lz = 0.0;
@@ -689,7 +704,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         const int par = p & 1;
         const int row = p % P.hist_rows, prow = (p + P.hist_rows - 1) % P.hist_rows;
         double M, total;
-        if constexpr (PUSH) xchg_wait_combine(*Xp, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, s_dyn + 2 * nbt, M, total, p);
+        if constexpr (PUSH) xchg_wait_combine(*Xp, fsh, Xp->gen0 + (unsigned)(p - 1), b, P.nb, tid, sm, s_pfx, s_scale, s_dyn + 2 * nbt, M, total, p);
         else combine_partials(P, f, par ^ 1, tid, sm, s_pfx, s_scale, M, total);
         const bool ok = (M > -CUDART_INF && M < CUDART_INF) && (total > 0.0);
         if (!ok) {
@@ -716,7 +731,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         }
         PHASE(2);
         if constexpr (PUSH)                                  // resample, offspring form: one record per child, to the slot's owner
-            xchg_offspring<Model>(P, *Xp, Xp->gen0 + (unsigned)(p - 1), p, fid, b, gb, tid, pidx, active, j, x, ls.incl, total, s_pfx, s_scale, s_J);
+            xchg_offspring<Model>(P, *Xp, fsh, Xp->gen0 + (unsigned)(p - 1), p, fid, b, gb, tid, pidx, active, j, x, ls.incl, total, s_pfx, s_scale, s_J);
         PHASE(18);
         long long pairs = 0;
         int32_t *Xr = Xf + (size_t)row * Model::C * N;
@@ -724,7 +739,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         PairSource<false> src;
         if (starts) {
             if constexpr (PUSH) {
-                const int a = xchg_take_record<Model>(P, *Xp, Xp->gen0 + (unsigned)p, j, x);   // (state, global parent) stored by the parent
+                const int a = xchg_take_record<Model>(P, *Xp, fsh, Xp->gen0 + (unsigned)p, j, x);   // (state, global parent) stored by the parent
                 PHASE(6);
                 Af[(size_t)row * N + j] = a;
             } else {
@@ -809,21 +824,17 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
                 // warps each, on different schedulers: warp 4W + g serves the first half of the batch's candidates
                 // and hands the continuation over, warp 4W + 2 + g finishes the interval -- W + 1/2 rounds per scheduler
                 // instead of W + 1 on two of them.
-                // Heavier chunks go to HIGHER warp ids: the scheduler's arbiter serves the highest eligible warp id first, so
-                // the warp with the longest dependent chain (the CTA's critical path) runs at its own pace from the start
-                // and the lighter warps fill the issue slots it leaves -- instead of all warps sharing the scheduler
-                // equally and the heaviest one finishing alone, latency-bound, after the others.  (Without helper warps
-                // the last warp keeps the lightest chunk: it issues the exchange's fence.)
+                // Heavier chunks go to HIGHER warp ids: the scheduler's arbiter favours the higher warp id among eligible
+                // warps, so the warps with the longest dependent chains (the CTA's critical path) get more than an equal
+                // share and finish with the lighter ones instead of alone, latency-bound, after them (measured: the 32
+                // heaviest particles of a CTA end 3 us after the median warp instead of 8; +1.2 % on the filter;
+                // profiles/r02b_probe_nat_vs_rev.txt).  Without helper warps the last warp keeps the lightest chunk: it
+                // issues the exchange's fence.
                 const int nw = NT >> 5, main_w = P.split_main == -2 ? nw - 4 : nw;
                 const int nrev = (P.split_main == -2 || !PUSH) ? main_w : main_w - 1;
-#ifdef SEM_DEAL_NATURAL
-#define SEM_WR(w_) (w_)
-#else
-#define SEM_WR(w_) (nrev - 1 - (w_))
-#endif
                 int chunk;
                 if (warp < nrev) {
-                    const int wr = SEM_WR(warp), rnd = wr >> 2, r_last = (nrev - 1) >> 2;
+                    const int wr = nrev - 1 - warp, rnd = wr >> 2, r_last = (nrev - 1) >> 2;
                     chunk = 4 * rnd + ((((r_last - rnd) & 1) == 0) ? (wr & 3) : 3 - (wr & 3));   // (the last round is in natural order)
                 } else if (warp < main_w) {
                     chunk = main_w - 1;
@@ -929,6 +940,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         __syncthreads();                                     // keep the CTA in the SSA loop until its last warp is done: letting early
 #endif
         PHASE(4);                                            // warps run ahead into the weights code costs 27% (measured; profiles/)
+        CTA_T(0);
         if constexpr (kUnif) {
             if (active && via_smem) {
                 const int32_t *x_ret = (const int32_t *)(s_dyn + soff + 2 * blockDim.x) + Model::C * blockDim.x;
@@ -943,7 +955,8 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         if (p < P.T - 1) {
             ls = weigh_local<Model, PUSH>(P, p, f, b, tid, active, j, x, sm, s_tab);
             PHASE(19);
-            if constexpr (PUSH) xchg_publish(*Xp, Xp->gen0 + (unsigned)p, gb, tid, ls.mb, ls.sb);
+            CTA_T(1);
+            if constexpr (PUSH) xchg_publish(*Xp, fsh, Xp->gen0 + (unsigned)p, gb, tid, ls.mb, ls.sb);
         }
         PHASE(5);
     }
@@ -957,8 +970,8 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
     if constexpr (PUSH) {
         grid.sync();                                         // this rank's history, events and status are complete
         if (b == 0 && tid == 0) {
-            if (*(volatile int *)Xp->err) atomicExch(&P.status[0], SEM_ERR_PEER);
-            if (P.iter_out) xchg_iteration_epilogue<Model::C>(P, *Xp);
+            if (xchg_failed(*Xp, fsh)) atomicExch(&P.status[f], SEM_ERR_PEER);
+            if (P.iter_out) xchg_iteration_epilogue<Model::C>(P, *Xp, f, fsh);
         }
     } else if (P.iter_out) {                                 // path sample + packed result of the MH iteration
         grid.sync();

@@ -13,6 +13,17 @@ static int choose_ppb(const sem_pf_config *c) {
         const int lim = c->arith == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads;
         return c->block_particles > lim ? lim : c->block_particles;
     }
+    if (c->n_filters > 1) {
+        // several filters side by side: give each an equal share of the SMs so that all CTAs of all filters are
+        // co-resident (one launch for the whole batch); the occupancy query of the caller has the last word
+        const int cap = c->arith == SEM_ARITH_UNIFORMIZED ? kMaxThreadsUnif : kMaxThreads;
+        const int share = sm_count() / c->n_filters > 0 ? sm_count() / c->n_filters : 1;
+        long long ppb = (c->n_particles + share - 1) / share;
+        if (ppb < 32) ppb = 32;
+        if (ppb > cap) ppb = 256;                            // not co-resident anyway: 256-wide CTAs in waves
+        if (ppb > c->n_particles) ppb = c->n_particles;
+        return (int)ppb;
+    }
     const long long all = (long long)c->n_particles * c->n_filters;
     const long long per_sm = (all + sm_count() - 1) / sm_count();
     // co-resident population: ceil(N*F/SMs) particles per SM split over as few CTAs as the thread cap allows (threads =
@@ -83,7 +94,7 @@ static ArenaLayout arena_layout_nb(const sem_pf_config *cfg, int world, int nb_r
 static bool push_eligible(const sem_pf_config *c) {
     static int env_off = -1;
     if (env_off < 0) { const char *e = getenv("SEM_NO_PUSH"); env_off = (e && e[0] == '1') ? 1 : 0; }
-    return !env_off && c->n_filters == 1 && c->resampler == SEM_RESAMPLE_SYSTEMATIC && c->reserved == 0 && c->n_obs >= 2 &&
+    return !env_off && c->n_filters >= 1 && c->resampler == SEM_RESAMPLE_SYSTEMATIC && c->reserved == 0 && c->n_obs >= 2 &&
            (c->arith == SEM_ARITH_FAST32 || c->arith == SEM_ARITH_UNIFORMIZED32);
 }
 
@@ -102,7 +113,7 @@ static WsLayout ws_layout(const sem_pf_config *c) {
     w.counter = take(F * sizeof(unsigned int));
     w.wt_n = weight_table_n(c);
     w.wtab = take(w.wt_n ? (size_t)(c->n_obs - 1) * c->n_obs_cols * ((size_t)w.wt_n + 1) * sizeof(double) : 0);
-    w.xarena_bytes = push_eligible(c) ? arena_layout_nb(c, 1, w.nb).bytes : 0;
+    w.xarena_bytes = push_eligible(c) ? arena_layout_nb(c, 1, w.nb).bytes * (size_t)c->n_filters : 0;   // one arena per filter
     w.xarena = take(w.xarena_bytes);
     w.bytes = off;
     return w;
@@ -135,7 +146,7 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
     P.probs = cfg->probs; P.dt = cfg->dt;
     P.key = make_philox_key(cfg->seed); P.filter_id0 = cfg->filter_id0;
     for (int g = 0; g < SEM_MAX_GROUPS; g++) { P.mu[g] = cfg->mu[g]; P.npop[g] = cfg->n_population[g]; }
-    P.Y = buf->Y; P.theta = buf->theta; P.X0 = buf->X0;
+    P.Y = buf->Y; P.theta = buf->theta; P.X0 = buf->X0; P.probs_f = buf->probs_per_filter;
     P.res_u = buf->replay_resample_u; P.ssa_u = buf->replay_ssa_u; P.ssa_off = (const long long *)buf->replay_ssa_off;
     P.X_hist = buf->X_hist; P.ancestry = buf->ancestry; P.status = buf->status; P.log_zetas = buf->log_zetas;
     P.n_events = (unsigned long long *)buf->n_events;
@@ -145,7 +156,7 @@ static int fill_dev(const sem_pf_config *cfg, const sem_pf_buffers *buf, PfDev &
     }
     P.part = (double2 *)(ws + w.part); P.counter = (unsigned int *)(ws + w.counter);
     // the table covers counts up to the configured population: only valid when X_0 is drawn from it (pmcmc.py:156-169)
-    P.wt_n = (P.init_poisson && !replay) ? w.wt_n : 0;
+    P.wt_n = (P.init_poisson && !replay && !P.probs_f) ? w.wt_n : 0;
     P.wtab = P.wt_n ? (double *)(ws + w.wtab) : nullptr;
     P.j0 = 0; P.sharded = 0; P.X_in = nullptr; P.summary = nullptr; P.split_main = 0;
     P.iter_out = buf->iteration_result; P.path_exact = (int)cfg->path_exact;

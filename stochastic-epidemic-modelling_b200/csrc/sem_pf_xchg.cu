@@ -45,7 +45,7 @@ static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
     int rc = validate(cfg);
     if (rc) return rc;
     if (world < 1 || world > SEM_MAX_RANKS) { set_error("world must be 1..8"); return SEM_ERR_INVALID; }
-    if (cfg->n_filters != 1) { set_error("the sharded filter runs one filter (n_filters = 1)"); return SEM_ERR_INVALID; }
+    if (cfg->n_filters != 1 && world != 1) { set_error("the sharded filter runs one filter (n_filters = 1)"); return SEM_ERR_INVALID; }
     if (cfg->resampler != SEM_RESAMPLE_SYSTEMATIC) { set_error("the sharded filter resamples systematically"); return SEM_ERR_INVALID; }
     if (cfg->n_obs >= (1 << 20) - 1) { set_error("n_obs too large for the path-sampler token"); return SEM_ERR_INVALID; }
     if ((long long)cfg->n_particles * world > 0x7fffffffLL) { set_error("global particle count exceeds int32"); return SEM_ERR_INVALID; }
@@ -64,7 +64,7 @@ static int xchg_plan(const sem_pf_config *cfg, int world, XchgPlan &pl) {
     rc = persistent_prepare(pl.fn, pl.smem);
     if (rc) return rc;
     SEM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pl.fn, pl.threads, pl.smem));
-    if ((long long)per_sm * sm_count() < (long long)w.nb) {
+    if ((long long)per_sm * sm_count() < (long long)w.nb * cfg->n_filters) {
         set_error("this rank's particles are not co-resident on one GPU: use the host-driven exchange (sem_shard_*)");
         return SEM_ERR_INVALID;
     }
@@ -98,10 +98,11 @@ static int xchg_launch(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, co
         X.mail[r] = (unsigned long long *)(base + a.mail); X.iter[r] = (double *)(base + a.iter);
     }
     X.err = (int *)((char *)arenas[rank] + a.err);
+    X.filter_stride = a.bytes;
     if (world == 1 && P.iter_out) X.iter[0] = P.iter_out;    // one rank: the caller's own result buffer
     else P.iter_out = want_iter ? X.iter[rank] : nullptr;
     void *args[] = {(void *)&P, (void *)&X};
-    SEM_CUDA(cudaLaunchCooperativeKernel(pl.fn, dim3(w.nb, 1), dim3(pl.threads), args, pl.smem, s));
+    SEM_CUDA(cudaLaunchCooperativeKernel(pl.fn, dim3(w.nb, world == 1 ? cfg->n_filters : 1), dim3(pl.threads), args, pl.smem, s));
     return SEM_OK;
 }
 
@@ -126,7 +127,10 @@ int xchg_run_single(const sem_pf_config *cfg, PfDev &P, const WsLayout &w, void 
     if (!push_eligible(cfg) || !w.xarena_bytes) return SEM_OK;
     if (xchg_plan(cfg, 1, pl) != SEM_OK) { cudaGetLastError(); return SEM_OK; }
     const ArenaLayout a = arena_layout(cfg, 1);
-    int rc = arena_mark_empty(a, arena, s);                  // the workspace is scratch: empty marks per launch (a few MB of memset)
+    // the workspace is scratch: empty marks per launch, one arena per filter (all-ones everywhere; the error flag counts as
+    // set only when it is 1, and one rank never reads its mailbox)
+    int rc = SEM_OK;
+    SEM_CUDA(cudaMemsetAsync(arena, 0xFF, a.bytes * (size_t)cfg->n_filters, s));
     if (rc) return rc;
     void *arenas[1] = {arena};
     rc = xchg_launch(cfg, P, w, pl, a, 1, 0, arenas, 0u, 1u, 0.0, P.iter_out != nullptr, s);
@@ -237,6 +241,10 @@ int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_
 #ifdef SEM_PHASES
 int sem_debug_phases_x(unsigned long long *host_out) {
     SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 24 * 256));
+    return SEM_OK;
+}
+int sem_debug_cta_times_x(unsigned long long *host_out) {
+    SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_cta_t, sizeof(unsigned long long) * 2 * 128 * 160));
     return SEM_OK;
 }
 #endif

@@ -198,26 +198,35 @@ class PreparedIteration:
             self.dev_th = torch.empty((F, self.P), dtype=torch.float64, device=self.dev)
             self.dev_it = torch.empty((F, ITER_HEADER + T * self.Cn), dtype=torch.float64, device=self.dev)
             self.pin_it = torch.empty((F, ITER_HEADER + T * self.Cn), dtype=torch.float64).pin_memory()
+            self.pin_pr = torch.empty((F,), dtype=torch.float64).pin_memory()          # observation parameter per filter
+            self.dev_pr = torch.empty((F,), dtype=torch.float64, device=self.dev)
         X_hist, anc, logz, status, nev, ws = self.out
         self.buf = _lib.PfBuffers(Y=_ptr(self.Y), theta=_ptr(self.dev_th), X0=None, X_hist=_ptr(X_hist), ancestry=_ptr(anc),
                                   log_zetas=_ptr(logz), status=_ptr(status), n_events=_ptr(nev), workspace=_ptr(ws),
                                   iteration_result=_ptr(self.dev_it))
         self.th_host = self.pin_th.numpy()
         self.it_host = self.pin_it.numpy()
+        self.pr_host = self.pin_pr.numpy()
         self.launches = self.L.sem_pf_launch_count(C.byref(cfg))
 
     def run(self, theta, filter_id, probs=None, arith=None):
-        """Returns the pinned [F, ITER_HEADER + T*C] result (valid until the next run)."""
+        """Returns the pinned [F, ITER_HEADER + T*C] result (valid until the next run).  theta (F,P) or (P,); probs a
+        scalar, or one value per filter (a batch of proposals that also differ in the observation parameter)."""
         cfg = self.cfg
         cfg.filter_id0 = int(filter_id) & 0xFFFFFF
-        if probs is not None:
+        per_filter = probs is not None and np.ndim(probs) > 0
+        if probs is not None and not per_filter:
             cfg.probs = float(probs)
         if arith is not None:
             cfg.arith = int(arith)
         self.th_host[...] = theta
+        self.buf.probs_per_filter = _ptr(self.dev_pr) if per_filter else None
         stream = torch.cuda.current_stream(self.dev)
         with torch.cuda.stream(stream):
             self.dev_th.copy_(self.pin_th, non_blocking=True)
+            if per_filter:
+                self.pr_host[...] = probs
+                self.dev_pr.copy_(self.pin_pr, non_blocking=True)
             _lib.check(self.L.sem_pf_run(C.byref(cfg), C.byref(self.buf), C.c_void_p(stream.cuda_stream)), "sem_pf_run")
             self.pin_it.copy_(self.dev_it, non_blocking=True)
         stream.synchronize()

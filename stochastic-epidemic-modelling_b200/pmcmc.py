@@ -136,12 +136,20 @@ def particle_path_sampler(hidden_process, ancestry_matrix, *, exact_genealogy=Fa
 def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_chains=1000, observations=False,
                   probs=.1, n_particles=1000, n_population=4820, mu=20, jobs=4, *, resampler="systematic", seed=None,
                   arith="auto", exact_genealogy=False, return_log=False, progress=False, stats=None, sharded=False,
-                  group=None, exchange="auto"):
+                  group=None, exchange="auto", lookahead=1):
     """Particle marginal Metropolis-Hastings (pmcmc.py:251-408).
 
     Returns (thetas[n_chains,P], likelihoods[n_chains], sampled_trajs[T,n_chains,C]).  likelihoods are the linear
     zetas[-1] like the reference (log-likelihoods with return_log=True).  `stats`, if a dict, receives
     'filter_runs', 'acceptances', 'launches'.
+
+    lookahead = L > 1 (or "auto"): small filters leave most of the GPU idle and one iteration is pure latency (a filter of
+    10^3 particles takes as long as one of 3*10^4), so the next L proposals are evaluated in ONE launch (L filters with
+    their own theta and p_obs) under the assumption that the earlier ones are rejected -- after a rejection the chain has
+    not moved, so proposal k+1 is drawn from the same state, adaptive covariance included.  The first accepted
+    proposal ends the batch and the later evaluations are discarded (they are independent of everything kept), so the
+    chain has exactly the law of the sequential loop; with acceptance rate a a launch advances (1 - (1-a)^L) / a
+    iterations instead of one.  lookahead=1 is the sequential loop of the reference (same numpy draw order).
 
     sharded=True (every rank of an initialised torch.distributed group calls with the same arguments): ONE chain whose
     filter of n_particles (global count) is sharded over the ranks with global systematic resampling (BASELINE config 5;
@@ -162,6 +170,13 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     T = Y.shape[0]
     G = len(mu) if model >= 2 else 1
     Cn = engine.model_dims(model, G)[0]
+    if lookahead == "auto":                                   # fill the GPU's idle share, up to 16 proposals per launch
+        lookahead = int(max(1, min(16, 32768 // max(int(n_particles), 1))))
+    if int(lookahead) > 1:
+        return _particle_mcmc_lookahead(Y, type_model, parameters, h, adaptive, sigma, n_chains, observations, probs,
+                                        n_particles, n_population, mu, resampler=resampler, seed=seed, arith=arith,
+                                        exact_genealogy=exact_genealogy, return_log=return_log, stats=stats,
+                                        lookahead=int(lookahead))
     thetas = np.zeros((n_chains, n_par))
     loglik = np.zeros(n_chains)
     sampled_trajs = np.zeros((T, n_chains, Cn))                                  # pmcmc.py:269-272
@@ -229,6 +244,124 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
         if bar is not None:
             bar.update(1)
             bar.set_postfix_str(f"theta={thetas[i]}, logZ={loglik[i]:.3f}, acc={100 * counters['acceptances'] / (i + 1):.1f}%")
+    if isinstance(stats, dict):
+        stats.update(counters)
+    return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs
+
+
+def _particle_mcmc_lookahead(Y, type_model, parameters, h, adaptive, sigma, n_chains, observations, probs, n_particles,
+                             n_population, mu, *, resampler, seed, arith, exact_genealogy, return_log, stats, lookahead):
+    """particle_mcmc with `lookahead` proposals per launch (see particle_mcmc): pmcmc.py:276-403 with the filter calls of
+    consecutive iterations batched under the rejection assumption."""
+    dev = engine.require_cuda()
+    model = _model_id(type_model)
+    n_par = len(parameters)
+    T = Y.shape[0]
+    G = len(mu) if model >= 2 else 1
+    Cn = engine.model_dims(model, G)[0]
+    L = int(lookahead)
+    thetas = np.zeros((n_chains, n_par))
+    loglik = np.zeros(n_chains)
+    sampled_trajs = np.zeros((T, n_chains, Cn))
+    std = np.eye(n_par) if sigma is None else sigma
+    seed = engine.new_seed() if seed is None else seed
+    counters = dict(filter_runs=0, acceptances=1, launches=0, lookahead=L, discarded=0)
+    th0, pr0 = _split(model, G, np.asarray(parameters, dtype=float), probs)
+    th0 = _flatten_theta(model, th0)
+    while True:                                               # the whole batch must be ONE launch (all filters co-resident)
+        cfg0 = engine.make_pf_config(model, n_particles, T, G=G, n_filters=L, observations=observations, probs=.5,
+                                     resampler=resampler, arith=engine.resolve_arith(model, arith, theta=th0), seed=seed,
+                                     mu=np.atleast_1d(mu), n_population=np.atleast_1d(n_population), path_exact=exact_genealogy)
+        if Y.shape[1] != cfg0.n_obs_cols:
+            raise ValueError(f"Y has {Y.shape[1]} columns, the model observes {cfg0.n_obs_cols}")
+        if L == 1 or engine._lib.load().sem_pf_launch_count(engine.C.byref(cfg0)) == 1:
+            break
+        L = max(1, L // 2)
+    counters["lookahead"] = L
+    prep = engine.PreparedIteration(cfg0, Y, dev)
+    n_th = th0.size                                           # model parameters (the optional trailing p_obs excluded)
+    th_batch = np.tile(th0, (L, 1))
+    pr_batch = np.full(L, .5 if pr0 is None else float(pr0))
+    state = dict(it=0)
+
+    def run_batch(props, theta_ref):
+        """Filters for the non-negative proposals of the batch (the others are rejected without a run, pmcmc.py:333).
+        props (n, n_par).  Returns (ok[n], loglik[n], packed results) -- host work is vectorised: with 10^3 particles a
+        launch takes 0.57 ms and every 40 us of Python per proposal would show."""
+        n = len(props)
+        live = ~np.any(props < 0, axis=1)
+        th_batch[:] = theta_ref[:n_th]                        # idle slots re-run the current state (ignored)
+        th_batch[:n][live] = props[live][:, :n_th]            # (beta[G,G] row-major, gamma) is the vector itself, pmcmc.py:289-296
+        if probs is None:
+            pr_batch[:] = min(max(theta_ref[-1], 0), 1)
+            pr_batch[:n][live] = np.clip(props[live][:, -1], 0, 1)                # :313-314
+        if not live.any():
+            return live, np.zeros(n), None
+        first = int(np.argmax(live))
+        r = prep.run(th_batch, state["it"], probs=pr_batch, arith=engine.resolve_arith(model, arith, theta=th_batch[first]))
+        state["it"] += L
+        counters["filter_runs"] += int(live.sum())
+        counters["launches"] += prep.launches + (0 if prep.launches == 1 else 1)
+        ok = live & (r[:n, 1] == 0)                            # collapsed filters count as rejections (:365-369)
+        return ok, r[:n, 0], r
+
+    def finish_theta(theta_vec):
+        if probs is None:
+            out_t = np.array(theta_vec, dtype=float)
+            out_t[-1] = max(min(out_t[-1], 1), 0)
+            return out_t
+        return theta_vec
+
+    def proposals(mean, cov, n):
+        """n draws of N(mean, cov) (pmcmc.py:330) -- one factorisation, one call for the standard normals"""
+        w, v = np.linalg.eigh(np.asarray(cov, dtype=float))
+        return mean + (np.random.standard_normal((n, n_par)) * np.sqrt(np.maximum(w, 0))) @ v.T
+
+    start = np.array(parameters, dtype=float)
+    done = False
+    while not done:                                                               # pmcmc.py:276-310 initial draw
+        props = proposals(start, h * std, L)
+        ok, lz, r = run_batch(props, start)
+        if ok.any():
+            k = int(np.argmax(ok))
+            thetas[0] = finish_theta(props[k]); loglik[0] = lz[k]
+            sampled_trajs[:, 0, :] = r[k, engine.ITER_HEADER:].reshape(T, Cn)
+            counters["discarded"] += L - 1 - k
+            done = True
+
+    # running sums of the chain for the adaptive covariance (:327-328) under the rejection assumption: iterations
+    # i .. i+k-1 repeat thetas[i-1], so cov(thetas[:i+k]) follows from the sums over thetas[:i] in O(P^2)
+    s1 = thetas[0].copy(); s2 = np.outer(thetas[0], thetas[0])
+    i = 1
+    while i < n_chains:                                                           # pmcmc.py:325-403
+        n = min(L, n_chains - i)
+        cur = thetas[i - 1]
+        if adaptive and i + n - 1 > 1e3:
+            props = np.empty((n, n_par))
+            for k in range(n):                                                    # iteration i + k, if i .. i+k-1 all reject
+                if i + k > 1e3:
+                    m = (s1 + k * cur) / (i + k)
+                    std = (s2 + k * np.outer(cur, cur)) / (i + k) - np.outer(m, m) + 1e-4 * np.eye(n_par)
+                props[k] = proposals(cur, h * std, 1)[0]
+        else:
+            props = proposals(cur, h * std, n)
+        us = np.random.uniform(size=n)
+        ok, lz, r = run_batch(props, cur)
+        acc = ok & (np.log(us) < lz - loglik[i - 1])                              # :376-395, see D4
+        k_acc = int(np.argmax(acc)) if acc.any() else n
+        nrej = min(k_acc, n)
+        if nrej:                                                                  # rejections: the chain stays
+            thetas[i:i + nrej] = cur; loglik[i:i + nrej] = loglik[i - 1]
+            sampled_trajs[:, i:i + nrej, :] = sampled_trajs[:, i - 1:i, :]
+            s1 += nrej * cur; s2 += nrej * np.outer(cur, cur)
+            i += nrej
+        if k_acc < n:
+            counters["acceptances"] += 1
+            thetas[i] = finish_theta(props[k_acc]); loglik[i] = lz[k_acc]
+            sampled_trajs[:, i, :] = r[k_acc, engine.ITER_HEADER:].reshape(T, Cn)
+            s1 += thetas[i]; s2 += np.outer(thetas[i], thetas[i])
+            i += 1
+            counters["discarded"] += n - 1 - k_acc
     if isinstance(stats, dict):
         stats.update(counters)
     return thetas, (loglik if return_log else np.exp(loglik)), sampled_trajs

@@ -37,7 +37,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(L, name), f"{name} declared in include/sem_b200.h but not exported"
     assert set(_lib.EXPORTS) == declared
-    assert _lib.load().sem_abi_version() == 1
+    assert _lib.load().sem_abi_version() == 2
 
 
 def test_struct_layouts_match_header():

@@ -711,6 +711,59 @@ def test_pmcmc_posterior_vs_reference_slow_growth(sem):
     assert acc_our > acc_ref - 0.05, (acc_ref, acc_our)        # systematic resampling: no noisier a likelihood, no fewer acceptances
 
 
+def test_pmcmc_lookahead_posterior_vs_reference(sem):
+    """particle_mcmc(lookahead=8): eight proposals per launch under the rejection assumption.  The chain
+    has the law of the sequential loop: posterior means and 95 % HDI endpoints agree with four chains of the unmodified
+    reference within Monte-Carlo error, the acceptance rate is the sequential one, and a launch advances the chain by
+    more than two iterations on average."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "stat_pmcmc_sir_slow.npz")):
+        pytest.skip("reference PMCMC chains (slow growth) not generated")
+    g = golden("stat_pmcmc_sir_slow")
+    burn = 400
+    ref = g["thetas"][:, burn:]
+    ours, stats_all = [], []
+    for c in range(4):
+        np.random.seed(300 + c)
+        st = {}
+        th, lik, traj = sem.particle_mcmc(g["Y"], sem.ModelType.SIR, list(g["parameters"]), float(g["h"]), n_chains=6000,
+                                          probs=float(g["probs"]), n_particles=int(g["n_particles"]),
+                                          n_population=int(g["n_population"]), mu=float(g["mu"]), seed=700 + c, lookahead=8, stats=st)
+        assert np.all(np.isfinite(th)) and np.all(np.isfinite(lik)) and np.all(traj >= 0)
+        ours.append(th[burn:]); stats_all.append(st)
+    ours = np.stack(ours)
+    hdi = sem.helpers.hdi
+    for k in range(2):
+        stat_ref = np.array([[c[:, k].mean(), *hdi(c[:, k], .95)] for c in ref])
+        stat_our = np.array([[c[:, k].mean(), *hdi(c[:, k], .95)] for c in ours])
+        for q, name in enumerate(("mean", "hdi_lo", "hdi_hi")):
+            se = np.sqrt(stat_ref[:, q].var(ddof=1) / len(stat_ref) + stat_our[:, q].var(ddof=1) / len(stat_our))
+            diff = abs(stat_ref[:, q].mean() - stat_our[:, q].mean())
+            assert diff < 4.5 * se + 0.004, (k, name, stat_ref[:, q], stat_our[:, q], se)
+    acc_ref = np.mean([sem.helpers.acceptance_rate(c) for c in g["thetas"]])
+    acc_our = np.mean([sem.helpers.acceptance_rate(c) for c in ours])
+    assert abs(acc_our - acc_ref) < 0.08, (acc_ref, acc_our)
+    for st in stats_all:
+        assert st["lookahead"] == 8 and st["launches"] < 0.7 * 6000, st    # (acceptance ~0.55 here: ~1.8 iterations per launch)
+
+
+def test_pmcmc_lookahead_with_p_obs_and_adaptive(sem):
+    """lookahead with the estimated observation probability (one p_obs per filter of the batch) and the adaptive
+    covariance computed under the rejection assumption: same invariants as the sequential loop."""
+    import workloads
+    Y = workloads.observe_binomial(workloads.sir_truth((980, 20, 0), 12, 2.0, 1.0), .3, seed=4)
+    np.random.seed(5)
+    st = {}
+    th, lik, traj = sem.particle_mcmc(Y, sem.ModelType.SIR, [2.0, 1.0, .3], 1e-3, adaptive=True, n_chains=1300, probs=None,
+                                      n_particles=400, n_population=1000, mu=20, seed=9, lookahead="auto", stats=st)
+    assert th.shape == (1300, 3) and np.all((th[:, 2] >= 0) & (th[:, 2] <= 1)) and np.all(th[:, :2] > 0)
+    assert np.all(np.isfinite(lik)) and np.all(lik > 0)
+    assert np.all(traj.sum(axis=2) == 1000)                        # every sampled trajectory conserves the population
+    assert st["lookahead"] == 16 and st["acceptances"] > 20
+    assert 0.05 < np.mean(th[300:, 2]) < 0.9
+
+
 @pytest.mark.parametrize("x0", [(8000, 500, 1500), (9990, 3, 7), (3000, 1500, 5500)])
 def test_uniformized_end_state_law_vs_direct_method(sem, x0):
     """Law of the state at the END of one observation interval, headline theta / population 1e4: 1.2e6 propagations of

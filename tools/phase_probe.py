@@ -78,3 +78,23 @@ for k, nm in enumerate(names):
 step = (t[1:, 0] - t[:-1, 0])
 print("  step-to-step            mean %.2f  total %.2f ms" % (step.mean(), step.sum() / 1e3))
 pf.close()
+
+# ---- per-CTA view: when each CTA left its SSA phase / published its partial (globaltimer, ns), steps 1..100 of the last launch
+if hasattr(L, "sem_debug_cta_times_x"):
+    L.sem_debug_cta_times_x.argtypes = [C.c_void_p]
+    ct = np.zeros(2 * 128 * 160, dtype=np.uint64)
+    assert L.sem_debug_cta_times_x(ct.ctypes.data_as(C.c_void_p)) == 0
+    ct = ct.reshape(2, 128, 160).astype(np.int64)
+    nbk = int((ct[0, 5] > 0).sum())
+    e = ct[0, 1:100, :nbk] / 1e3; pub = ct[1, 1:99, :nbk] / 1e3
+    dur = e[1:] - pub[:-1].max(axis=1, keepdims=True) if False else None
+    print(f"per-CTA end of the SSA phase over {nbk} CTAs (us, per step): max - median mean {np.mean(e.max(1) - np.median(e, 1)):.2f}, "
+          f"max - min mean {np.mean(e.max(1) - e.min(1)):.2f}, std mean {np.mean(e.std(1)):.2f}")
+    last = np.bincount(e.argmax(1), minlength=nbk)
+    print("  CTAs most often last:", [(int(i), int(last[i])) for i in np.argsort(-last)[:8]])
+    rel = e - np.median(e, 1, keepdims=True)
+    m = rel.mean(0)
+    print("  mean lateness vs the step's median, by CTA: min %.2f  max %.2f  (CTAs %s)" % (m.min(), m.max(), np.argsort(-m)[:6].tolist()))
+    for p in (10, 28, 44, 60):
+        r = np.sort(rel[p])
+        print(f"  step {p + 1}: lateness quantiles 0/25/50/75/90/99/100 %: " + " ".join(f"{np.quantile(r, q):6.2f}" for q in (0, .25, .5, .75, .9, .99, 1)))

@@ -12,6 +12,15 @@ for N in (1000, 10000):
     sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, [2.0, 1.0], 1e-4, n_chains=400, probs=.1, n_particles=N, n_population=1000, mu=20, seed=2, stats=st)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     print(f"N={N}: {1e3*dt/st['filter_runs']:.3f} ms per PMCMC iteration ({st['filter_runs']} filter runs), {N*14*st['filter_runs']/dt/1e6:.2f} M particle-steps/s")
+    for L, hh in [(1, 1e-2), (4, 1e-2), (8, 1e-2), (16, 1e-2), (1, 6e-2), (8, 6e-2), (16, 6e-2)]:
+        st = {}
+        np.random.seed(0)
+        sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, [2.0, 1.0], hh, n_chains=40, probs=.1, n_particles=N, n_population=1000, mu=20, seed=1, lookahead=L)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        th, _, _ = sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, [2.0, 1.0], hh, n_chains=2000, probs=.1, n_particles=N, n_population=1000, mu=20, seed=2, stats=st, lookahead=L)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(f"   h={hh:g} lookahead {L:2d} (used {st.get('lookahead', 1)}): {1e3*dt/2000:.3f} ms per PMCMC iteration ({2000/dt:.0f} iterations/s; {st['launches']} launches for 2000 iterations, "
+              f"acceptance {sem_b200.helpers.acceptance_rate(th):.2f}, {1e3*dt/st['launches']:.3f} ms per launch)")
     cfg = sem_b200.engine.make_pf_config(0, N, 15, probs=.1, seed=3, mu=[20], n_population=[1000])
     out = sem_b200.engine.alloc_pf_outputs(cfg)
     Yd = torch.from_numpy(Y).cuda(); th = torch.tensor([2.0, 1.0], dtype=torch.float64).cuda()
