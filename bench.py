@@ -517,7 +517,7 @@ def main():
     if not args.no_e2e:
         np.random.seed(rank)
         st = {}
-        n_it = max(8, min(K, 40))                                        # MH iterations in the timed call (its setup is inside)
+        n_it = max(8, min(4 * K, 120))                                   # MH iterations in the timed call (its one-time setup is inside)
         shard_kw = dict(sharded=True) if world > 1 else {}
         sem_b200.particle_mcmc(Y, sem_b200.ModelType.SIR, list(theta), 1e-6, n_chains=3, probs=w["probs"], n_particles=world * N,
                                n_population=w["n_population"], mu=w["mu"], seed=77, **shard_kw)          # warm-up

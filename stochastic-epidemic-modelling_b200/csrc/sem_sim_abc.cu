@@ -131,16 +131,20 @@ struct AbcDev {
     unsigned long long *n_events, *work;
 };
 
-constexpr int kAbcMaxDays = 128;
+constexpr int kAbcSmemDays = 2048;        // observed series up to this length are staged in shared memory (32 KB); longer ones are read from L2
 
 template <int ARITH, bool REPLAY>
 __global__ void __launch_bounds__(128) abc_kernel(const __grid_constant__ AbcDev P) {
-    __shared__ double s_obs[kAbcMaxDays * 2];                            // (I_obs, R_obs) per day
+    extern __shared__ double s_obs_dyn[];                                // (I_obs, R_obs) per day, when the series fits
     __shared__ double2 s_tab[kLogTabSize];
     constexpr bool FAST = (ARITH == SEM_ARITH_FAST || ARITH == SEM_ARITH_FAST32) && !REPLAY;
     constexpr bool BITS32 = FAST && ARITH == SEM_ARITH_FAST32;           // two events per Philox call
     if (FAST) load_logtab(s_tab);
-    for (int i = threadIdx.x; i < P.T; i += blockDim.x) { s_obs[2 * i] = P.obs[3 * i + 1]; s_obs[2 * i + 1] = P.obs[3 * i + 2]; }
+    const bool obs_smem = P.T <= kAbcSmemDays;
+    if (obs_smem) for (int i = threadIdx.x; i < P.T; i += blockDim.x) { s_obs_dyn[2 * i] = P.obs[3 * i + 1]; s_obs_dyn[2 * i + 1] = P.obs[3 * i + 2]; }
+    // (the reference has no limit on the length of the observed series, abc_algo.py:58-99)
+    const double *obs_ir = obs_smem ? s_obs_dyn : P.obs + 1;             // element (day, c) at obs_ir[stride * day + c]
+    const int obs_stride = obs_smem ? 2 : 3;
     __syncthreads();
     const int T = P.T;
     const double t_stop = (double)(T - 1);                               // rows 0..T-1 are the states at integer times (abc_algo.py:58-93)
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(128) abc_kernel(const __grid_constant__ AbcDev
             int32_t *tr = P.traj + ((size_t)slot * T + day) * 3;                                       \
             tr[0] = (int32_t)x[0]; tr[1] = (int32_t)x[1]; tr[2] = (int32_t)x[2];                       \
         }                                                                                              \
-        sI += fabs(x[1] - s_obs[2 * day]); sR += fabs(x[2] - s_obs[2 * day + 1]);                      \
+        sI += fabs(x[1] - obs_ir[obs_stride * day]); sR += fabs(x[2] - obs_ir[obs_stride * day + 1]);  \
         day++;                                                                                         \
     } while (0)
 
@@ -320,7 +324,7 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
                 const int64_t *n_start_in, const double *replay_u, const int64_t *replay_off, double *theta_out,
                 double *distance, int32_t *traj, uint64_t *n_events, uint64_t *work_counter, void *stream) {
     if (!cfg || !obs || !theta_out || !distance || !work_counter) { set_error("bad abc args"); return SEM_ERR_INVALID; }
-    if (cfg->n_days < 1 || cfg->n_days > kAbcMaxDays) { set_error("n_days must be 1..128"); return SEM_ERR_INVALID; }
+    if (cfg->n_days < 1) { set_error("n_days must be >= 1"); return SEM_ERR_INVALID; }
     if (cfg->n_trials < 1) { set_error("n_trials must be >= 1"); return SEM_ERR_INVALID; }
     const bool replay = replay_u != nullptr;
     if (replay && (!theta_in || !n_start_in || !replay_off)) { set_error("replay needs theta_in, n_start_in, replay_off"); return SEM_ERR_INVALID; }
@@ -342,12 +346,13 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
                      : (cfg->arith == SEM_ARITH_FAST32 || cfg->arith == SEM_ARITH_UNIFORMIZED32) ? (const void *)abc_kernel<SEM_ARITH_FAST32, false>
                                                       : (const void *)abc_kernel<SEM_ARITH_FAST, false>;   // (UNIFORMIZED: the ABC loop needs event times)
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, 0) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
+    const size_t smem = cfg->n_days <= kAbcSmemDays ? (size_t)cfg->n_days * 2 * sizeof(double) : 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 4; }
     const long long want = (cfg->n_trials + threads - 1) / threads;
     const long long cap = (long long)sm_count() * per_sm;                // persistent lanes: every CTA resident, no second wave
     const int blocks = (int)(want < cap ? want : cap);
     void *args[] = {(void *)&P};
-    SEM_CUDA(cudaLaunchKernel(fn, dim3(blocks), dim3(threads), args, 0, s));
+    SEM_CUDA(cudaLaunchKernel(fn, dim3(blocks), dim3(threads), args, smem, s));
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }

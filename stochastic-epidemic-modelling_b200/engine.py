@@ -19,13 +19,15 @@ ARITH_NAMES = {v: k for k, v in ARITH.items()}
 
 
 AUTO_MAX_GROWTH = 0.5    # per observation interval; measured crossover between the two interval simulations
+AUTO_SMALL_FILTER = 20000   # particles (all filters of a launch) below which a step is latency-bound (profiles/r02f_arith_sweep.txt)
 
 
-def resolve_arith(model, arith, theta=None, dt=1.0):
+def resolve_arith(model, arith, theta=None, dt=1.0, n_particles=None):
     """'auto' (the filters' default) = the faster exact interval simulation for the model family and dynamics:
-    uniformized intervals with 32-bit candidates for SIR / SEIR (2-3 reactions) -- unless the epidemic's early growth per
+    uniformized intervals with 32-bit candidates for SIR / SEIR (2-3 reactions) -- unless the filter is small (a step is
+    then bound by the latency of one particle's chain, n_particles when known) AND the epidemic's early growth per
     observation interval (from theta, when it is known on the host) is so fast that an interval needs many short
-    batches -- and the direct method with 32-bit streams otherwise: for the subgroup models (their G^2+G propensities
+    batches, each with its own set-up latency -- and the direct method with 32-bit streams otherwise: for the subgroup models (their G^2+G propensities
     make a uniformized candidate as dear as a direct event), for ABC and for simulations that log event times."""
     if arith == "auto":            # (model None: simulations with event logs and ABC trials need event times -> direct method)
         if model not in (0, 1):
@@ -38,7 +40,7 @@ def resolve_arith(model, arith, theta=None, dt=1.0):
                 growth = 0.5 * (np.sqrt((th[1] - th[2]) ** 2 + 4 * th[1] * th[0]) - (th[1] + th[2])) * dt
             else:
                 growth = 0.0
-            if growth > AUTO_MAX_GROWTH:
+            if growth > AUTO_MAX_GROWTH and (n_particles is None or n_particles < AUTO_SMALL_FILTER):
                 return ARITH["fast32"]
         return ARITH["uniformized32"]
     return ARITH.get(arith, arith)
@@ -115,7 +117,7 @@ def make_pf_config(model, N, T, G=1, n_filters=1, observations=False, probs=.1, 
                    launch_per_step=False, path_exact=False, grid_barrier=False, theta=None):
     Cn, P, Cobs = model_dims(model, G)
     cfg = _lib.PfConfig(model=model, obs_kind=int(bool(observations)), resampler=RESAMPLERS.get(resampler, resampler),
-                        arith=resolve_arith(model, arith, theta=theta), n_particles=int(N), n_obs=int(T), n_groups=int(G),
+                        arith=resolve_arith(model, arith, theta=theta, n_particles=int(N) * int(n_filters)), n_particles=int(N), n_obs=int(T), n_groups=int(G),
                         n_obs_cols=Cobs, n_filters=int(n_filters), block_particles=int(block_particles),
                         store_history=int(bool(store_history)), reserved=1 if launch_per_step else 2 if grid_barrier else 0, probs=float(probs),
                         dt=float(dt), path_exact=int(bool(path_exact)),

@@ -57,7 +57,7 @@ def _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_po
         raise ValueError("Y must be (T, columns)")
     G = len(mu) if model >= 2 else 1
     theta = _flatten_theta(model, theta_proposal)
-    arith = engine.resolve_arith(model, arith, theta=theta)                  # 'auto' looks at the dynamics too
+    arith = engine.resolve_arith(model, arith, theta=theta, n_particles=n_particles)   # 'auto' looks at the dynamics and the size
     cfg = engine.make_pf_config(model, n_particles, Y.shape[0], G=G, observations=observations, probs=probs,
                                 resampler=resampler, arith=arith, seed=seed, filter_id0=filter_id,
                                 mu=np.atleast_1d(mu), n_population=np.atleast_1d(n_population),
@@ -195,7 +195,7 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     def run_filter(theta_vec, it):
         theta2, probs2 = _split(model, G, theta_vec, probs)
         th = _flatten_theta(model, theta2)
-        r = prep.run(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th))[0]
+        r = prep.run(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th, n_particles=n_particles))[0]
         counters["filter_runs"] += 1
         counters["launches"] += prep.launches + (0 if prep.launches == 1 else 1)
         if int(r[1]) != 0:
@@ -270,7 +270,7 @@ def _particle_mcmc_lookahead(Y, type_model, parameters, h, adaptive, sigma, n_ch
     th0 = _flatten_theta(model, th0)
     while True:                                               # the whole batch must be ONE launch (all filters co-resident)
         cfg0 = engine.make_pf_config(model, n_particles, T, G=G, n_filters=L, observations=observations, probs=.5,
-                                     resampler=resampler, arith=engine.resolve_arith(model, arith, theta=th0), seed=seed,
+                                     resampler=resampler, arith=engine.resolve_arith(model, arith, theta=th0, n_particles=n_particles * L), seed=seed,
                                      mu=np.atleast_1d(mu), n_population=np.atleast_1d(n_population), path_exact=exact_genealogy)
         if Y.shape[1] != cfg0.n_obs_cols:
             raise ValueError(f"Y has {Y.shape[1]} columns, the model observes {cfg0.n_obs_cols}")
@@ -298,7 +298,7 @@ def _particle_mcmc_lookahead(Y, type_model, parameters, h, adaptive, sigma, n_ch
         if not live.any():
             return live, np.zeros(n), None
         first = int(np.argmax(live))
-        r = prep.run(th_batch, state["it"], probs=pr_batch, arith=engine.resolve_arith(model, arith, theta=th_batch[first]))
+        r = prep.run(th_batch, state["it"], probs=pr_batch, arith=engine.resolve_arith(model, arith, theta=th_batch[first], n_particles=n_particles * L))
         state["it"] += L
         counters["filter_runs"] += int(live.sum())
         counters["launches"] += prep.launches + (0 if prep.launches == 1 else 1)
@@ -397,7 +397,7 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
               n_population=np.atleast_1d(n_population))
     n_local = n_particles // world
     if exchange == "auto":
-        exchange = "device" if sh.device_exchange_supported(model, n_local, T, world, arith=engine.resolve_arith(model, arith, theta=th0),
+        exchange = "device" if sh.device_exchange_supported(model, n_local, T, world, arith=engine.resolve_arith(model, arith, theta=th0, n_particles=n_local),
                                                             **kw) else "host"
     counters["exchange"] = exchange
     pf = None
@@ -409,7 +409,7 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
         th = _flatten_theta(model, theta2)
         counters["filter_runs"] += 1
         if pf is not None:
-            r = pf.iteration(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th))
+            r = pf.iteration(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th, n_particles=n_local))
             counters["launches"] += 1
             if int(r[1]) != 0:                               # same status on every rank: clean the arenas together
                 if int(r[1]) == engine._lib.ERR_PEER:

@@ -318,7 +318,7 @@ class PeerFilter:
         Y = np.ascontiguousarray(Y, dtype=np.float64)
         self.T = Y.shape[0]
         self.cfg = engine.make_pf_config(model, self.n_local, self.T, G=G, observations=observations, probs=probs,
-                                         resampler="systematic", arith=engine.resolve_arith(model, arith, theta=theta),
+                                         resampler="systematic", arith=engine.resolve_arith(model, arith, theta=theta, n_particles=self.n_local),
                                          seed=seed, mu=mu, n_population=n_population, store_history=store_history,
                                          block_particles=block_particles, path_exact=path_exact)
         with torch.cuda.device(self.dev):
@@ -456,7 +456,7 @@ def cached_peer_filter(group, rank, world, model, Y, n_local, *, G=1, observatio
         pf.Y.copy_(torch.from_numpy(Y))
         pf.cfg.seed = int(seed) & (2**64 - 1)
         pf.cfg.probs = float(probs)
-        pf.cfg.arith = engine.resolve_arith(model, arith, theta=theta)
+        pf.cfg.arith = engine.resolve_arith(model, arith, theta=theta, n_particles=n_local)
     return pf
 
 

@@ -424,6 +424,8 @@ def test_auto_interval_simulation_choice():
     assert engine.resolve_arith(0, "auto") == A["uniformized32"] and engine.resolve_arith(1, "auto") == A["uniformized32"]
     assert engine.resolve_arith(0, "auto", theta=[.4, .2]) == A["uniformized32"]          # the BASELINE workload
     assert engine.resolve_arith(0, "auto", theta=[2.0, 1.0]) == A["fast32"]               # growth 1 per interval
+    assert engine.resolve_arith(0, "auto", theta=[2.0, 1.0], n_particles=1000) == A["fast32"]       # ... and a latency-bound filter
+    assert engine.resolve_arith(0, "auto", theta=[2.0, 1.0], n_particles=10**5) == A["uniformized32"]   # a full GPU: throughput decides
     assert engine.resolve_arith(1, "auto", theta=[.4, .1, .1]) == A["uniformized32"]
     assert engine.resolve_arith(1, "auto", theta=[4.0, 1.0, 1.0]) == A["fast32"]
     assert engine.resolve_arith(2, "auto") == engine.resolve_arith(3, "auto", theta=[5, 2, 1, 3, .5]) == A["fast32"]

@@ -386,6 +386,22 @@ def test_abc_philox_vs_oracle(sem, c_oracle, arith):
     assert int(er["n_events"].cpu()[0]) < ref["n_events"]
 
 
+@pytest.mark.parametrize("T", [200, 2500])
+def test_abc_long_observed_series_vs_oracle(sem, c_oracle, T):
+    """The reference puts no limit on the length of the observed series (abc_algo.py:58-99): 200 days (staged in shared
+    memory) and 2500 days (read from L2) against the oracle."""
+    import workloads
+    truth = workloads.sir_truth((990, 10, 0), T, .12, .05)
+    obs = truth.astype(int).astype(float)                         # rows (S, I, R); the trial starts from Poisson(obs[0]) (abc_algo.py:39-40)
+    n = 400
+    thr = 60.0
+    out = sem.engine.abc_trials(obs, n, thr, [0, .5, 0, .5], seed=5, trial0=10, arith=3, want_traj=True)
+    ref = c_oracle.abc_trials(obs, n, thr, (0, .5, 0, .5), arith=3, seed=5, trial0=10)
+    assert np.array_equal(out["theta"].cpu().numpy(), ref["theta"])
+    assert np.array_equal(out["traj"].cpu().numpy(), ref["traj"])
+    np.testing.assert_allclose(out["distance"].cpu().numpy(), ref["distance"], rtol=1e-13)
+
+
 def test_abc_algo_dropin(sem, c_oracle):
     g = golden("abc_sir_small")
     obs = g["observed"]

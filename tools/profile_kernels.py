@@ -48,6 +48,9 @@ def pf_case(tag, kernel, model, G, theta, T, N, Y, mu, npop, observations=False,
 
 w = workloads.HEADLINE
 Yh = workloads.headline_Y()
+if os.environ.get("SEM_PROFILE_ONLY") == "headline_sir":     # (the full ncu capture of the headline kernel: nothing else to replay)
+    pf_case("headline_sir", "pf_persistent_x<sem::SirModel, 4>", 0, 1, list(w["theta"]), w["T"], w["n_particles"], Yh, [w["mu"]], [w["n_population"]])
+    sys.exit(0)
 pf_case("headline_sir", "pf_persistent_x<sem::SirModel, 4>", 0, 1, list(w["theta"]), w["T"], w["n_particles"], Yh, [w["mu"]], [w["n_population"]])
 pf_case("headline_sir_grid_barrier", "pf_persistent<sem::SirModel, 4>", 0, 1, list(w["theta"]), w["T"], w["n_particles"], Yh, [w["mu"]],
         [w["n_population"]], grid_barrier=True)
