@@ -140,6 +140,12 @@ size_t sem_pf_ancestry_elems(const sem_pf_config *cfg);
 /* launches made by one sem_pf_run (for launch accounting) */
 int sem_pf_launch_count(const sem_pf_config *cfg);
 int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream);
+/* One Metropolis-Hastings iteration's device work in one call (pmcmc.py:354-371, for a batch of n_filters proposals):
+ * copies theta_host [n_filters][P] (and probs_host [n_filters], or NULL) from pinned host memory into buf->theta
+ * (buf->probs_per_filter), runs sem_pf_run with buf->iteration_result, and copies the packed results to result_host
+ * [n_filters][SEM_ITER_HEADER + T*C].  Everything is enqueued on `stream`; the caller synchronises. */
+int sem_pf_iteration(const sem_pf_config *cfg, const sem_pf_buffers *buf, const double *theta_host, const double *probs_host,
+                     double *result_host, void *stream);
 
 /* Host-buffer variant (end-to-end call): Y, theta, X0 (may be NULL) and all outputs are HOST pointers;
  * outputs may be NULL when not wanted.  X_hist_out is (T,N,C) float64 and ancestry_out (T,N) float64 exactly

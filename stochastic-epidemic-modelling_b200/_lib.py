@@ -20,7 +20,7 @@ SEM_MAX_RANKS = 8
 EXPORTS = [
     "sem_abi_version", "sem_last_error", "sem_device_info", "sem_host_workspace_release",
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
-    "sem_pf_run", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
+    "sem_pf_run", "sem_pf_iteration", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
     "sem_ssa_simulate", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
     "sem_xchg_bytes", "sem_xchg_alloc", "sem_xchg_open", "sem_xchg_close", "sem_xchg_free", "sem_peer_enable",
     "sem_xchg_reset", "sem_xchg_iteration_result", "sem_pf_sharded_supported", "sem_pf_run_sharded",
@@ -105,6 +105,8 @@ def load():
     L.sem_pf_launch_count.argtypes = [C.POINTER(PfConfig)]
     L.sem_pf_run.restype = C.c_int
     L.sem_pf_run.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p]
+    L.sem_pf_iteration.restype = C.c_int
+    L.sem_pf_iteration.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     L.sem_pf_run_host.restype = C.c_int
     L.sem_pf_run_host.argtypes = [C.POINTER(PfConfig)] + [C.c_void_p] * 8
     L.sem_shard_init.restype = C.c_int

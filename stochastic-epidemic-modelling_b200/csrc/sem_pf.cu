@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(kMaxThreads) pf_init(const __grid_constant__ P
 
 template <int C>
 __global__ void iteration_epilogue_kernel(const __grid_constant__ PfDev P) {
-    if (threadIdx.x == 0) iteration_epilogue<C>(P, blockIdx.x);
+    iteration_epilogue<C>(P, blockIdx.x);                   // (one warp per filter)
 }
 
 // Step p >= 1: resample, gather, propagate, store, weigh (see the file header).
@@ -363,6 +363,27 @@ int sem_pf_run(const sem_pf_config *cfg, const sem_pf_buffers *buf, void *stream
         }
     }
     SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+// One PMCMC iteration's device work enqueued by ONE call (pmcmc.py:354-371 for a batch of n_filters proposals): H2D of
+// the proposals' theta (and observation parameters) from pinned host memory, sem_pf_run with iteration_result, D2H of
+// the packed results.  Does not synchronise.
+int sem_pf_iteration(const sem_pf_config *cfg, const sem_pf_buffers *buf, const double *theta_host, const double *probs_host,
+                     double *result_host, void *stream) {
+    int rc = validate(cfg);
+    if (rc) return rc;
+    if (!buf || !buf->theta || !buf->iteration_result || !theta_host || !result_host) { set_error("sem_pf_iteration: null buffer"); return SEM_ERR_INVALID; }
+    if (probs_host && !buf->probs_per_filter) { set_error("sem_pf_iteration: probs_host needs probs_per_filter"); return SEM_ERR_INVALID; }
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
+    const size_t F = (size_t)cfg->n_filters;
+    cudaStream_t s = (cudaStream_t)stream;
+    SEM_CUDA(cudaMemcpyAsync((void *)buf->theta, theta_host, F * model_ntheta(cfg->model, G) * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (probs_host) SEM_CUDA(cudaMemcpyAsync((void *)buf->probs_per_filter, probs_host, F * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = sem_pf_run(cfg, buf, stream);
+    if (rc) return rc;
+    SEM_CUDA(cudaMemcpyAsync(result_host, buf->iteration_result, F * (SEM_ITER_HEADER + (size_t)cfg->n_obs * C) * sizeof(double),
+                             cudaMemcpyDeviceToHost, s));
     return SEM_OK;
 }
 

@@ -292,29 +292,43 @@ __device__ __forceinline__ int select_ancestor(const PfDev &P, const int p, cons
     return base + min(a, len - 1);
 }
 
-// End of one PMCMC iteration (pmcmc.py:371 particle_path_sampler + the three small results the MH loop reads), by one
-// thread per filter after everything else of the filter is globally visible.  Same draw and indexing as
-// path_sample_kernel.
+// End of one PMCMC iteration (pmcmc.py:371 particle_path_sampler + the three small results the MH loop reads), by ONE
+// WARP per filter after everything else of the filter is globally visible.  Same draw and indexing as
+// path_sample_kernel.  The ancestry chase is a chain of T dependent loads (L2 or DRAM latency each: the history of the
+// headline filter is 160 MB); lane 0 walks it alone, parking the indices in the first column of the output, and the
+// 3 T state loads -- which depended on the chain when one thread did everything, 0.18 ms of a 4.5 ms pass -- are then
+// issued by all lanes at once.  Call with the 32 lanes of a warp converged.
 template <int C>
 __device__ void iteration_epilogue(const PfDev &P, const int f) {
-    const int T = P.T, N = P.N;
+    const int T = P.T, N = P.N, lane = threadIdx.x & 31;
     double *out = P.iter_out + (size_t)f * (SEM_ITER_HEADER + (size_t)T * C);
     const int status = *(volatile int32_t *)&P.status[f];
-    out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
-    out[1] = (double)status;
-    out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
-    if (status != 0) { out[3] = -1.0; return; }
     const int32_t *X = P.X_hist + (size_t)f * P.hist_rows * C * N, *A = P.ancestry + (size_t)f * P.hist_rows * N;
     const uint4 w = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, P.filter_id0 + f), P.key);
     int chosen = min((int)((bits_to_d12(w.x, w.y) - 1.0) * (double)N), N - 1);          // np.random.randint(0, N) (pmcmc.py:241)
-    out[3] = (double)chosen;
     double *traj = out + SEM_ITER_HEADER;
+    if (lane == 0) {
+        out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
+        out[1] = (double)status;
+        out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
+        out[3] = status != 0 ? -1.0 : (double)chosen;
+        if (status == 0) {
+            traj[(size_t)(T - 1) * C] = (double)chosen;
+            for (int p = T - 2; p >= 0; p--) {
+                chosen = __ldcg(&A[(size_t)(P.path_exact ? p + 1 : p) * N + chosen]);   // reference indexes row p
+                traj[(size_t)p * C] = (double)chosen;
+            }
+        }
+    }
+    __syncwarp();
+    if (status != 0) return;
+    for (int p = lane; p < T; p += 32) {
+        const int idx = (int)*(volatile double *)&traj[(size_t)p * C];
+        double v[C];
 #pragma unroll
-    for (int c = 0; c < C; c++) traj[(size_t)(T - 1) * C + c] = (double)__ldcg(&X[((size_t)(T - 1) * C + c) * N + chosen]);
-    for (int p = T - 2; p >= 0; p--) {
-        chosen = __ldcg(&A[(size_t)(P.path_exact ? p + 1 : p) * N + chosen]);           // reference indexes row p
+        for (int c = 0; c < C; c++) v[c] = (double)__ldcg(&X[((size_t)p * C + c) * N + idx]);
 #pragma unroll
-        for (int c = 0; c < C; c++) traj[(size_t)p * C + c] = (double)__ldcg(&X[((size_t)p * C + c) * N + chosen]);
+        for (int c = 0; c < C; c++) traj[(size_t)p * C + c] = v[c];
     }
 }
 
@@ -969,13 +983,15 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
     }
     if constexpr (PUSH) {
         grid.sync();                                         // this rank's history, events and status are complete
-        if (b == 0 && tid == 0) {
-            if (xchg_failed(*Xp, fsh)) atomicExch(&P.status[f], SEM_ERR_PEER);
-            if (P.iter_out) xchg_iteration_epilogue<Model::C>(P, *Xp, f, fsh);
+        if (b == 0 && tid == 0 && xchg_failed(*Xp, fsh)) atomicExch(&P.status[f], SEM_ERR_PEER);
+        if (b == 0 && tid < 32 && P.iter_out) {
+            __syncwarp();
+            if (Xp->W == 1) iteration_epilogue<Model::C>(P, f);          // one rank: the lineage never leaves this GPU
+            else if (tid == 0) xchg_iteration_epilogue<Model::C>(P, *Xp, f, fsh);
         }
     } else if (P.iter_out) {                                 // path sample + packed result of the MH iteration
         grid.sync();
-        if (b == 0 && tid == 0) iteration_epilogue<Model::C>(P, f);
+        if (b == 0 && tid < 32) iteration_epilogue<Model::C>(P, f);
     }
 }
 

@@ -223,14 +223,12 @@ class PreparedIteration:
             cfg.arith = int(arith)
         self.th_host[...] = theta
         self.buf.probs_per_filter = _ptr(self.dev_pr) if per_filter else None
+        if per_filter:
+            self.pr_host[...] = probs
         stream = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(stream):
-            self.dev_th.copy_(self.pin_th, non_blocking=True)
-            if per_filter:
-                self.pr_host[...] = probs
-                self.dev_pr.copy_(self.pin_pr, non_blocking=True)
-            _lib.check(self.L.sem_pf_run(C.byref(cfg), C.byref(self.buf), C.c_void_p(stream.cuda_stream)), "sem_pf_run")
-            self.pin_it.copy_(self.dev_it, non_blocking=True)
+        _lib.check(self.L.sem_pf_iteration(C.byref(cfg), C.byref(self.buf), C.c_void_p(self.pin_th.data_ptr()),
+                                           C.c_void_p(self.pin_pr.data_ptr()) if per_filter else None,
+                                           C.c_void_p(self.pin_it.data_ptr()), C.c_void_p(stream.cuda_stream)), "sem_pf_iteration")
         stream.synchronize()
         return self.it_host
 

@@ -49,6 +49,28 @@ def _flatten_theta(model, theta_proposal):
     return np.asarray(theta_proposal, dtype=np.float64).reshape(-1)
 
 
+class _Mvn:
+    """np.random.multivariate_normal(mean, cov) with the factorisation of cov cached while cov does not change: the same
+    standard normals from numpy's global stream, the same arithmetic (numpy's legacy algorithm: x = z (sqrt(s) v) + mean
+    with u, s, v = svd(cov)), hence the same proposals bit for bit -- without an SVD per MH iteration (60 us of a
+    0.57 ms iteration at 10^3 particles)."""
+
+    def __init__(self):
+        self.cov = None
+        self.factor = None
+
+    def __call__(self, mean, cov, rng=np.random):
+        cov = np.array(cov, dtype=np.double)
+        if self.cov is None or cov.shape != self.cov.shape or not np.array_equal(cov, self.cov):
+            _, sv, v = np.linalg.svd(cov)
+            self.cov, self.factor = cov, np.sqrt(sv)[:, None] * v
+        mean = np.array(mean, dtype=np.double)
+        x = rng.standard_normal(mean.shape[0]).reshape(-1, mean.shape[0])
+        x = np.dot(x, self.factor)
+        x += mean
+        return x.reshape(mean.shape[0])
+
+
 def _setup(Y, type_model, theta_proposal, observations, probs, n_particles, n_population, mu, resampler, seed, arith,
            filter_id, store_history=True, block_particles=0):
     model = _model_id(type_model)
@@ -210,8 +232,9 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
         return theta_vec
 
     it = 0
+    mvn = _Mvn()
     while True:                                                                   # :276-310 initial draw
-        theta_proposal = np.random.multivariate_normal(np.array(parameters), h * std)
+        theta_proposal = mvn(np.array(parameters), h * std)
         if np.sum(theta_proposal < 0) > 0:
             continue
         lz, traj = run_filter(theta_proposal, it)
@@ -229,7 +252,7 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     for i in range(1, n_chains):                                                  # :325
         if adaptive and i > 1e3:
             std = np.cov(thetas[:i].T, ddof=0) + 1e-4 * np.eye(n_par)             # :327-328
-        theta_proposal = np.random.multivariate_normal(thetas[i - 1], h * std)    # :330
+        theta_proposal = mvn(thetas[i - 1], h * std)                              # :330
         lz = None
         if not np.sum(theta_proposal < 0) > 0:                                    # :333
             lz, traj = run_filter(theta_proposal, it)
@@ -434,8 +457,9 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
 
     if True:
         it = 0
+        mvn = _Mvn()
         while True:                                                               # pmcmc.py:276-310
-            theta_proposal = rng.multivariate_normal(np.array(parameters), h * std)
+            theta_proposal = mvn(np.array(parameters), h * std, rng)
             if np.sum(theta_proposal < 0) > 0:
                 continue
             lz, traj = run_filter(theta_proposal, it)
@@ -446,7 +470,7 @@ def _particle_mcmc_sharded(Y, type_model, parameters, h, adaptive, sigma, n_chai
         for i in range(1, n_chains):                                              # pmcmc.py:325-403
             if adaptive and i > 1e3:
                 std = np.cov(thetas[:i].T, ddof=0) + 1e-4 * np.eye(n_par)
-            theta_proposal = rng.multivariate_normal(thetas[i - 1], h * std)
+            theta_proposal = mvn(thetas[i - 1], h * std, rng)
             lz = None
             if not np.sum(theta_proposal < 0) > 0:
                 lz, traj = run_filter(theta_proposal, it)
