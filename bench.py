@@ -40,7 +40,7 @@ import workloads  # noqa: E402
 # smsp__inst_executed / events once the kernel exists".  The measured per-kernel figures (executed thread-instructions per
 # event, DRAM bytes per launch) are NOT pasted here: they are read from profiles/r02_kernel_profile.json, which
 # tools/profile_kernels.py (under ncu) + tools/make_kernel_profile.py write together with the sha256 of the library they
-# were measured on.  If the library loaded now is a different build, the measured roofline is withheld (frac = null,
+# were measured on and the sha256 of its sources + compiler flags.  If the library loaded now matches neither, the measured roofline is withheld (frac = null,
 # "stale_profile") and only the declared-budget figure is printed.
 I_ALG_DECLARED = 128
 B_ALG = 48             # algorithmic HBM bytes per particle-step, SIR: 8C+24
@@ -54,8 +54,10 @@ def kernel_profile(tag):
     try:
         prof = json.load(open(KERNEL_PROFILE))
         from sem_b200 import _lib
+        from sem_b200 import build as _build
         sha = hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()
-        return prof["kernels"].get(tag), prof["lib_sha256"] != sha
+        current = prof["lib_sha256"] == sha or (prof.get("src_sha256") and prof["src_sha256"] == _build.source_hash())
+        return prof["kernels"].get(tag), not current
     except Exception:
         return None, True
 
@@ -584,11 +586,15 @@ def main():
                     "issue_active_pct_ncu": rec["issue_active_pct"] if measured else None,
                     "active_lanes_per_inst_ncu": rec["lanes_per_inst"] if measured else None,
                     "frac_with_declared_I_alg_128": events_per_s * I_ALG_DECLARED / issue_peak,
+                    "frac_at_round1_I_alg_60.6": events_per_s * 60.6 / issue_peak,
                     "sm_mhz_used": f_sm / 1e6, "launches_per_pass": launches, "avg_launch_us": 1e3 * per_gpu_ms / launches,
                     "note": "SSA propagate is bound by SM instruction issue, not HBM (SURVEY 8(d)); peak = 148 SMs x 4 "
                             "schedulers x 32 lanes x SM clock sampled during the run; frac = issue-active x active lanes / 32; sm_100a "
                             "issues the IMAD.WIDE of Philox once per ~4 cycles, so the reachable fraction for this mix is ~0.65 "
-                            "(DESIGN.md); events = fired SSA events (uniformized modes) or uniform pairs drawn (direct modes)"}
+                            "(DESIGN.md); events = fired SSA events (uniformized modes) or uniform pairs drawn (direct modes); frac uses the "
+                            "MEASURED instructions per event of this build, so removing instructions lowers it while raising "
+                            "throughput: frac_at_round1_I_alg_60.6 prices the same events at round 1's instruction count "
+                            "(the unit in which the round-1 review set its 0.58 target)"}
         hbm_ach = N * (T - 1) * B_ALG / (per_gpu_ms / 1e3) / 1e9
         roofline_hbm = {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s", "frac": hbm_ach / hbm_peak,
                         "traffic": traffic, "peak_source": how, "bytes_per_launch": N * (T - 1) * B_ALG / launches,

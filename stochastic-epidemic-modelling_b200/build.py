@@ -34,6 +34,18 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
+def source_hash():
+    """sha256 over the kernel sources, headers and compiler flags: identifies WHAT was built, whatever the binary's own
+    hash (kept beside measurements so that a profile can be recognised as belonging to the library in use)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in sorted(SOURCES + HEADERS):
+        with open(os.path.join(CSRC, name), "rb") as f:
+            h.update(name.encode()); h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
 def stale():
     if not os.path.exists(LIB):
         return True

@@ -23,7 +23,7 @@ for r in rows:
     d = launch.setdefault(int(r["ID"]), {"kernel": r["Kernel Name"]})
     d[r["Metric Name"]] = float(r["Metric Value"].replace(",", ""))
 order = [launch[k] for k in sorted(launch)]
-out = dict(lib_sha256=ev["lib_sha256"], how="tools/profile_kernels.py under ncu --metrics (cold-cache, serialised launches) + its plain run "
+out = dict(lib_sha256=ev["lib_sha256"], src_sha256=ev.get("src_sha256"), how="tools/profile_kernels.py under ncu --metrics (cold-cache, serialised launches) + its plain run "
            "(event-timed ms, event counts); third pass of every workload", kernels={})
 pos = 0
 for k, rec in enumerate(ev["records"]):

@@ -85,4 +85,5 @@ print(records[-1], flush=True)
 sha = hashlib.sha256(open(_lib.LIB_PATH, "rb").read()).hexdigest()
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 if not os.environ.get("SEM_PROFILE_NO_WRITE"):
-    json.dump(dict(lib_sha256=sha, records=records), open(OUT, "w"), indent=1)
+    from sem_b200 import build as _build
+    json.dump(dict(lib_sha256=sha, src_sha256=_build.source_hash(), records=records), open(OUT, "w"), indent=1)
