@@ -391,6 +391,7 @@ def main():
                          "auto = sem_pf_run's default (pf_persistent_x with one rank: resampling in offspring form)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-abc", action="store_true", help="skip the secondary ABC measurement (config 2)")
     ap.add_argument("--workload", default="pf", choices=["pf", "abc", "sharded", "config5"],
                     help="pf = the BASELINE metric workload (default); abc = ABC rejection trials (config 2); sharded = one "
                          "particle-sharded filter over all ranks (config 5 shape); the last two are extra measurements")
@@ -514,6 +515,32 @@ def main():
         independent = {"value": world * K2 * N * (T - 1) / (float(t2.cpu()[0]) / 1e3), "unit": "particle-steps/s", "steps": K2,
                        "note": "N independent filters of 1e5 particles, one per GPU (independent PMCMC chains); L2 not flushed"}
 
+    # ---------------------------------------------------------------- secondary: ABC trials sharded by trial id (config 2)
+    # 10^7 simulated epidemics over the ranks (tests/test_abc_sir.py: y0=(4800,20,0), beta=2, gamma=1, T=15, priors
+    # U(0,5)^2, threshold 150): every rank runs its own id range, no data-path collective; device events, max over ranks
+    abc = None
+    if not args.no_abc:
+        obs_abc = workloads.observe_normal(workloads.sir_truth((4800, 20, 0), 15, 2.0, 1.0), .1, seed=0)
+        n_abc = 10_000_000 // world
+        for i in range(2):
+            engine.abc_trials(obs_abc, 1 << 18, 150.0, [0, 5, 0, 5], seed=5, trial0=(rank * 100 + i) << 24)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        o_abc = engine.abc_trials(obs_abc, n_abc, 150.0, [0, 5, 0, 5], seed=5, trial0=rank * n_abc)
+        a1.record(stream)
+        torch.cuda.synchronize()
+        ta = torch.tensor([a0.elapsed_time(a1), float(o_abc["n_events"].cpu()[0]), float((o_abc["distance"] <= 150.0).sum().cpu())],
+                          dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = ta.clone(); dist.all_reduce(tmax, op=dist.ReduceOp.MAX); dist.all_reduce(ta, op=dist.ReduceOp.SUM); ta[0] = tmax[0]
+        abc = {"metric": "simulated epidemics/s", "value": world * n_abc / (float(ta[0].cpu()) / 1e3), "unit": "epidemics/s",
+               "n_trials": world * n_abc, "ms": float(ta[0].cpu()), "events_per_s": float(ta[1].cpu()) / (float(ta[0].cpu()) / 1e3),
+               "accepted": int(ta[2].cpu()), "config": "BASELINE config 2: ABC rejection for SIR, 10^7 epidemics sharded by trial id over the ranks",
+               "launches": 1}
+
     # ---------------------------------------------------------------- end-to-end through the public API
     e2e = None
     if not args.no_e2e:
@@ -605,7 +632,7 @@ def main():
             "warmup": W, "ms_per_step": dev_ms_max / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": workload_config(w, N, T, theta, world, args.resampler, args.arith, args.exchange),
-            "independent_chains": independent,
+            "independent_chains": independent, "abc_config2": abc,
             "pmcmc_iters_per_s": world * K / (dev_ms_max / 1e3), "events_per_s": events_per_s * world,
             "log_likelihood": logz, "gpu_launches": K * res.launches, "clocks": clocks,
             "roofline": roofline, "roofline_hbm": roofline_hbm, "e2e": e2e, "wall_s_timed_region": t_wall,

@@ -262,6 +262,27 @@ int sem_ssa_simulate(const sem_sim_config *cfg, const int32_t *x0, const double 
                      void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Deterministic ODE data synthesiser, batched (replaces differential_sir / differential_seir /
+ * differential_sir_subroups + odeint of pmcmc.py:16-52 and the daily sub-sampling of *_simulate_discrete,
+ * pmcmc.py:54-113).  One thread per parameter set integrates the mean-field ODE over the caller's time
+ * grid with classical RK4 (`substeps` equal steps between consecutive grid points, fp64) and stores the grid points
+ * selected by row_of_grid (row index in the output, or -1): the reference keeps, per integer day d, the LAST grid
+ * point with ceil(t) == d.  theta: SIR (beta, gamma); SEIR (beta, alpha, gamma); subgroups: beta row-major [i][j]
+ * (the rate applied to susceptibles of group i by infectives of group j, as pmcmc.py:47 uses it), then gamma. */
+typedef struct sem_ode_config {
+    int32_t model, n_groups;    /* SEM_MODEL_*; subgroup models: G */
+    int32_t n_sets;             /* parameter sets (threads) */
+    int32_t n_grid;             /* points of the time grid */
+    int32_t n_rows;             /* rows kept per set */
+    int32_t substeps;           /* RK4 steps per grid interval (>= 1) */
+    int32_t shared_y0;          /* 1: y0 is [C] for all sets, 0: [n_sets][C] */
+    int32_t shared_theta;       /* 1: theta is [P], 0: [n_sets][P] */
+} sem_ode_config;
+/* all pointers device: y0 double, theta double, t_grid [n_grid] double, row_of_grid [n_grid] int32, out [n_sets][n_rows][C] double */
+int sem_ode_daily(const sem_ode_config *cfg, const double *y0, const double *theta, const double *t_grid,
+                  const int32_t *row_of_grid, double *out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * ABC rejection trials: replaces the trial loop body of abc_algo (abc_algo.py:33-99) for SIR:
  * prior draw, Poisson-perturbed start, SSA, daily discretisation, L1 distance (abc_algo.py:10-13).
  * ---------------------------------------------------------------------------------------------- */

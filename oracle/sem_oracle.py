@@ -305,3 +305,48 @@ def abc_trial(observed_data, beta, gamma, n_start, stream):
         traj[k] = [k, cur[0], cur[1], cur[2]]
     d = (np.mean(np.abs(traj[:, 2] - obs[:, 1])) + np.mean(np.abs(traj[:, 3] - obs[:, 2]))) / 2    # :10-13
     return traj, float(d)
+
+
+# ------------------------------------------------------------------ ODE data synthesiser (pmcmc.py:16-113)
+def ode_rhs(model, G, th, y):
+    """differential_sir / differential_seir / differential_sir_subroups (pmcmc.py:16-52), N = sum(y) per evaluation."""
+    N = 0.0
+    for v in y:
+        N += v
+    if model == 0:
+        return np.array([-th[0] * y[0] * y[1] / N, ((th[0] * y[0] / N) - th[1]) * y[1], th[1] * y[1]])
+    if model == 1:
+        return np.array([-th[0] * y[0] * y[2] / N, th[0] * y[0] * y[2] / N - th[1] * y[1], th[1] * y[1] - th[2] * y[2], th[2] * y[2]])
+    d = np.zeros(3 * G)
+    gamma = th[G * G]
+    for i in range(G):
+        force = 0.0
+        for j in range(G):
+            force += th[i * G + j] * y[3 * j + 1]
+        inf = y[3 * i] * force / N
+        d[3 * i] = -inf; d[3 * i + 1] = inf - gamma * y[3 * i + 1]; d[3 * i + 2] = gamma * y[3 * i + 1]
+    return d
+
+
+def ode_daily(model, G, y0, th, t, substeps=8):
+    """Restatement of sem_ode_daily's scheme: classical RK4, `substeps` per grid interval, then the reference's daily
+    sub-sampling (last grid point with ceil(t) == day, pmcmc.py:68-74).  Returns (days+1, C)."""
+    t = np.asarray(t, dtype=np.float64)
+    y = np.array(y0, dtype=np.float64).reshape(-1)
+    th = np.asarray(th, dtype=np.float64).reshape(-1)
+    days = np.ceil(t).astype(int)
+    rows = np.zeros((days[-1] + 1, y.size))
+    last = {d: np.nonzero(days == d)[0][-1] for d in range(days[-1] + 1)}
+    keep = {k: d for d, k in last.items()}
+    for k in range(t.size):
+        if k > 0:
+            h = (t[k] - t[k - 1]) / float(substeps)
+            for _ in range(substeps):
+                k1 = ode_rhs(model, G, th, y)
+                k2 = ode_rhs(model, G, th, y + 0.5 * h * k1)
+                k3 = ode_rhs(model, G, th, y + 0.5 * h * k2)
+                k4 = ode_rhs(model, G, th, y + h * k3)
+                y = y + h / 6.0 * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+        if k in keep:
+            rows[keep[k]] = y
+    return rows

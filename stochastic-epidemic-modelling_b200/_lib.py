@@ -21,7 +21,7 @@ EXPORTS = [
     "sem_abi_version", "sem_last_error", "sem_device_info", "sem_host_workspace_release",
     "sem_pf_workspace_bytes", "sem_pf_hist_elems", "sem_pf_ancestry_elems", "sem_pf_launch_count",
     "sem_pf_run", "sem_pf_iteration", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
-    "sem_ssa_simulate", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
+    "sem_ssa_simulate", "sem_ode_daily", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
     "sem_xchg_bytes", "sem_xchg_alloc", "sem_xchg_open", "sem_xchg_close", "sem_xchg_free", "sem_peer_enable",
     "sem_xchg_reset", "sem_xchg_iteration_result", "sem_pf_sharded_supported", "sem_pf_run_sharded",
     "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson", "sem_test_fast_math",
@@ -46,6 +46,11 @@ class PfBuffers(C.Structure):
         ("n_events", C.c_void_p), ("workspace", C.c_void_p), ("iteration_result", C.c_void_p),
         ("probs_per_filter", C.c_void_p),
     ]
+
+
+class OdeConfig(C.Structure):
+    _fields_ = [("model", C.c_int32), ("n_groups", C.c_int32), ("n_sets", C.c_int32), ("n_grid", C.c_int32),
+                ("n_rows", C.c_int32), ("substeps", C.c_int32), ("shared_y0", C.c_int32), ("shared_theta", C.c_int32)]
 
 
 class ShardStep(C.Structure):
@@ -107,6 +112,8 @@ def load():
     L.sem_pf_run.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p]
     L.sem_pf_iteration.restype = C.c_int
     L.sem_pf_iteration.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.sem_ode_daily.restype = C.c_int
+    L.sem_ode_daily.argtypes = [C.POINTER(OdeConfig)] + [C.c_void_p] * 6
     L.sem_pf_run_host.restype = C.c_int
     L.sem_pf_run_host.argtypes = [C.POINTER(PfConfig)] + [C.c_void_p] * 8
     L.sem_shard_init.restype = C.c_int

@@ -34,12 +34,16 @@ def nvcc_path():
     raise RuntimeError("nvcc not found")
 
 
-def source_hash():
-    """sha256 over the kernel sources, headers and compiler flags: identifies WHAT was built, whatever the binary's own
-    hash (kept beside measurements so that a profile can be recognised as belonging to the library in use)."""
+PF_KERNEL_FILES = ["sem_pf.cu", "sem_pf_xchg.cu", "sem_pf_dev.cuh", "sem_pf_host.h", "sem_common.cuh", "sem_host.h", "sem_logtab.inc"]
+
+
+def source_hash(files=None):
+    """sha256 over the sources the particle-filter kernels are compiled from (everything but the simulation / ABC unit and
+    the public header) and the compiler flags: identifies WHAT was built, whatever the binary's own hash (kept beside
+    measurements so that a profile can be recognised as belonging to the library in use)."""
     import hashlib
     h = hashlib.sha256()
-    for name in sorted(SOURCES + HEADERS):
+    for name in sorted(files or PF_KERNEL_FILES):
         with open(os.path.join(CSRC, name), "rb") as f:
             h.update(name.encode()); h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())

@@ -115,6 +115,89 @@ static void launch_sim(const SimDev &P, int arith, bool replay, cudaStream_t s) 
     else sim_kernel<Model, SEM_ARITH_FAST, false><<<blocks, threads, 0, s>>>(P);
 }
 
+// ------------------------------------------------------------------------------------------ ODE synthesiser
+// Mean-field ODEs of pmcmc.py:16-52 (N = sum of the state, recomputed per evaluation like the reference), classical RK4,
+// one thread per parameter set; the state lives in registers (C <= 12 doubles).
+struct OdeDev {
+    int n_sets, n_grid, n_rows, substeps, shared_y0, shared_theta, G;
+    const double *y0, *theta, *t;
+    const int32_t *row_of_grid;
+    double *out;
+};
+
+template <int MODEL, int G> struct OdeDims { static constexpr int C = MODEL == SEM_MODEL_SIR ? 3 : MODEL == SEM_MODEL_SEIR ? 4 : 3 * G,
+                                              P = MODEL == SEM_MODEL_SIR ? 2 : MODEL == SEM_MODEL_SEIR ? 3 : G * G + 1; };
+
+template <int MODEL, int G>
+__device__ __forceinline__ void ode_rhs(const double *th, const double *y, double *d) {
+    constexpr int C = OdeDims<MODEL, G>::C;
+    double N = 0.0;
+#pragma unroll
+    for (int c = 0; c < C; c++) N += y[c];
+    if constexpr (MODEL == SEM_MODEL_SIR) {                      // pmcmc.py:16-24
+        d[0] = -th[0] * y[0] * y[1] / N;
+        d[1] = ((th[0] * y[0] / N) - th[1]) * y[1];
+        d[2] = th[1] * y[1];
+    } else if constexpr (MODEL == SEM_MODEL_SEIR) {              // :27-35
+        d[0] = -th[0] * y[0] * y[2] / N;
+        d[1] = th[0] * y[0] * y[2] / N - th[1] * y[1];
+        d[2] = th[1] * y[1] - th[2] * y[2];
+        d[3] = th[2] * y[2];
+    } else {                                                     // :38-52: group i is infected by sum_j beta[i][j] I_j
+        const double gamma = th[G * G];
+#pragma unroll
+        for (int i = 0; i < G; i++) {
+            double force = 0.0;
+#pragma unroll
+            for (int j = 0; j < G; j++) force += th[i * G + j] * y[3 * j + 1];
+            const double inf = y[3 * i] * force / N;
+            d[3 * i] = -inf; d[3 * i + 1] = inf - gamma * y[3 * i + 1]; d[3 * i + 2] = gamma * y[3 * i + 1];
+        }
+    }
+}
+
+template <int MODEL, int G>
+__global__ void __launch_bounds__(128) ode_kernel(const OdeDev P) {
+    constexpr int C = OdeDims<MODEL, G>::C, NP = OdeDims<MODEL, G>::P;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.n_sets) return;
+    double th[NP], y[C], k1[C], k2[C], k3[C], k4[C], w[C];
+#pragma unroll
+    for (int i = 0; i < NP; i++) th[i] = P.theta[(P.shared_theta ? 0 : (size_t)b * NP) + i];
+#pragma unroll
+    for (int c = 0; c < C; c++) y[c] = P.y0[(P.shared_y0 ? 0 : (size_t)b * C) + c];
+    double *out = P.out + (size_t)b * P.n_rows * C;
+    for (int k = 0; k < P.n_grid; k++) {
+        if (k > 0) {
+            const double h = (P.t[k] - P.t[k - 1]) / (double)P.substeps;
+            for (int q = 0; q < P.substeps; q++) {
+                ode_rhs<MODEL, G>(th, y, k1);
+#pragma unroll
+                for (int c = 0; c < C; c++) w[c] = y[c] + 0.5 * h * k1[c];
+                ode_rhs<MODEL, G>(th, w, k2);
+#pragma unroll
+                for (int c = 0; c < C; c++) w[c] = y[c] + 0.5 * h * k2[c];
+                ode_rhs<MODEL, G>(th, w, k3);
+#pragma unroll
+                for (int c = 0; c < C; c++) w[c] = y[c] + h * k3[c];
+                ode_rhs<MODEL, G>(th, w, k4);
+#pragma unroll
+                for (int c = 0; c < C; c++) y[c] += h / 6.0 * (k1[c] + 2.0 * k2[c] + 2.0 * k3[c] + k4[c]);
+            }
+        }
+        const int row = P.row_of_grid[k];
+        if (row >= 0 && row < P.n_rows) {
+#pragma unroll
+            for (int c = 0; c < C; c++) out[(size_t)row * C + c] = y[c];
+        }
+    }
+}
+
+template <int MODEL, int G>
+static void launch_ode(const OdeDev &P, cudaStream_t s) {
+    ode_kernel<MODEL, G><<<(P.n_sets + 127) / 128, 128, 0, s>>>(P);
+}
+
 // ------------------------------------------------------------------------------------------ ABC
 struct AbcDev {
     int T, early_reject;
@@ -353,6 +436,33 @@ int sem_abc_run(const sem_abc_config *cfg, const double *obs, const uint64_t *tr
     const int blocks = (int)(want < cap ? want : cap);
     void *args[] = {(void *)&P};
     SEM_CUDA(cudaLaunchKernel(fn, dim3(blocks), dim3(threads), args, smem, s));
+    SEM_CUDA(cudaGetLastError());
+    return SEM_OK;
+}
+
+
+int sem_ode_daily(const sem_ode_config *cfg, const double *y0, const double *theta, const double *t_grid,
+                  const int32_t *row_of_grid, double *out, void *stream) {
+    if (!cfg || !y0 || !theta || !t_grid || !row_of_grid || !out) { set_error("bad ode args"); return SEM_ERR_INVALID; }
+    if (cfg->model < 0 || cfg->model > 3 || cfg->n_sets < 1 || cfg->n_grid < 1 || cfg->n_rows < 1 || cfg->substeps < 1) { set_error("bad ode config"); return SEM_ERR_INVALID; }
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1;
+    if (G < 1 || G > SEM_MAX_GROUPS) { set_error("n_groups must be 1..4"); return SEM_ERR_INVALID; }
+    OdeDev P;
+    P.n_sets = cfg->n_sets; P.n_grid = cfg->n_grid; P.n_rows = cfg->n_rows; P.substeps = cfg->substeps;
+    P.shared_y0 = cfg->shared_y0; P.shared_theta = cfg->shared_theta; P.G = G;
+    P.y0 = y0; P.theta = theta; P.t = t_grid; P.row_of_grid = row_of_grid; P.out = out;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch (cfg->model) {
+        case SEM_MODEL_SIR: launch_ode<SEM_MODEL_SIR, 1>(P, s); break;
+        case SEM_MODEL_SEIR: launch_ode<SEM_MODEL_SEIR, 1>(P, s); break;
+        default:
+            switch (G) {
+                case 1: launch_ode<SEM_MODEL_SIR_SUBGROUPS, 1>(P, s); break;
+                case 2: launch_ode<SEM_MODEL_SIR_SUBGROUPS, 2>(P, s); break;
+                case 3: launch_ode<SEM_MODEL_SIR_SUBGROUPS, 3>(P, s); break;
+                default: launch_ode<SEM_MODEL_SIR_SUBGROUPS, 4>(P, s); break;
+            }
+    }
     SEM_CUDA(cudaGetLastError());
     return SEM_OK;
 }

@@ -290,6 +290,44 @@ def simulate(model, x0, theta, max_time, G=1, arith="fast32", seed=0, sim_index0
         return dict(x=x_out, n_rows=n_rows, times=times, states=states, _keep=[x0t, tht, ru, ro])
 
 
+def daily_rows_of_grid(t):
+    """pmcmc.py:68-74 (and :92-98, :107-113): per integer day d = 0 .. ceil(t[-1]) the reference keeps the LAST grid point
+    with ceil(t) == d.  Returns (row_of_grid[n_grid] int32 with -1 = not kept, n_rows); raises ValueError like the
+    reference's list.index when a day has no grid point."""
+    t = np.asarray(t, dtype=np.float64).reshape(-1)
+    days = np.ceil(t).astype(np.int64)
+    n_rows = int(days[-1]) + 1
+    row = np.full(t.size, -1, dtype=np.int32)
+    for d in range(n_rows):
+        hit = np.nonzero(days == d)[0]
+        if hit.size == 0:
+            raise ValueError(f"{d} is not in list")
+        row[hit[-1]] = d
+    return row, n_rows
+
+
+def ode_daily(model, y0, theta, t, G=1, substeps=8, device=None):
+    """Batched deterministic ODE synthesiser (sem_ode_daily; pmcmc.py:16-113): y0 (B,C) or (C,), theta (B,P) or (P,), time
+    grid t.  Returns a CUDA float64 tensor (B, days+1, C): for every integer day the last grid point with ceil(t) == day."""
+    L = _lib.load()
+    dev = require_cuda(device)
+    Cn, P, _ = model_dims(model, G)
+    row, n_rows = daily_rows_of_grid(t)
+    with torch.cuda.device(dev):
+        y0t = _dev_f64(y0, dev); tht = _dev_f64(theta, dev)
+        shared_y0, shared_th = y0t.dim() == 1, tht.dim() == 1
+        B = 1 if (shared_y0 and shared_th) else (tht.shape[0] if shared_y0 else y0t.shape[0])
+        tg = _dev_f64(t, dev).reshape(-1)
+        rg = torch.from_numpy(row).to(dev)
+        out = torch.empty((B, n_rows, Cn), dtype=torch.float64, device=dev)
+        cfg = _lib.OdeConfig(model=model, n_groups=G, n_sets=B, n_grid=tg.numel(), n_rows=n_rows, substeps=int(substeps),
+                             shared_y0=int(shared_y0), shared_theta=int(shared_th))
+        _lib.check(L.sem_ode_daily(C.byref(cfg), _ptr(y0t.contiguous()), _ptr(tht.contiguous()), _ptr(tg), _ptr(rg), _ptr(out), _stream()),
+                   "sem_ode_daily")
+        out._keep = [y0t, tht, tg, rg]
+        return out
+
+
 def abc_trials(obs, n_trials, threshold, priors, seed=0, trial0=0, trial_ids=None, arith="fast32", early_reject=False,
                want_traj=False, replay=None, device=None):
     """Run n_trials ABC trials (sem_abc_run).  Returns dict(theta (n,2), distance (n,), traj (n,T,3)|None, n_events)."""

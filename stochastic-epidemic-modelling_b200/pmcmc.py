@@ -15,7 +15,7 @@ Deliberate, documented differences from the reference:
       0/0 underflow is not reproduced.
   D8  particle_path_sampler keeps the reference's off-by-one ancestry indexing by default (exact_genealogy=False).
   `jobs` is accepted and ignored (no process pool).
-The ODE data synthesiser (pmcmc.py:16-113) is out of scope.
+The ODE data synthesiser (pmcmc.py:16-113) is a batched GPU utility here (RK4): *_simulate_discrete.
 """
 from enum import Enum
 
@@ -26,7 +26,8 @@ from . import engine
 from .gillespie_algo import *  # noqa: F401,F403  (pmcmc.py:13 re-exports the simulators)
 from .gillespie_algo import __all__ as _g_all
 
-__all__ = ["ModelType", "particle_filter", "particle_path_sampler", "particle_mcmc", "pf_loglik"] + list(_g_all)
+__all__ = ["ModelType", "particle_filter", "particle_path_sampler", "particle_mcmc", "pf_loglik", "sir_simulate_discrete",
+           "seir_simulate_discrete", "sir_subgroups_simulate_discrete", "simulate_discrete_batch"] + list(_g_all)
 
 
 class ModelType(Enum):          # pmcmc.py:116-120
@@ -47,6 +48,48 @@ def _flatten_theta(model, theta_proposal):
         betas, gamma = theta_proposal
         return np.concatenate([np.asarray(betas, dtype=np.float64).reshape(-1), [float(gamma)]])
     return np.asarray(theta_proposal, dtype=np.float64).reshape(-1)
+
+
+def simulate_discrete_batch(type_model, y0, theta, t, *, substeps=8):
+    """The reference's ODE data synthesiser for a BATCH of parameter sets: mean-field ODE of the model
+    integrated over the grid t (RK4 on the GPU, `substeps` per grid interval; odeint in the reference), one row per integer
+    day (pmcmc.py:54-113).  y0 (B,C) or (C,), theta (B,P) or (P,) with the subgroup betas row-major as pmcmc.py:47 uses
+    them, then gamma.  Returns float64 numpy (B, days+1, C)."""
+    model = _model_id(type_model)
+    y0 = np.asarray(y0, dtype=np.float64)
+    G = (y0.shape[-1] // 3) if model >= 2 else 1
+    return engine.ode_daily(model, y0, np.asarray(theta, dtype=np.float64), t, G=G, substeps=substeps).cpu().numpy()
+
+
+def _discrete_frame(rows, names):
+    import pandas as pd
+    return pd.DataFrame({"time": np.arange(rows.shape[0]), **{n: rows[:, c] for c, n in enumerate(names)}})
+
+
+def sir_simulate_discrete(y0, t, beta, gamma):
+    """pmcmc.py:54-74: DataFrame(time, susceptible, infected, removed), one row per integer day."""
+    rows = simulate_discrete_batch(ModelType.SIR, np.asarray(y0, dtype=float), [beta, gamma], t)[0]
+    return _discrete_frame(rows, ["susceptible", "infected", "removed"])
+
+
+def seir_simulate_discrete(y0, t, beta, alpha, gamma):
+    """pmcmc.py:77-98: DataFrame(time, susceptible, exposed, infected, removed)."""
+    rows = simulate_discrete_batch(ModelType.SEIR, np.asarray(y0, dtype=float), [beta, alpha, gamma], t)[0]
+    return _discrete_frame(rows, ["susceptible", "exposed", "infected", "removed"])
+
+
+def sir_subgroups_simulate_discrete(y0, t, beta, gamma):
+    """pmcmc.py:101-113: y0 (G,3), beta (G,G); DataFrame(susceptible0, infected0, removed0, ..., time)."""
+    import pandas as pd
+    y0 = np.asarray(y0, dtype=float)
+    G = y0.shape[0]
+    rows = simulate_discrete_batch(ModelType.SIR_SUBGROUPS, y0.reshape(-1), np.concatenate([np.asarray(beta, dtype=float).reshape(-1), [gamma]]), t)[0]
+    cols = {}
+    for g in range(G):
+        for c, n in enumerate(("susceptible", "infected", "removed")):
+            cols[f"{n}{g}"] = rows[:, 3 * g + c]
+    cols["time"] = np.arange(rows.shape[0])
+    return pd.DataFrame(cols)
 
 
 class _Mvn:

@@ -234,3 +234,46 @@ def test_fast32_stream_layout(c_oracle):
     # and the 52-bit stream of arith 1 is a different stream over the same law: one call per event
     out52 = c_oracle.ssa(0, 1, x0, theta, tmax, arith=1, seed=seed, sim_index=sim, max_rec=4000)
     assert out52["pairs"] != out["pairs"] or not np.array_equal(out52["states"], out["states"])
+
+
+# ------------------------------------------------------------------ ODE data synthesiser
+ODE_CASES = [("sir", 0, 1, (4800, 20, 0), [2, 1], "t200"), ("sir_slow", 0, 1, (9980, 20, 0), [.4, .2], "t1500"),
+             ("seir", 1, 1, (4800, 0, 20, 0), [2., 1., 1.], "t200"), ("sir_coarse", 0, 1, (990, 10, 0), [1.2, .4], "tc")]
+
+
+@pytest.mark.parametrize("name,model,G,y0,th,tkey", ODE_CASES, ids=[c[0] for c in ODE_CASES])
+def test_ode_synthesiser_scheme_vs_reference(name, model, G, y0, th, tkey):
+    """The RK4 scheme the CUDA synthesiser uses (restated in numpy) against rows made by the unmodified reference
+    (odeint + its daily sub-sampling, tests/golden/make_golden_ode.py): within 1e-7 of the population (odeint's own
+    tolerance is 1.5e-8 relative)."""
+    g = golden("ode_synth")
+    rows = so.ode_daily(model, G, y0, th, g[tkey])
+    ref = g[name]
+    assert np.array_equal(ref[:, 0], np.arange(ref.shape[0]))              # the reference's `time` column = the day
+    assert rows.shape == ref[:, 1:].shape
+    assert np.abs(rows - ref[:, 1:]).max() < 1e-7 * sum(y0)
+
+
+def test_ode_synthesiser_subgroups_vs_reference():
+    g = golden("ode_synth")
+    for name, G, pop, beta, gamma in (("sub2", 2, g["pop2"], g["beta2"], .5), ("sub3", 3, g["pop3"], g["beta3"], .4)):
+        rows = so.ode_daily(2, G, pop.reshape(-1), list(beta.reshape(-1)) + [gamma], g["t200"])
+        ref = g[name]
+        assert np.array_equal(ref[:, -1], np.arange(ref.shape[0]))          # (subgroup frames carry `time` last)
+        assert np.abs(rows - ref[:, :-1]).max() < 1e-7 * pop.sum()
+
+
+def test_daily_rows_of_grid_is_the_reference_selection():
+    import sem_b200
+    g = golden("ode_synth")
+    for tkey in ("t200", "t1500", "tc"):
+        t = g[tkey]
+        row, n = sem_b200.engine.daily_rows_of_grid(t)
+        days = np.ceil(t).astype(int)
+        assert n == days[-1] + 1
+        for d in range(n):                                                  # pmcmc.py:68-74: last index whose ceil(time) is d
+            k = len(days) - 1 - list(days)[::-1].index(d)
+            assert row[k] == d
+        assert (row >= 0).sum() == n
+    with pytest.raises(ValueError):                                         # a day without a grid point: list.index raises
+        sem_b200.engine.daily_rows_of_grid(np.array([0.0, 2.5]))

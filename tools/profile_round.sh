@@ -8,9 +8,9 @@ M=gpu__time_duration.sum,smsp__inst_executed.sum,smsp__thread_inst_executed.sum,
 python tools/profile_kernels.py > $out/profile_plain.log 2>&1 || { tail -5 $out/profile_plain.log; exit 1; }
 SEM_PROFILE_NO_WRITE=1 ncu --metrics $M --clock-control none --csv --log-file $out/profile_metrics.csv \
     -k regex:"pf_persistent|abc_kernel|pf_step|pf_offspring|pf_init|weight_table" python tools/profile_kernels.py > $out/profile_ncu.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-e2e > $out/${tag}_bench_short.log 2>&1 && \
+python bench.py --steps 2 --warmup 3 --no-e2e --no-abc > $out/${tag}_bench_short.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/${tag}_launches_default_bench.csv \
-    python bench.py --steps 2 --warmup 3 --no-e2e > $out/${tag}_launches_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-e2e --no-abc > $out/${tag}_launches_ncu.log 2>&1
 SEM_PROFILE_ONLY=headline_sir ncu --set full --clock-control none --import-source on -k regex:pf_persistent_x --launch-skip 2 -c 1 \
     -f -o $out/${tag}_pf_persistent_x python tools/profile_kernels.py > $out/${tag}_ncu_full.log 2>&1
 python bench.py > $out/${tag}_bench.log 2>&1
