@@ -247,7 +247,7 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     sampled_trajs = np.zeros((T, n_chains, Cn))                                  # pmcmc.py:269-272
     std = np.eye(n_par) if sigma is None else sigma                               # :273-275
     seed = engine.new_seed() if seed is None else seed
-    counters = dict(filter_runs=0, acceptances=1, launches=0)
+    counters = dict(filter_runs=0, acceptances=1, launches=0, arith=set())
 
     # One iteration = ONE launch (the filter, the path sample of pmcmc.py:371 and the packing of the results happen in
     # the whole-filter kernel) + one small H2D (theta) + one small D2H (log-likelihood, status, sampled trajectory);
@@ -260,7 +260,9 @@ def particle_mcmc(Y, type_model, parameters, h, adaptive=False, sigma=None, n_ch
     def run_filter(theta_vec, it):
         theta2, probs2 = _split(model, G, theta_vec, probs)
         th = _flatten_theta(model, theta2)
-        r = prep.run(th, it, probs=probs2, arith=engine.resolve_arith(model, arith, theta=th, n_particles=n_particles))[0]
+        a_now = engine.resolve_arith(model, arith, theta=th, n_particles=n_particles)    # 'auto' may pick another interval simulation
+        r = prep.run(th, it, probs=probs2, arith=a_now)[0]                                # for another proposal: both are exact
+        counters["arith"].add(engine.ARITH_NAMES.get(a_now, a_now))
         counters["filter_runs"] += 1
         counters["launches"] += prep.launches + (0 if prep.launches == 1 else 1)
         if int(r[1]) != 0:

@@ -298,6 +298,40 @@ def test_pf_multi_filter_batch(sem, c_oracle):
         np.testing.assert_allclose(res.log_zetas[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11)
 
 
+@pytest.mark.parametrize("arith,normal", [(4, False), (3, False), (4, True)])
+def test_batch_of_proposals_equals_single_filters(sem, c_oracle, arith, normal):
+    """A batch of MH proposals in ONE launch (the offspring-form kernel with several filters side by side, each with its
+    own theta AND observation parameter, sem_pf_iteration / probs_per_filter): every filter equals the oracle's run of
+    that proposal alone -- states, ancestors, log-likelihoods, and the packed iteration result."""
+    import torch
+    T, N = 12, 1300
+    Y = _truth_Y(0, T, 5, .1, normal)
+    thetas = np.array([[.45, .2], [.4, .25], [.6, .2], [.5, .3], [.42, .18]])
+    probs = np.array([.1, .12, .08, .15, .1])
+    F = len(thetas)
+    cfg = sem.engine.make_pf_config(0, N, T, n_filters=F, observations=normal, probs=.5, resampler=1, arith=arith, seed=77,
+                                    mu=[20], n_population=[1000])
+    assert sem._lib.load().sem_pf_launch_count(sem.engine.C.byref(cfg)) == 1
+    prep = sem.engine.PreparedIteration(cfg, Y)
+    r = prep.run(thetas, 40, probs=probs, arith=arith).copy()
+    torch.cuda.synchronize()
+    X_hist, anc, logz, status, nev, _ = prep.out
+    for f in range(F):
+        ref = c_oracle.pf_run(0, Y, thetas[f], normal, probs[f], N, resampler=1, arith=arith, seed=77, filter_id=40 + f, mu=[20], npop=[1000])
+        assert int(status[f]) == ref["collapsed"] == 0
+        assert np.array_equal(X_hist[f].permute(0, 2, 1).cpu().numpy(), ref["X_hist"]), f
+        assert np.array_equal(anc[f].cpu().numpy(), ref["ancestry"]), f
+        np.testing.assert_allclose(logz[f].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
+        assert r[f, 0] == float(logz[f, -1]) and r[f, 1] == 0 and int(r[f, 2]) == ref["n_events"]
+        traj = r[f, sem.engine.ITER_HEADER:].reshape(T, 3)
+        chosen = int(r[f, 3])
+        assert np.array_equal(traj[-1], ref["X_hist"][-1, chosen])          # the path ends in the chosen particle ...
+        k = chosen
+        for p in range(T - 2, -1, -1):                                      # ... and follows the reference's ancestry indexing (D8)
+            k = ref["ancestry"][p, k]
+            assert np.array_equal(traj[p], ref["X_hist"][p, k])
+
+
 # ------------------------------------------------------------------ headline size: size-independent properties
 def test_pf_full_size_properties(sem, c_oracle):
     """BASELINE config 4 size (SIR, pop 1e4, 1e5 particles, 101 observations): invariants of every particle."""
@@ -762,6 +796,21 @@ def test_pmcmc_lookahead_posterior_vs_reference(sem):
     assert abs(acc_our - acc_ref) < 0.08, (acc_ref, acc_our)
     for st in stats_all:
         assert st["lookahead"] == 8 and st["launches"] < 0.7 * 6000, st    # (acceptance ~0.55 here: ~1.8 iterations per launch)
+
+
+def test_pmcmc_auto_switches_interval_simulation_mid_chain(sem):
+    """arith='auto' is resolved per proposal: around growth 0.5 per interval a small filter's chain alternates between the
+    direct method and uniformized intervals (both exact); the chain stays well-behaved and both kernels ran."""
+    import workloads
+    Y = workloads.observe_binomial(workloads.sir_truth((980, 20, 0), 12, 1.0, .5), .2, seed=2)
+    np.random.seed(8)
+    st = {}
+    th, lik, traj = sem.particle_mcmc(Y, sem.ModelType.SIR, [1.0, .5], 4e-3, n_chains=400, probs=.2, n_particles=600, n_population=1000,
+                                      mu=20, seed=21, stats=st)
+    assert st["arith"] == {"fast32", "uniformized32"}, st["arith"]
+    assert np.all(np.isfinite(th)) and np.all(th > 0) and np.all(np.isfinite(lik)) and np.all(traj.sum(2) == 1000)
+    assert 20 < st["acceptances"] < 390
+    assert abs(th[100:, 0].mean() - 1.0) < .25 and abs(th[100:, 1].mean() - .5) < .15
 
 
 def test_pmcmc_lookahead_with_p_obs_and_adaptive(sem):
