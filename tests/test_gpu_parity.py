@@ -902,6 +902,28 @@ def test_named_sizes_match_oracle_exactly(sem, c_oracle, name, model, G, theta, 
 
 
 # ------------------------------------------------------------------ robustness / edge cases
+@pytest.mark.parametrize("pop,mu0,theta,T,N", [(250_000, 800, [.5, .2], 9, 3000),       # batch means 1e3 .. 1e4: alias tables AND the PTRS fallback (> 4096)
+                                               (1000, 2, [.15, .4], 10, 5000),            # dying epidemic: means below 4 (the grid's first table), absorptions
+                                               (30_000, 3000, [3.0, .3], 6, 2000)])        # explosive growth: many growth-capped batches per interval
+def test_uniformized_candidate_count_regimes_vs_oracle(sem, c_oracle, pop, mu0, theta, T, N):
+    """The candidate counts of a uniformized batch come from alias tables for means in [4, 4096] (smaller means use the
+    table of 4, larger ones the PTRS sampler): filters whose batch means sit below, inside, across and above that range
+    equal the oracle bit for bit."""
+    import torch
+    import workloads
+    Y = workloads.observe_binomial(workloads.sir_truth((pop - mu0, mu0, 0), T, theta[0], theta[1]), .1, seed=3)
+    cfg = sem.engine.make_pf_config(0, N, T, probs=.1, resampler=1, arith=4, seed=31337, filter_id0=5, mu=[mu0], n_population=[pop])
+    res = sem.engine.run_pf(cfg, Y, np.array(theta, float))
+    torch.cuda.synchronize()
+    ref = c_oracle.pf_run(0, Y, theta, False, .1, N, resampler=1, arith=4, seed=31337, filter_id=5, mu=[mu0], npop=[pop])
+    assert int(res.status.cpu()[0]) == ref["collapsed"]
+    if ref["collapsed"] == 0:
+        assert np.array_equal(res.X_hist[0].permute(0, 2, 1).cpu().numpy(), ref["X_hist"])
+        assert np.array_equal(res.ancestry[0].cpu().numpy(), ref["ancestry"])
+        np.testing.assert_allclose(res.log_zetas[0].cpu().numpy(), ref["log_zetas"], rtol=1e-11, atol=1e-11)
+        assert int(res.n_events.cpu()[0]) == ref["n_events"]
+
+
 def test_many_ctas_global_prefix_path(sem, c_oracle):
     """More CTAs than fit the shared-memory prefix stage (nb > 4096) and than one finalize chunk: same answers."""
     import torch
