@@ -231,6 +231,10 @@ int sem_pf_sharded_supported(const sem_pf_config *cfg, int32_t world);
 /* one filter pass of this rank's shard.  ancestry holds GLOBAL parent indices; log_zetas / status are identical on all
  * ranks.  X0 (if given) is this rank's slice [C][n].  Advances x->generation and x->launch_tag. */
 int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_xchg_desc *x, void *stream);
+/* sem_pf_iteration for the sharded filter: theta_host [P] (pinned) -> buf->theta, this rank's launch with
+ * buf->iteration_result = sem_xchg_iteration_result(arena), packed result -> result_host (pinned).  Enqueue only. */
+int sem_pf_iteration_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_xchg_desc *x, const double *theta_host,
+                             double *result_host, void *stream);
 
 /* particle_path_sampler (pmcmc.py:236-248).  chosen < 0: pick uniformly with Philox(seed); exact = 0 keeps
  * the reference's off-by-one ancestry indexing, 1 follows the true genealogy.  traj: device [T][C] int32. */

@@ -23,7 +23,7 @@ EXPORTS = [
     "sem_pf_run", "sem_pf_iteration", "sem_pf_run_host", "sem_path_sample", "sem_hist_to_f64",
     "sem_ssa_simulate", "sem_ode_daily", "sem_abc_run", "sem_shard_init", "sem_shard_offspring", "sem_shard_propagate",
     "sem_xchg_bytes", "sem_xchg_alloc", "sem_xchg_open", "sem_xchg_close", "sem_xchg_free", "sem_peer_enable",
-    "sem_xchg_reset", "sem_xchg_iteration_result", "sem_pf_sharded_supported", "sem_pf_run_sharded",
+    "sem_xchg_reset", "sem_xchg_iteration_result", "sem_pf_sharded_supported", "sem_pf_run_sharded", "sem_pf_iteration_sharded",
     "sem_test_philox", "sem_test_binom_logpmf", "sem_test_norm_logpdf", "sem_test_poisson", "sem_test_fast_math",
 ]
 
@@ -143,6 +143,8 @@ def load():
     L.sem_pf_sharded_supported.argtypes = [C.POINTER(PfConfig), C.c_int32]
     L.sem_pf_run_sharded.restype = C.c_int
     L.sem_pf_run_sharded.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(XchgDesc), C.c_void_p]
+    L.sem_pf_iteration_sharded.restype = C.c_int
+    L.sem_pf_iteration_sharded.argtypes = [C.POINTER(PfConfig), C.POINTER(PfBuffers), C.POINTER(XchgDesc), C.c_void_p, C.c_void_p, C.c_void_p]
     L.sem_path_sample.restype = C.c_int
     L.sem_path_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                   C.c_uint64, C.c_uint32, C.c_void_p, C.c_void_p]

@@ -556,60 +556,92 @@ __device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X
     return w[C];
 }
 
-// particle_path_sampler (pmcmc.py:236-248) over the shards, by thread 0 of CTA 0 of every rank after its grid barrier.
+// particle_path_sampler (pmcmc.py:236-248) over the shards, by warp 0 of CTA 0 of every rank after its grid barrier.
 // The lineage is chased by whichever rank owns the current particle (local loads only); when the parent lives on
-// another rank a token (time, global index) goes to that rank's mailbox.  The holder of the token stores the row it
-// reads into EVERY rank's packed iteration result, so all ranks end with the same trajectory and can run the MH accept
-// step redundantly (no host collective per iteration).
+// another rank a token (time, global index) goes to that rank's mailbox.  The holder walks its SEGMENT of the lineage
+// with lane 0 alone (a chain of dependent ancestry loads, indices parked in its own copy of the result), then all lanes
+// fetch the segment's rows at once and store them into EVERY rank's packed iteration result, so all ranks end with the
+// same trajectory and can run the MH accept step redundantly (no host collective per iteration).  Every lane fences its
+// own remote stores (system scope) before lane 0 passes the token on.  Call with the 32 lanes of the warp converged.
 template <int C>
 __device__ void xchg_iteration_epilogue(const PfDev &P, const XchgDev &X, const int f, const size_t fsh) {
-    const int T = P.T, N = P.N, W = X.W, me = X.rank;
+    const int T = P.T, N = P.N, W = X.W, me = X.rank, lane = threadIdx.x & 31;
     const size_t ish = (size_t)f * (SEM_ITER_HEADER + (size_t)T * C);    // this filter's block of the packed results (one rank)
     double *out = P.iter_out + ish;
     const int status = *(volatile int32_t *)&P.status[f];
-    out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
-    out[1] = (double)status;
-    out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
-    if (status != 0) { out[3] = -1.0; return; }
     const uint4 wd = philox4x32_10(0u, 0u, 0u, stream_word(DOM_PATH, P.filter_id0 + f), P.key);
     long long idx = min((long long)((bits_to_d12(wd.x, wd.y) - 1.0) * (double)X.Ng), X.Ng - 1);   // np.random.randint(0, N) (pmcmc.py:241)
-    out[3] = (double)idx;
+    if (lane == 0) {
+        out[0] = __ldcg(&P.log_zetas[(size_t)f * T + T - 1]);
+        out[1] = (double)status;
+        out[2] = P.n_events ? (double)__ldcg(&P.n_events[f]) : 0.0;
+        out[3] = status != 0 ? -1.0 : (double)idx;
+    }
+    if (status != 0) return;
     const unsigned long long tag = (unsigned long long)X.tag << 52, kDone = 0xFFFFFull;
     volatile unsigned long long *mail = xsh(X.mail[me], fsh);
+    volatile double *park = X.iter[me] + ish + SEM_ITER_HEADER;           // row p, column 0: local index of the lineage at p
     int cur = T - 1;
     bool hold = (int)(idx / N) == me;
     const long long t0 = clock64();
     for (;;) {
-        if (!hold) {
-            unsigned long long tok;
-            unsigned spins = 0;
-            for (;;) {
-                tok = *mail;
-                if ((tok >> 52) == X.tag) break;
-                if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X, fsh); return; }
+        int seg_hi = 0, seg_lo = 0, next_owner = -2;                      // -2: nothing to do (failed / done), -1: lineage complete
+        long long next_idx = 0;
+        if (lane == 0) {
+            bool go = true;
+            if (!hold) {
+                unsigned long long tok = 0;
+                unsigned spins = 0;
+                for (;;) {
+                    tok = *mail;
+                    if ((tok >> 52) == X.tag) break;
+                    if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) { xchg_fail(X, fsh); go = false; break; }
+                }
+                if (go) {
+                    *mail = 0ull;
+                    const unsigned long long pp = (tok >> 32) & kDone;
+                    if (pp == kDone) go = false;
+                    else { cur = (int)pp - 1; idx = (long long)(tok & 0xffffffffull); }
+                }
             }
-            *mail = 0ull;
-            const unsigned long long pp = (tok >> 32) & kDone;
-            if (pp == kDone) return;
-            cur = (int)pp - 1; idx = (long long)(tok & 0xffffffffull); hold = true;
+            if (go) {                                                     // walk this rank's segment of the lineage
+                seg_hi = cur;
+                long long id = idx;
+                int p = cur;
+                for (;;) {
+                    const int loc = (int)(id - (long long)me * N);
+                    park[(size_t)p * C] = (double)loc;
+                    if (p == 0) { next_owner = -1; seg_lo = 0; break; }
+                    const long long nid = __ldcg(&P.ancestry[((size_t)f * P.hist_rows + (P.path_exact ? p : p - 1)) * N + loc]);   // reference indexes row p
+                    p -= 1;
+                    if ((int)(nid / N) != me) { next_owner = (int)(nid / N); next_idx = nid; seg_lo = p + 1; break; }
+                    id = nid;
+                }
+            }
         }
-        const int loc = (int)(idx - (long long)me * N);
+        next_owner = __shfl_sync(0xffffffffu, next_owner, 0);
+        if (next_owner == -2) return;
+        seg_hi = __shfl_sync(0xffffffffu, seg_hi, 0); seg_lo = __shfl_sync(0xffffffffu, seg_lo, 0);
+        __syncwarp();                                                     // lane 0's parked indices are visible to the warp
+        for (int q = seg_lo + lane; q <= seg_hi; q += 32) {               // the segment's rows, all lanes at once
+            const int loc = (int)park[(size_t)q * C];
+            double v[C];
 #pragma unroll
-        for (int c = 0; c < C; c++) {
-            const double v = (double)__ldcg(&P.X_hist[(((size_t)f * P.hist_rows + cur) * C + c) * N + loc]);
-            for (int r = 0; r < W; r++) *(volatile double *)&X.iter[r][ish + SEM_ITER_HEADER + (size_t)cur * C + c] = v;
+            for (int c = 0; c < C; c++) v[c] = (double)__ldcg(&P.X_hist[(((size_t)f * P.hist_rows + q) * C + c) * N + loc]);
+            for (int r = 0; r < W; r++) {
+#pragma unroll
+                for (int c = 0; c < C; c++) *(volatile double *)&X.iter[r][ish + SEM_ITER_HEADER + (size_t)q * C + c] = v[c];
+            }
         }
-        if (cur == 0) {
-            __threadfence_system();
-            for (int r = 0; r < W; r++) if (r != me) *(volatile unsigned long long *)X.mail[r] = tag | (kDone << 32);
+        __threadfence_system();                                           // (keeps the rows stored so far ahead of the token, transitively ahead of DONE)
+        __syncwarp();
+        if (next_owner == -1) {
+            if (lane == 0) for (int r = 0; r < W; r++) if (r != me) *(volatile unsigned long long *)X.mail[r] = tag | (kDone << 32);
             return;
         }
-        idx = __ldcg(&P.ancestry[((size_t)f * P.hist_rows + (P.path_exact ? cur : cur - 1)) * N + loc]);     // reference indexes row p
-        cur -= 1;
-        const int owner = (int)(idx / N);
-        if (owner != me) {
-            __threadfence_system();                          // (keeps the rows stored so far ahead of the token, transitively ahead of DONE)
-            *(volatile unsigned long long *)X.mail[owner] = tag | ((unsigned long long)(cur + 1) << 32) | (unsigned long long)idx;
+        if (lane == 0) {
+            cur = seg_lo - 1;
+            *(volatile unsigned long long *)X.mail[next_owner] = tag | ((unsigned long long)(cur + 1) << 32) | (unsigned long long)next_idx;
             hold = false;
         }
     }
@@ -987,7 +1019,7 @@ __device__ __forceinline__ void pf_persistent_body(const PfDev &P, const XchgDev
         if (b == 0 && tid < 32 && P.iter_out) {
             __syncwarp();
             if (Xp->W == 1) iteration_epilogue<Model::C>(P, f);          // one rank: the lineage never leaves this GPU
-            else if (tid == 0) xchg_iteration_epilogue<Model::C>(P, *Xp, f, fsh);
+            else xchg_iteration_epilogue<Model::C>(P, *Xp, f, fsh);
         }
     } else if (P.iter_out) {                                 // path sample + packed result of the MH iteration
         grid.sync();

@@ -238,6 +238,22 @@ int sem_pf_run_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_
     return SEM_OK;
 }
 
+// One MH iteration of the sharded filter enqueued by one call: H2D of theta from pinned host memory, this rank's launch
+// with the path sample over the shards, D2H of the packed result (every rank receives the same one).  No synchronisation.
+int sem_pf_iteration_sharded(const sem_pf_config *cfg, const sem_pf_buffers *buf, sem_xchg_desc *x, const double *theta_host,
+                             double *result_host, void *stream) {
+    if (!cfg || !buf || !buf->theta || !buf->iteration_result || !theta_host || !result_host) { set_error("sem_pf_iteration_sharded: null buffer"); return SEM_ERR_INVALID; }
+    int rc = validate(cfg);
+    if (rc) return rc;
+    const int G = cfg->model >= SEM_MODEL_SIR_SUBGROUPS ? cfg->n_groups : 1, C = model_cols(cfg->model, G);
+    cudaStream_t s = (cudaStream_t)stream;
+    SEM_CUDA(cudaMemcpyAsync((void *)buf->theta, theta_host, model_ntheta(cfg->model, G) * sizeof(double), cudaMemcpyHostToDevice, s));
+    rc = sem_pf_run_sharded(cfg, buf, x, stream);
+    if (rc) return rc;
+    SEM_CUDA(cudaMemcpyAsync(result_host, buf->iteration_result, (SEM_ITER_HEADER + (size_t)cfg->n_obs * C) * sizeof(double), cudaMemcpyDeviceToHost, s));
+    return SEM_OK;
+}
+
 #ifdef SEM_PHASES
 int sem_debug_phases_x(unsigned long long *host_out) {
     SEM_CUDA(cudaMemcpyFromSymbol(host_out, g_phase, sizeof(unsigned long long) * 24 * 256));

@@ -399,12 +399,16 @@ class PeerFilter:
         self.pin_th.numpy()[...] = np.asarray(theta, dtype=np.float64).reshape(-1)
         stream = stream or torch.cuda.current_stream(self.dev)
         self.buf.iteration_result = self.iter_ptr if want_path else None
-        with torch.cuda.device(self.dev), torch.cuda.stream(stream):
-            self.dev_th.copy_(self.pin_th, non_blocking=True)
-            _lib.check(self.L.sem_pf_run_sharded(C.byref(cfg), C.byref(self.buf), C.byref(self.desc),
-                                                 C.c_void_p(stream.cuda_stream)), "sem_pf_run_sharded")
-            if want_path:
-                self.pin_it.copy_(self.dev_it, non_blocking=True)
+        with torch.cuda.device(self.dev):
+            if want_path:                                    # theta H2D + launch + result D2H in one C call
+                _lib.check(self.L.sem_pf_iteration_sharded(C.byref(cfg), C.byref(self.buf), C.byref(self.desc), C.c_void_p(self.pin_th.data_ptr()),
+                                                           C.c_void_p(self.pin_it.data_ptr()), C.c_void_p(stream.cuda_stream)),
+                           "sem_pf_iteration_sharded")
+            else:
+                with torch.cuda.stream(stream):
+                    self.dev_th.copy_(self.pin_th, non_blocking=True)
+                    _lib.check(self.L.sem_pf_run_sharded(C.byref(cfg), C.byref(self.buf), C.byref(self.desc),
+                                                         C.c_void_p(stream.cuda_stream)), "sem_pf_run_sharded")
         self.launches += 1
 
     def iteration(self, theta, filter_id=0, probs=None, arith=None):
