@@ -14,6 +14,7 @@ using namespace sem;
 // V2: Philox only (the words are xor-ed into a checksum)
 // V3: V1's candidates fed by a counter hash instead of Philox (candidate cost alone)
 // V4: V1 with Philox4x32 cut to 7 rounds (what the generator costs)
+// V5: V1 with the next group's Philox call inside the current group's straight-line block (software pipeline)
 template <int ROUNDS>
 __device__ __forceinline__ uint4 philox_r(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKey &key) {
 #pragma unroll
@@ -44,11 +45,39 @@ __global__ void __launch_bounds__(768) k_cand(const double *theta, int n, const 
     uint32_t cand = 0, chk = 0;
     const uint32_t last = 4u * groups;
     bool stop = false;
+    if constexpr (V == 5) {                                  // V1 with the next group's Philox call INSIDE the straight-line block of the current group
+        uint4 w = philox4x32_10(0u, (uint32_t)j, 5u, stream_word(DOM_SSA, 0), key);
+        while (cand < last && !stop) {
+            const uint32_t k = cand >> 2;
+            if ((cand & 3u) == 0u && last - cand >= 4u) {
+                const uint4 wn = philox4x32_10(k + 1u, (uint32_t)j, 5u, stream_word(DOM_SSA, 0), key);
+                const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const bool live = !stop;
+                    cand += live ? 1u : 0u;
+                    unif32_candidate<SirModel, false>(m, sc, x, T, words[q], live, stop);
+                }
+                w = wn;
+            } else {
+                const uint32_t base = cand & ~3u;
+#pragma unroll 1
+                for (uint32_t q = 0; q < 4u; q++) {
+                    const uint32_t c = base + q;
+                    const bool live = !stop && c >= cand && c < last;
+                    const uint32_t wq = q == 0u ? w.x : q == 1u ? w.y : q == 2u ? w.z : w.w;
+                    unif32_candidate<SirModel, false>(m, sc, x, T, wq, live, stop);
+                    cand += live ? 1u : 0u;
+                }
+                w = philox4x32_10((cand >> 2), (uint32_t)j, 5u, stream_word(DOM_SSA, 0), key);
+            }
+        }
+    }
     if constexpr (V == 1) {                                  // the production loop
         PairSource<false> loc; loc.init(key, (uint32_t)j, 5u, stream_word(DOM_SSA, 0));
         unif32_serve<SirModel, false>(m, sc, x, T, loc, cand, last, stop);
     }
-    while (V != 1 && cand < last && !stop) {
+    while (V != 1 && V != 5 && cand < last && !stop) {
         uint4 w;
         if constexpr (V == 3) {
             uint32_t h = (cand >> 2) * 0x9E3779B9u + (uint32_t)j;
@@ -133,6 +162,7 @@ int main(int argc, char **argv) {
         run<2>(w, d_theta, d_out, groups);
         run<3>(w, d_theta, d_out, groups);
         run<4>(w, d_theta, d_out, groups);
+        run<5>(w, d_theta, d_out, groups);
     }
     return 0;
 }
