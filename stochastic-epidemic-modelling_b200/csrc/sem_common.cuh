@@ -1038,8 +1038,10 @@ __device__ __forceinline__ void unif32_candidate(const Model &m, const typename 
 }
 
 // Serve the candidates [cand, last) of a batch, four per Philox call (candidate c = word c & 3 of call c >> 2), until the
-// batch stops.  A full group is straight-line code (live = not stopped yet); the first group after a restart or a
-// hand-over and the last group of a batch take the general path (words before cand were served already).  (Computing the
+// batch stops.  An aligned group is straight-line code (live = not stopped yet and inside the batch); only the first group
+// after a restart or a hand-over takes the general path (words before cand were served already).  (The last, partial
+// group of a batch used to take the general path too: the lanes of a sorted warp end within ~10 consecutive iterations,
+// each of which then ran both paths -- 7-9 % of the loop.)  (Computing the
 // next group's Philox words behind this group's candidates was measured: the lone-warp latency of a group stays 540
 // cycles -- ptxas does not interleave the two chains -- and the filter gets 6 % slower; tools/micro/cand_loop.cu.)
 template <class Model, bool TRACK_R>
@@ -1048,11 +1050,12 @@ __device__ __forceinline__ void unif32_serve(const Model &m, const typename Mode
     while (cand < last && !stop) {
         loc.k = cand >> 2;
         const uint4 w = loc.raw();
-        if ((cand & 3u) == 0u && last - cand >= 4u) {
-            const uint32_t words[4] = {w.x, w.y, w.z, w.w};
+        if ((cand & 3u) == 0u) {                                       // an aligned group: straight-line; the last group of a batch
+            const uint32_t words[4] = {w.x, w.y, w.z, w.w};              // has fewer than four candidates left (rem)
+            const uint32_t rem = last - cand;
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                const bool live = !stop;
+                const bool live = !stop && (uint32_t)q < rem;
                 cand += live ? 1u : 0u;
                 unif32_candidate<Model, TRACK_R>(m, sc, x, T, words[q], live, stop);
             }
