@@ -433,3 +433,56 @@ def test_auto_interval_simulation_choice():
     assert engine.resolve_arith(0, "fast") == 1 and engine.resolve_arith(0, 2) == 2
     cfg = engine.make_pf_config(0, 100, 5, mu=[20], n_population=[1000])
     assert cfg.arith == A["uniformized32"]
+
+
+def test_lookahead_mh_has_the_law_of_the_sequential_loop(monkeypatch):
+    """Host logic of particle_mcmc(lookahead=L) with the filter replaced by a stub that returns an exact
+    log-density: the speculative batches (proposals drawn under the rejection assumption, first acceptance ends the batch,
+    later evaluations discarded, adaptive covariance from running sums) must leave the chain's stationary law and
+    acceptance rate unchanged -- an off-by-one in the bookkeeping would bias both."""
+    import sem_b200
+    from sem_b200 import engine, pmcmc
+    mu, sd = np.array([2.0, 1.0]), np.array([.3, .2])
+    T = 5
+    launches = {"n": 0}
+
+    class StubIteration:
+        def __init__(self, cfg, Y, device=None):
+            self.F = cfg.n_filters
+            self.launches = 1
+            self.buf = np.zeros((self.F, engine.ITER_HEADER + T * 3))
+
+        def run(self, theta, filter_id, probs=None, arith=None):
+            th = np.atleast_2d(np.asarray(theta, dtype=float))
+            launches["n"] += 1
+            self.buf[:, 0] = -0.5 * (((th - mu) / sd) ** 2).sum(1)
+            self.buf[:, 1] = 0
+            self.buf[:, engine.ITER_HEADER:] = np.repeat(th[:, :1], T * 3, axis=1)     # "trajectory" = beta of the evaluated proposal
+            return self.buf
+
+    class StubLib:
+        def sem_pf_launch_count(self, cfg):
+            return 1
+
+    monkeypatch.setattr(engine, "PreparedIteration", StubIteration)
+    monkeypatch.setattr(engine, "require_cuda", lambda device=None: "cpu")
+    monkeypatch.setattr(engine._lib, "load", lambda: StubLib())
+    Y = np.zeros((T, 3))
+    n = 40000
+    out = {}
+    for L in (1, 8):
+        np.random.seed(12)
+        launches["n"] = 0
+        st = {}
+        th, lik, traj = pmcmc.particle_mcmc(Y, pmcmc.ModelType.SIR, [2.0, 1.0], .12, adaptive=(L == 8), n_chains=n, probs=.1, n_particles=100,
+                                            n_population=1000, mu=20, seed=1, lookahead=L, return_log=True, stats=st)
+        assert np.all(th > 0)
+        np.testing.assert_allclose(lik, -0.5 * (((th - mu) / sd) ** 2).sum(1), rtol=1e-12, atol=1e-12)   # stored likelihood belongs to the stored theta
+        assert np.array_equal(traj[0, :, 0], th[:, 0])                                                 # ... and so does the stored trajectory
+        acc = np.mean(np.any(th[1:] != th[:-1], axis=1))
+        out[L] = (th[2000:].mean(0), th[2000:].std(0), acc, launches["n"])
+        ess = n / 12.0
+        assert np.all(np.abs(th[2000:].mean(0) - mu) < 5 * sd / np.sqrt(ess)), out[L]
+        assert np.all(np.abs(th[2000:].std(0) / sd - 1) < .08), out[L]
+    assert out[1][3] > 0.95 * n and out[8][3] < 0.9 * n               # (negative proposals need no launch; the adaptive chain accepts ~80 %: 1.2 iterations per launch)
+    assert 0.15 < out[1][2] < 0.6
