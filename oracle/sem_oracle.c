@@ -192,6 +192,10 @@ static int64_t ssa_run_unif32(const so_model *m, double *x, double max_time, so_
 
 static int64_t ssa_run(const so_model *m, double *x, double max_time, int arith, so_stream *s,
                        double *times, double *states, int64_t max_rec, int64_t *n_rec) {
+    /* Philox orders only: a state holding a negative count fires no events.  The reference raises
+     * ValueError there (negative probabilities in np.random.choice, gillespie_algo.py:63); the speculative / uniformized
+     * loops would see a negative total propensity, i.e. time running backwards. */
+    if (arith != ARITH_REF) for (int c = 0; c < m->C; c++) if (x[c] < 0) return 0;
     if (arith == ARITH_UNIF && s->philox && !times) return ssa_run_unif(m, x, max_time, s);
     if (arith == ARITH_UNIF32 && s->philox && !times) return ssa_run_unif32(m, x, max_time, s);
     if (arith == ARITH_UNIF) arith = ARITH_FAST;
@@ -314,6 +318,10 @@ double so_norm_logpdf(double y, double x, double probs) {
 /* per-particle log-weight = min over observed columns (pmcmc.py:179,181).  x: C doubles. */
 static double log_weight(int model, int G, int obs_kind, double probs, const double *Yrow, int Cobs, const double *x) {
     double lw = INFINITY;
+    /* extension: a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169)
+     * weighs zero; in the reference scipy returns nan for it and np.random.choice raises ValueError (pmcmc.py:193) */
+    const int Call = model == M_SIR ? 3 : model == M_SEIR ? 4 : 3 * G;
+    for (int c = 0; c < Call; c++) if (x[c] < 0) return -INFINITY;
     for (int c = 0; c < Cobs; c++) {
         double xc;
         if (model == M_SUB2) { xc = 0; for (int g = 0; g < G; g++) xc = xc + x[3 * g + c]; }   /* pmcmc.py:172-173 */

@@ -1129,6 +1129,12 @@ __device__ __forceinline__ long long ssa_run_unif32(const Model &m, double *x, d
 template <class Model, int ARITH, bool REPLAY, bool TRACK_R, class Rec>
 __device__ __forceinline__ long long ssa_run(const Model &m, double *x, double max_time, PairSource<REPLAY> &src,
                                              const double2 *tab, Rec rec) {
+    if constexpr (ARITH != SEM_ARITH_REFERENCE) {            // a state holding a negative count fires no events (the
+        bool neg = false;                                    // reference raises ValueError, gillespie_algo.py:63; the blocked
+#pragma unroll                                               // loops would run time backwards under a negative propensity)
+        for (int c = 0; c < Model::C; c++) neg = neg || x[c] < 0.0;
+        if (neg) return 0;
+    }
     if constexpr (ARITH == SEM_ARITH_FAST && !REPLAY) {
         if constexpr (SpecBlock<Model>::bits52 > 0) return ssa_run_spec<Model, SpecBlock<Model>::bits52, false, TRACK_R>(m, x, max_time, src, tab, rec);
         else return ssa_run_fast<Model, TRACK_R>(m, x, max_time, src, tab, rec);

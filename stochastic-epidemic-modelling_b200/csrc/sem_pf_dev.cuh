@@ -92,6 +92,13 @@ template <class Model>
 __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double *wrow, const double2 *tab,
                                                 const double probs) {
     double lw = CUDART_INF;
+    // extension: a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169)
+    // weighs zero -- the reference gets nan from scipy and raises in np.random.choice (pmcmc.py:193) -- so the interval
+    // simulation never sees a negative propensity
+    bool neg = false;
+#pragma unroll
+    for (int c = 0; c < Model::C; c++) neg = neg || x[c] < 0.0;
+    if (neg) return -CUDART_INF;
 #pragma unroll
     for (int c = 0; c < Model::C; c++) {
         if (c < P.Cobs) {
@@ -373,7 +380,10 @@ __device__ __forceinline__ long long first_slot_ge_quick(const SlotMap &sm, cons
 //             and combines them itself, so every CTA on every GPU holds bit-identical prefixes / total.
 //   records   each particle computes the slots [J(lower), J(upper)) of its children and stores one record
 //             (state, global parent index) per child straight into the receive buffer rec[gen & 1][N] of the rank that owns
-//             the slot; the child's thread polls its own record until no word is the -1 sentinel, then resets it.
+//             the slot; the child's thread polls its own record until no word is the all-ones sentinel, then resets it.
+//             Words travel with the sign bit flipped (rec_enc): a state count may be NEGATIVE -- the reference draws
+//             I0 ~ Poisson(mu) and sets S0 = n_population - I0 without a clamp (pmcmc.py:156-169) -- so the sign cannot mark
+//             an empty word; all-ones would be the count 2^31 - 1, which the int32 history cannot hold anyway.
 // Re-use is safe without further synchronisation: a slot written in generation g is next written in generation g + 2
 // (records) / g + 3 (partials), and nobody can get there before its reader has published generation g + 1, which it
 // does after a system-scope fence that follows its reset (see the order of operations in pf_persistent_body).
@@ -408,6 +418,7 @@ __device__ __forceinline__ int4 ld_vol(const int32_t *p) {
 }
 constexpr unsigned long long kPartSentinel = ~0ull;
 template <int C> struct RecWords { static constexpr int value = (C + 1 + 3) & ~3; };
+__device__ __forceinline__ int rec_enc(const int v) { return v ^ (int)0x80000000u; }   // (its own inverse)
 
 template <class T> __device__ __forceinline__ T *xsh(T *p, const size_t fsh) { return (T *)((char *)p + fsh); }   // pointer into filter f's arena
 __device__ __forceinline__ void xchg_fail(const XchgDev &X, const size_t fsh) { *(volatile int *)xsh(X.err, fsh) = 1; }
@@ -501,8 +512,8 @@ __device__ __forceinline__ void xchg_offspring(const PfDev &P, const XchgDev &X,
     if (!active || hi < lo) hi = lo;
     int w[RW];
 #pragma unroll
-    for (int c = 0; c < RW; c++) w[c] = c < C ? (active ? (int)x[c] : 0) : 0;
-    w[C] = P.j0 + j;
+    for (int c = 0; c < RW; c++) w[c] = rec_enc(c < C ? (active ? (int)x[c] : 0) : 0);
+    w[C] = rec_enc(P.j0 + j);
     const size_t half = (size_t)((gen + 1u) & 1u) * N * RW;
     auto put = [&](const long long ch, const int (&rec)[RW]) {
         const int r = (int)(ch / N);
@@ -539,21 +550,21 @@ __device__ __forceinline__ int xchg_take_record(const PfDev &P, const XchgDev &X
         for (int q = 0; q < RW; q += 4) {
             const int4 v = ld_vol(src + q);
             w[q] = v.x; w[q + 1] = v.y; w[q + 2] = v.z; w[q + 3] = v.w;
-            ok = ok && ((v.x | v.y | v.z | v.w) >= 0);
+            ok = ok && (max(max((unsigned)v.x, (unsigned)v.y), max((unsigned)v.z, (unsigned)v.w)) != 0xffffffffu);
         }
         if (ok) break;
         if ((++spins & 1023u) == 0u && clock64() - t0 > X.timeout) {
             xchg_fail(X, fsh);
 #pragma unroll
-            for (int c = 0; c < RW; c++) w[c] = 0;               // an extinct particle: the launch ends quickly, status SEM_ERR_PEER
+            for (int c = 0; c < RW; c++) w[c] = rec_enc(0);      // an extinct particle: the launch ends quickly, status SEM_ERR_PEER
             break;
         }
     }
 #pragma unroll
     for (int q = 0; q < RW; q += 4) st_vol(src + q, -1, -1, -1, -1);
 #pragma unroll
-    for (int c = 0; c < C; c++) x[c] = (double)w[c];
-    return w[C];
+    for (int c = 0; c < C; c++) x[c] = (double)rec_enc(w[c]);
+    return rec_enc(w[C]);
 }
 
 // particle_path_sampler (pmcmc.py:236-248) over the shards, by warp 0 of CTA 0 of every rank after its grid barrier.

@@ -76,6 +76,17 @@ def _dev_f64(a, dev):
     return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev, non_blocking=True)
 
 
+def check_rates(theta, what="theta"):
+    """Host-side guard of the simulators' inputs: a negative rate constant gives a negative propensity, which the
+    reference refuses inside np.random.choice (gillespie_algo.py:63, "probabilities are not non-negative") -- and which
+    would run the kernels' blocked event loops backwards in time.  Device-resident inputs are the caller's job."""
+    if theta is None or isinstance(theta, torch.Tensor):
+        return
+    th = np.asarray(theta, dtype=np.float64)
+    if (th < 0).any():
+        raise ValueError(f"probabilities are not non-negative ({what} holds a negative rate)")
+
+
 def new_seed():
     """A Philox seed drawn from numpy's global generator, so np.random.seed() makes runs reproducible
     the same way it does for the reference."""
@@ -147,6 +158,7 @@ def run_pf(cfg, Y, theta, X0=None, replay=None, device=None, out=None, iter_out=
     F, T, N = cfg.n_filters, cfg.n_obs, cfg.n_particles
     G = cfg.n_groups if cfg.model >= 2 else 1
     Cn, P, Cobs = model_dims(cfg.model, G)
+    check_rates(theta)
     with torch.cuda.device(dev):
         Yd = _dev_f64(Y, dev).reshape(T, Cobs)
         thd = _dev_f64(theta, dev).reshape(F, P)
@@ -221,6 +233,7 @@ class PreparedIteration:
             cfg.probs = float(probs)
         if arith is not None:
             cfg.arith = int(arith)
+        check_rates(theta)
         self.th_host[...] = theta
         self.buf.probs_per_filter = _ptr(self.dev_pr) if per_filter else None
         if per_filter:
@@ -256,6 +269,7 @@ def simulate(model, x0, theta, max_time, G=1, arith="fast32", seed=0, sim_index0
     L = _lib.load()
     dev = require_cuda(device)
     Cn, P, _ = model_dims(model, G)
+    check_rates(theta)
     with torch.cuda.device(dev):
         x0t = torch.as_tensor(np.asarray(x0)).to(dev).to(torch.int32).contiguous()
         tht = _dev_f64(theta, dev)
@@ -333,6 +347,9 @@ def abc_trials(obs, n_trials, threshold, priors, seed=0, trial0=0, trial_ids=Non
     """Run n_trials ABC trials (sem_abc_run).  Returns dict(theta (n,2), distance (n,), traj (n,T,3)|None, n_events)."""
     L = _lib.load()
     dev = require_cuda(device)
+    check_rates(priors, "the prior box")
+    if replay is not None:
+        check_rates(replay.get("theta"))
     with torch.cuda.device(dev):
         obsd = _dev_f64(obs, dev).reshape(-1, 3)
         T = obsd.shape[0]

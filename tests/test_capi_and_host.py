@@ -435,6 +435,17 @@ def test_auto_interval_simulation_choice():
     assert cfg.arith == A["uniformized32"]
 
 
+def test_negative_rates_are_refused_on_the_host():
+    """A negative rate constant is refused before anything is launched, with numpy's own words for it
+    (np.random.choice inside gillespie_algo.py:63); device-resident parameters are the caller's job."""
+    import torch
+    from sem_b200 import engine
+    engine.check_rates([.4, .2]); engine.check_rates(None); engine.check_rates(torch.tensor([-1.0]))
+    for bad in ([-.4, .2], np.array([[.4, .2], [.4, -1e-9]])):
+        with pytest.raises(ValueError, match="not non-negative"):
+            engine.check_rates(bad)
+
+
 def test_lookahead_mh_has_the_law_of_the_sequential_loop(monkeypatch):
     """Host logic of particle_mcmc(lookahead=L) with the filter replaced by a stub that returns an exact
     log-density: the speculative batches (proposals drawn under the rejection assumption, first acceptance ends the batch,

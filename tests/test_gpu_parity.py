@@ -938,6 +938,36 @@ def test_many_ctas_global_prefix_path(sem, c_oracle):
     np.testing.assert_allclose(r.log_zetas[0].cpu().numpy(), o["log_zetas"], rtol=1e-11)
 
 
+@pytest.mark.parametrize("model,G,theta,npop,mu,arith,resampler", [
+    (3, 2, [2.665, 1.706, 1.764, 1.242, 0.934], [3, 4], [0, 1], 3, 1),    # the case tools/fuzz_parity.py found (Poisson(1) > 4)
+    (0, 1, [1.2, .4], [6], [4], 4, 1), (0, 1, [1.2, .4], [6], [4], 3, 0), (1, 1, [2.0, .5, .4], [5], [3], 3, 1)])
+def test_negative_initial_susceptibles_vs_oracle(sem, c_oracle, model, G, theta, npop, mu, arith, resampler):
+    """pmcmc.py:156-169 sets S0 = n_population - Poisson(mu) without a clamp: with a tiny population some particles start
+    with S0 < 0.  They weigh zero (k > n) and the filter goes on; the device-side exchange must carry the negative counts
+    (its records once used the sign bit as the empty mark: every such launch ended with SEM_ERR_PEER after the time limit)."""
+    import torch
+    import workloads
+    N, T, F = 1000, 4, 5
+    truth = (workloads.subgroups_truth(((npop[0] - mu[0], mu[0], 0), (npop[1] - mu[1], mu[1], 0)), T, np.array(theta[:4]).reshape(2, 2), theta[4]).reshape(T, 2, 3).sum(1)
+             if model == 3 else workloads.seir_truth((npop[0] - mu[0], 0, mu[0], 0), T, *theta) if model == 1
+             else workloads.sir_truth((npop[0] - mu[0], mu[0], 0), T, *theta))
+    Y = workloads.observe_binomial(truth, .4, seed=7)
+    thetas = np.array([theta] * F) * (1 + 0.05 * np.arange(F))[:, None]
+    cfg = sem.engine.make_pf_config(model, N, T, G=G, n_filters=F, probs=.4, resampler=resampler, arith=arith, seed=99, filter_id0=3, mu=mu, n_population=npop)
+    r = sem.engine.run_pf(cfg, Y, thetas)
+    torch.cuda.synchronize()
+    negative = False
+    for f in range(F):
+        o = c_oracle.pf_run(model, Y, thetas[f], False, .4, N, G=G, resampler=resampler, arith=arith, seed=99, filter_id=3 + f, mu=mu, npop=npop)
+        assert int(r.status.cpu()[f]) == o["collapsed"]
+        negative = negative or bool((o["X_hist"][0] < 0).any())
+        if o["collapsed"] == 0:
+            assert np.array_equal(r.X_hist[f].permute(0, 2, 1).cpu().numpy(), o["X_hist"])
+            assert np.array_equal(r.ancestry[f].cpu().numpy(), o["ancestry"])
+            np.testing.assert_allclose(r.log_zetas[f].cpu().numpy(), o["log_zetas"], rtol=1e-11, atol=1e-11)
+    assert negative, "the case is meant to start some particles below zero"
+
+
 def test_one_filter_of_a_batch_collapses(sem, c_oracle):
     """Filters of a batch are independent: one collapsing (its status = step) leaves the others untouched."""
     import torch

@@ -277,3 +277,21 @@ def test_daily_rows_of_grid_is_the_reference_selection():
         assert (row >= 0).sum() == n
     with pytest.raises(ValueError):                                         # a day without a grid point: list.index raises
         sem_b200.engine.daily_rows_of_grid(np.array([0.0, 2.5]))
+
+
+@pytest.mark.parametrize("model,G,theta,npop,mu", [(0, 1, [1.2, .4], [6], [4]), (3, 2, [2.7, 1.7, 1.8, 1.2, .9], [3, 4], [0, 1])])
+def test_negative_counts_weigh_zero_and_never_propagate(c_oracle, model, G, theta, npop, mu):
+    """S0 = n_population - Poisson(mu) can be negative (pmcmc.py:156-169; the reference then raises in
+    np.random.choice).  Such a particle weighs zero: it is nobody's ancestor, and no later state holds a negative count."""
+    import workloads
+    T, N = 4, 1000
+    truth = (workloads.subgroups_truth(((npop[0] - mu[0], mu[0], 0), (npop[1] - mu[1], mu[1], 0)), T, np.array(theta[:4]).reshape(2, 2), theta[4]).reshape(T, 2, 3).sum(1)
+             if model == 3 else workloads.sir_truth((npop[0] - mu[0], mu[0], 0), T, *theta))
+    Y = workloads.observe_binomial(truth, .4, seed=7)
+    for arith in (1, 3, 4) if model == 0 else (1, 3):
+        o = c_oracle.pf_run(model, Y, theta, False, .4, N, G=G, resampler=1, arith=arith, seed=99, filter_id=3, mu=mu, npop=npop)
+        assert o["collapsed"] == 0
+        neg0 = (o["X_hist"][0] < 0).any(axis=1)
+        assert neg0.any()
+        assert not neg0[o["ancestry"][1]].any()
+        assert (o["X_hist"][1:] >= 0).all()
