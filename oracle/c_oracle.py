@@ -120,9 +120,10 @@ def ssa(model, G, x0, theta, max_time, arith=0, u=None, seed=None, sim_index=0, 
         if over.value:
             raise RuntimeError("replay buffer exhausted")
     else:
+        # no event log asked for: null buffers, so that the uniformized orders run as such (they have no event times)
         pairs = lib().so_ssa_philox(C.c_int(model), C.c_int(G), _p(x), _p(theta), C.c_double(max_time), C.c_int(arith),
-                                    C.c_uint64(seed), C.c_uint32(sim_index), _p(times), _p(states),
-                                    C.c_int64(max_rec), C.byref(nrec))
+                                    C.c_uint64(seed), C.c_uint32(sim_index), _p(times if max_rec > 0 else None),
+                                    _p(states if max_rec > 0 else None), C.c_int64(max_rec), C.byref(nrec))
     n = min(nrec.value, max_rec)
     return dict(x=x, pairs=int(pairs), n_rec=int(nrec.value), times=times[:n], states=states[:n])
 
