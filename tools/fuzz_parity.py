@@ -1,6 +1,6 @@
 """Randomised parity sweep (not collected by pytest): random configurations on the GPU against the C oracle, bit for bit.
 
-    python tools/fuzz_parity.py [cases] [seed] [mode ...]          modes: filter simulate abc peer   (default: all four)
+    python tools/fuzz_parity.py [cases] [seed] [mode ...]          modes: filter simulate abc peer dropin iteration   (default: all)
 
 filter    particle filter: model, sizes, population, parameters, observation model, interval simulation, resampler, several
           filters per launch, CTA shape (balanced / sorted / helper layouts), kernel (offspring form, grid barrier, launch per
@@ -8,6 +8,9 @@ filter    particle filter: model, sizes, population, parameters, observation mod
           (states, ancestors, event counts, status; log-likelihoods to 1e-11; trajectory of the chosen particle)
 simulate  sem_ssa_simulate: final states of batches of runs, per-run parameters and initial states, all interval simulations
 abc       sem_abc_run: sampled parameters, trajectories, distances, event count
+dropin    sem_b200.particle_filter (the reference's call: host numpy in, float64 numpy out, arith / kernel chosen by `auto`)
+iteration engine.PreparedIteration (what particle_mcmc runs): a batch of proposals with per-filter theta and p_obs, several
+          launches on the same buffers
 peer      the device-side exchange with 2..4 ranks' kernels on this GPU == the single-rank filter (and through it the oracle)
 """
 import os, sys
@@ -19,9 +22,10 @@ from oracle import c_oracle as co
 
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 60
 rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
-modes = sys.argv[3:] or ["filter", "simulate", "abc", "peer"]
+modes = sys.argv[3:] or ["filter", "simulate", "abc", "peer", "dropin", "iteration"]
 bad = 0
-stats = dict(filters_compared_in_full=0, filters_collapsed=0, peer_compared_in_full=0, peer_collapsed=0, abc_accepted=0, sim_runs=0)
+stats = dict(filters_compared_in_full=0, filters_collapsed=0, peer_compared_in_full=0, peer_collapsed=0, abc_accepted=0, sim_runs=0,
+             dropin_compared_in_full=0, dropin_collapsed=0, iterations_compared_in_full=0, iterations_collapsed=0)
 
 
 def cols(model, G):
@@ -230,7 +234,87 @@ def fuzz_peer(k):
         print("ERROR", tag, repr(e), flush=True)
 
 
-run = dict(filter=fuzz_filter, simulate=fuzz_simulate, abc=fuzz_abc, peer=fuzz_peer)
+def fuzz_dropin(k):
+    global bad
+    model, G, theta = random_model((0, 0, 1, 2, 3))
+    N = int(rng.choice([8, 100, 1000, 4000]))
+    T = int(rng.randint(2, 12))
+    pop = int(rng.choice([40, 300, 4820, 20000]))
+    normal = bool(rng.randint(2))
+    probs = float(rng.uniform(.05, .5))
+    rs = str(rng.choice(["systematic", "systematic", "multinomial"]))
+    i0 = max(1, int(pop * rng.choice([.005, .05, .2])))
+    npop, mu, truth = truth_and_init(model, theta, pop, i0, T)
+    Y = workloads.observe_normal(truth, probs, seed=k) if normal else workloads.observe_binomial(truth, probs, seed=k)
+    seed = int(rng.randint(1, 2**31)); fid = int(rng.randint(0, 1000))
+    mt = [sem_b200.ModelType.SIR, sem_b200.ModelType.SEIR, sem_b200.ModelType.SIR_SUBGROUPS, sem_b200.ModelType.SIR_SUBGROUPS2][model]
+    th_in = np.array(theta) if model < 2 else (np.array(theta[:4]).reshape(2, 2), theta[4])      # (betas, gamma) like pmcmc.py:214-215
+    tag = f"dropin {k}: model {model} N {N} T {T} pop {pop} normal {normal} resampler {rs} mu {mu} theta {np.round(theta, 3).tolist()} seed {seed} fid {fid}"
+    try:
+        arith = engine.resolve_arith(model, "auto", theta=np.array(theta), n_particles=N)
+        z, H, A = sem_b200.particle_filter(Y, mt, th_in, normal, probs, N, npop if model >= 2 else pop, mu if model >= 2 else mu[0],
+                                           resampler=rs, seed=seed, filter_id=fid)
+        ref = co.pf_run(model, Y, theta, normal, probs, N, G=G, resampler=int(rs == "systematic"), arith=arith, seed=seed, filter_id=fid, mu=mu, npop=npop)
+        stats["dropin_compared_in_full" if z is not None else "dropin_collapsed"] += 1
+        ok = (z is None) == (ref["collapsed"] != 0)
+        if ok and z is not None:
+            ok = (z.dtype == H.dtype == A.dtype == np.float64 and np.array_equal(H, ref["X_hist"].astype(np.float64)) and
+                  np.array_equal(A, ref["ancestry"].astype(np.float64)) and np.allclose(z, np.exp(ref["log_zetas"]), rtol=1e-10, atol=0) and
+                  np.allclose(np.log(z[z > 0]), ref["log_zetas"][z > 0], rtol=1e-11, atol=1e-11))    # (zetas, like the reference's, underflow to 0)
+        if not ok:
+            bad += 1
+            print("MISMATCH", tag, flush=True)
+    except Exception as e:                                   # noqa: BLE001
+        bad += 1
+        print("ERROR", tag, repr(e), flush=True)
+
+
+def fuzz_iteration(k):
+    global bad
+    model, G, theta = random_model((0, 0, 1, 3))
+    arith = int(rng.choice([4, 3])) if model < 2 else 3
+    N = int(rng.choice([64, 1000, 2048, 5000]))
+    T = int(rng.randint(3, 10))
+    F = int(rng.choice([1, 2, 4, 8, 16]))
+    pop = int(rng.choice([300, 2000, 20000]))
+    normal = bool(rng.randint(2))
+    hist = True                                             # (the packed result needs the history)
+    exact = bool(rng.randint(2))
+    i0 = max(1, int(pop * rng.choice([.01, .05, .2])))
+    npop, mu, truth = truth_and_init(model, theta, pop, i0, T)
+    Y = workloads.observe_normal(truth, .2, seed=k) if normal else workloads.observe_binomial(truth, .2, seed=k)
+    seed = int(rng.randint(1, 2**31))
+    Cn = cols(model, G)
+    tag = f"iteration {k}: model {model} arith {arith} N {N} T {T} F {F} pop {pop} normal {normal} history {hist} exact {exact} mu {mu} seed {seed}"
+    try:
+        cfg = engine.make_pf_config(model, N, T, G=G, n_filters=F, observations=normal, probs=.2, resampler=1, arith=arith, seed=seed,
+                                    mu=mu, n_population=npop, store_history=hist, path_exact=exact)
+        prep = engine.PreparedIteration(cfg, Y)
+        for launch in range(3):
+            fid = int(rng.randint(0, 10**6))
+            thetas = np.array([theta] * F) * rng.uniform(.8, 1.25, (F, 1))
+            per = bool(rng.randint(2))
+            pr = rng.uniform(.1, .4, F) if per else float(rng.uniform(.1, .4))
+            it = prep.run(thetas, fid, probs=pr).copy()
+            for f in range(F):
+                ref = co.pf_run(model, Y, thetas[f], normal, pr[f] if per else pr, N, G=G, resampler=1, arith=arith, seed=seed, filter_id=fid + f, mu=mu, npop=npop)
+                st = int(it[f, 1])
+                stats["iterations_compared_in_full" if st == 0 else "iterations_collapsed"] += 1
+                ok = st == ref["collapsed"]
+                if ok and st == 0:
+                    chosen = int(it[f, 3])
+                    ok = np.isclose(it[f, 0], ref["log_zetas"][-1], rtol=1e-11, atol=1e-11) and int(it[f, 2]) == ref["n_events"] and 0 <= chosen < N
+                    if ok and hist:
+                        ok = np.array_equal(it[f, engine.ITER_HEADER:].reshape(T, Cn), co.path_sample(ref["X_hist"], ref["ancestry"], chosen, exact=exact).astype(np.float64))
+                if not ok:
+                    bad += 1
+                    print("MISMATCH", tag, "launch", launch, "filter", f, "per-filter p_obs", per, "status", st, ref["collapsed"], flush=True)
+    except Exception as e:                                   # noqa: BLE001
+        bad += 1
+        print("ERROR", tag, repr(e), flush=True)
+
+
+run = dict(dropin=fuzz_dropin, iteration=fuzz_iteration, filter=fuzz_filter, simulate=fuzz_simulate, abc=fuzz_abc, peer=fuzz_peer)
 for m in modes:
     before = bad
     for k in range(cases):
