@@ -318,10 +318,11 @@ double so_norm_logpdf(double y, double x, double probs) {
 /* per-particle log-weight = min over observed columns (pmcmc.py:179,181).  x: C doubles. */
 static double log_weight(int model, int G, int obs_kind, double probs, const double *Yrow, int Cobs, const double *x) {
     double lw = INFINITY;
-    /* extension: a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169)
-     * weighs zero; in the reference scipy returns nan for it and np.random.choice raises ValueError (pmcmc.py:193) */
+    /* a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169) has no
+     * weight: scipy returns nan for binom.pmf(k, n < 0, p) and for a negative scale of norm.pdf, np.random.choice refuses
+     * the weights and the reference's filter returns (None, None, None) (pmcmc.py:187-192).  NaN = collapse at this step. */
     const int Call = model == M_SIR ? 3 : model == M_SEIR ? 4 : 3 * G;
-    for (int c = 0; c < Call; c++) if (x[c] < 0) return -INFINITY;
+    for (int c = 0; c < Call; c++) if (x[c] < 0) return NAN;
     for (int c = 0; c < Cobs; c++) {
         double xc;
         if (model == M_SUB2) { xc = 0; for (int g = 0; g < G; g++) xc = xc + x[3 * g + c]; }   /* pmcmc.py:172-173 */

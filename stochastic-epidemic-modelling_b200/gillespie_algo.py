@@ -22,8 +22,31 @@ def _max_rows(model, x0):
     return int((2 * x[:, 0] + x[:, 1]).sum()) + 2
 
 
+def _check_propensities(model, G, x0, theta):
+    """The reference raises ValueError("probabilities are not non-negative") from np.random.choice when a propensity is
+    negative (gillespie_algo.py:63,134,209-212) -- a negative count next to a live infection, or a negative rate
+    constant.  Same error here, before anything is launched (the kernels themselves fire no events from such a state,
+    DESIGN section 2, D9)."""
+    x = np.asarray(x0, dtype=np.float64).reshape(-1)
+    th = np.asarray(theta, dtype=np.float64).reshape(-1)
+    n_tot = x.sum()
+    if not n_tot > 0:
+        return
+    if model == 0:
+        alive, rates = x[1] > 0, [th[0] * x[0] * x[1] / n_tot, th[1] * x[1]]
+    elif model == 1:
+        alive, rates = (x[1] > 0) or (x[2] > 0), [th[0] * x[0] * x[2] / n_tot, th[1] * x[1], th[2] * x[2]]
+    else:
+        xs = x.reshape(G, 3)
+        alive = xs[:, 1].sum() > 0
+        rates = [th[a * G + b] * xs[b, 0] * xs[a, 1] / n_tot for a in range(G) for b in range(G)] + [th[G * G] * xs[a, 1] for a in range(G)]
+    if alive and min(rates) < 0:
+        raise ValueError("probabilities are not non-negative")
+
+
 def _run_one(model, G, x0, theta, max_time, last_values_only, names, seed, arith, replay_u):
     seed = engine.new_seed() if seed is None else seed
+    _check_propensities(model, G, x0, theta)
     replay = None
     if replay_u is not None:
         replay_u = np.asarray(replay_u, dtype=np.float64)

@@ -444,6 +444,15 @@ def test_negative_rates_are_refused_on_the_host():
     for bad in ([-.4, .2], np.array([[.4, .2], [.4, -1e-9]])):
         with pytest.raises(ValueError, match="not non-negative"):
             engine.check_rates(bad)
+    # the drop-in simulators: a negative count next to a live infection is the reference's ValueError (gillespie_algo.py:63;
+    # tests/golden/negative_s0_reference.npz holds the reference's own message), without one the loop never runs
+    import sem_b200
+    chk = sem_b200.gillespie_algo._check_propensities
+    chk(0, 1, [10, 5, 0], [1.2, .4]); chk(0, 1, [-1, 0, 0], [1.2, .4]); chk(2, 2, [[3, 1, 0], [2, 5, 0]], [2.7, 1.7, 1.8, 1.2, .9])
+    for model, G, x0, th in [(0, 1, [-1, 5, 0], [1.2, .4]), (1, 1, [10, -1, 5, 0], [1, 1, 1]), (2, 2, [[3, 0, 0], [-1, 5, 0]], [2.7, 1.7, 1.8, 1.2, .9])]:
+        with pytest.raises(ValueError, match="not non-negative"):
+            chk(model, G, x0, th)
+    assert "non-negative" in str(golden("negative_s0_reference")["simulator_error"])
 
 
 def test_lookahead_mh_has_the_law_of_the_sequential_loop(monkeypatch):

@@ -280,9 +280,9 @@ def test_daily_rows_of_grid_is_the_reference_selection():
 
 
 @pytest.mark.parametrize("model,G,theta,npop,mu", [(0, 1, [1.2, .4], [6], [4]), (3, 2, [2.7, 1.7, 1.8, 1.2, .9], [3, 4], [0, 1])])
-def test_negative_counts_weigh_zero_and_never_propagate(c_oracle, model, G, theta, npop, mu):
-    """S0 = n_population - Poisson(mu) can be negative (pmcmc.py:156-169; the reference then raises in
-    np.random.choice).  Such a particle weighs zero: it is nobody's ancestor, and no later state holds a negative count."""
+def test_negative_counts_collapse_the_filter(c_oracle, model, G, theta, npop, mu):
+    """S0 = n_population - Poisson(mu) can be negative (pmcmc.py:156-169); scipy has no weight for such
+    a particle (nan) and the reference's filter returns (None, None, None) (pmcmc.py:187-192): collapse at the first step."""
     import workloads
     T, N = 4, 1000
     truth = (workloads.subgroups_truth(((npop[0] - mu[0], mu[0], 0), (npop[1] - mu[1], mu[1], 0)), T, np.array(theta[:4]).reshape(2, 2), theta[4]).reshape(T, 2, 3).sum(1)
@@ -290,8 +290,16 @@ def test_negative_counts_weigh_zero_and_never_propagate(c_oracle, model, G, thet
     Y = workloads.observe_binomial(truth, .4, seed=7)
     for arith in (1, 3, 4) if model == 0 else (1, 3):
         o = c_oracle.pf_run(model, Y, theta, False, .4, N, G=G, resampler=1, arith=arith, seed=99, filter_id=3, mu=mu, npop=npop)
-        assert o["collapsed"] == 0
-        neg0 = (o["X_hist"][0] < 0).any(axis=1)
-        assert neg0.any()
-        assert not neg0[o["ancestry"][1]].any()
-        assert (o["X_hist"][1:] >= 0).all()
+        assert (o["X_hist"][0] < 0).any() and o["collapsed"] == 1
+    X0 = np.tile(np.array([[2, 4, 0]], dtype=np.int32), (N, 1))          # the same sizes with valid particles only: no collapse
+    if model == 0:
+        assert c_oracle.pf_run(0, Y, theta, False, .4, N, resampler=1, arith=3, seed=99, X0=X0)["collapsed"] == 0
+
+
+def test_reference_collapses_on_a_negative_initial_count():
+    """The pin of D9: the unmodified reference, run by tests/golden/make_golden_negative.py (numpy seed 1, SIR, population 6,
+    mu 4, 1000 particles), returned (None, None, None); scipy's values for a negative n are recorded beside it."""
+    g = golden("negative_s0_reference")
+    assert bool(g["returned_none"]) and int(g["n_negative_s0"]) > 0
+    assert np.isnan(g["binom_pmf_negative_n"]).all() and np.isnan(g["norm_pdf_negative_scale"]).all()
+    assert str(g["simulator_error"]).startswith("ValueError") and "non-negative" in str(g["simulator_error"])
