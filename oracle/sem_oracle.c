@@ -295,8 +295,6 @@ static double bd0(double x, double np) {
 
 /* log binom.pmf(k | n, p) with scipy's support rules (pmcmc.py:179): k<0, k>n or non-integer k -> 0 */
 double so_binom_logpmf(double k, double n, double p) {
-    if (n < 0) return NAN;      /* scipy: nan for n < 0 -- a particle with S0 = n_population - Poisson(mu) < 0 (pmcmc.py:156-169) has no
-                                 * weight, np.random.choice refuses the weights, the filter returns None (pmcmc.py:187-192) */
     if (!(k >= 0) || k > n || k != floor(k)) return -INFINITY;
     double q = 1 - p;
     if (p == 0) return k == 0 ? 0.0 : -INFINITY;
@@ -320,6 +318,11 @@ double so_norm_logpdf(double y, double x, double probs) {
 /* per-particle log-weight = min over observed columns (pmcmc.py:179,181).  x: C doubles. */
 static double log_weight(int model, int G, int obs_kind, double probs, const double *Yrow, int Cobs, const double *x) {
     double lw = INFINITY;
+    /* a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169) has no
+     * weight: scipy returns nan for binom.pmf(k, n < 0, p) and for a negative scale of norm.pdf, np.random.choice refuses
+     * the weights and the reference's filter returns (None, None, None) (pmcmc.py:187-192).  NaN = collapse at this step. */
+    const int Call = model == M_SIR ? 3 : model == M_SEIR ? 4 : 3 * G;
+    for (int c = 0; c < Call; c++) if (x[c] < 0) return NAN;
     for (int c = 0; c < Cobs; c++) {
         double xc;
         if (model == M_SUB2) { xc = 0; for (int g = 0; g < G; g++) xc = xc + x[3 * g + c]; }   /* pmcmc.py:172-173 */

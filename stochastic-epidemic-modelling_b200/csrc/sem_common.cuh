@@ -187,7 +187,6 @@ __device__ __forceinline__ double bd0_w(double x, double np, const double2 *tab)
 
 // log binom.pmf(k | n, p) with scipy's support rules (pmcmc.py:179): k<0, k>n, non-integer k -> -inf
 static __device__ __noinline__ double binom_logpmf(double k, double n, double p, const double2 *tab) {
-    if (n < 0) return CUDART_NAN;                            // scipy: nan for n < 0 (S0 = n_population - Poisson(mu) < 0)
     if (!(k >= 0) || k > n || k != floor(k)) return -CUDART_INF;
     const double q = 1 - p;
     if (p == 0) return k == 0 ? 0.0 : -CUDART_INF;

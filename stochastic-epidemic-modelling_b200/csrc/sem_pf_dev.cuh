@@ -92,6 +92,14 @@ template <class Model>
 __device__ __forceinline__ double particle_logw(const PfDev &P, const double *x, const double *Yrow, const double *wrow, const double2 *tab,
                                                 const double probs) {
     double lw = CUDART_INF;
+    // a particle holding a negative count (S0 = n_population - Poisson(mu) < 0, pmcmc.py:156-169) has
+    // no weight -- scipy returns nan for binom.pmf(k, n < 0, p) and for a negative scale of norm.pdf, np.random.choice
+    // refuses the weights and the reference's filter returns (None, None, None) (pmcmc.py:187-192): NaN here, which
+    // collapses the filter at this step in the same way (and keeps negative propensities out of the interval simulation)
+    bool neg = false;
+#pragma unroll
+    for (int c = 0; c < Model::C; c++) neg = neg || x[c] < 0.0;
+    if (neg) return CUDART_NAN;
 #pragma unroll
     for (int c = 0; c < Model::C; c++) {
         if (c < P.Cobs) {
