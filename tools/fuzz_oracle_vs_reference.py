@@ -7,8 +7,8 @@ Each case draws a random small particle-filter problem -- model, population (dow
 model and its parameter, number of particles and rows, data that may be impossible under the model -- runs the reference's
 particle_filter (pmcmc.py:123-233, jobs=1, numpy seeded) and replays the SAME uniform stream through oracle/sem_oracle.c:
 trajectories and resampling indices bit for bit, likelihoods to 1e-9 relative, and the same collapse / no-collapse verdict
-(including the reference's collapse on a negative initial count).  Then the simulators alone
-(gillespie_algo.py) with event-by-event logs.
+(including the reference's collapse on a negative initial count).  Then abc_algo (every trial the
+reference ran: trajectories, distances, accepted set) and the simulators alone (gillespie_algo.py) with event-by-event logs.
 """
 import os
 import sys
@@ -27,7 +27,7 @@ cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
 co.build()
 bad = 0
-stats = dict(pf_full=0, pf_collapsed=0, pf_negative_init=0, pf_reference_raised_on_hidden_negative=0, pf_d2_linear_underflow=0, pf_sub2_hidden_negative=0, ssa=0, ssa_events=0)
+stats = dict(pf_full=0, pf_collapsed=0, pf_negative_init=0, pf_reference_raised_on_hidden_negative=0, pf_d2_linear_underflow=0, pf_sub2_hidden_negative=0, ssa=0, ssa_events=0, abc_cases=0, abc_trials=0, abc_accepted=0)
 NAMES = ["SIR", "SEIR", "SIR_SUBGROUPS", "SIR_SUBGROUPS2"]
 
 
@@ -153,9 +153,63 @@ def fuzz_ssa(k):
         print("MISMATCH", tag, flush=True)
 
 
+def fuzz_abc(k):
+    """abc_algo (abc_algo.py:17-109): every trial the reference ran -- its prior draw, Poisson-perturbed start and the
+    MT19937 state at the simulator's entry are captured -- replayed through the oracle: day-by-day trajectories, distance,
+    and the accepted set in the reference's order."""
+    global bad
+    T = int(rng.randint(3, 10))
+    pop = int(rng.choice([20, 80, 400]))
+    i0 = max(1, pop // int(rng.choice([5, 20])))
+    beta, gamma = float(rng.uniform(.5, 2.5)), float(rng.uniform(.2, 1))
+    t = np.arange(T)
+    I = np.minimum(i0 * np.exp((beta - gamma) * t * .5), pop * .6); R = np.minimum(gamma * np.cumsum(I), pop * .4)
+    truth = np.stack([np.maximum(pop - I - R, 0), I, R], 1)
+    obs = truth + rng.normal(0, .1 * truth + 1e-12)
+    pri = {"beta": [0, float(rng.uniform(2, 5))], "gamma": [float(rng.choice([0, .1])), float(rng.uniform(1, 3))]}
+    thr = float(rng.choice([.08, .15, .3]) * pop)
+    want = int(rng.choice([1, 2, 4]))
+    seed = int(rng.randint(0, 2**31 - 1))
+    tag = f"abc {k}: T {T} pop {pop} priors {pri} threshold {thr} samples {want} seed {seed}"
+    import signal
+
+    def too_long(*_):
+        raise TimeoutError
+    signal.signal(signal.SIGALRM, too_long)
+    signal.alarm(45)                                         # the reference samples until `want` trials are accepted
+    try:
+        ref = ref_harness.run_abc(obs, want, thr, pri, seed)
+    except TimeoutError:
+        stats["abc_skipped_slow"] = stats.get("abc_skipped_slow", 0) + 1
+        return
+    finally:
+        signal.alarm(0)
+    tr = ref["trials"]
+    n = len(tr)
+    cap = 2 * (3 * int(max(x["n_start"].sum() for x in tr)) + 8)
+    us = [mt_doubles(x["mt_key"], x["mt_pos"], cap) for x in tr]
+    out = co.abc_trials(obs, n, thr, theta=np.array([x["theta"] for x in tr]), n_start=np.array([x["n_start"] for x in tr]),
+                        ssa_u=np.concatenate(us), ssa_off=np.arange(n + 1) * cap)
+    stats["abc_cases"] += 1; stats["abc_trials"] += n
+    d = np.array([x["distance"] for x in tr])
+    acc = out["distance"] <= thr
+    stats["abc_accepted"] += int(acc.sum())
+    ok = (np.allclose(out["distance"], d, rtol=1e-13, atol=0) and
+          np.array_equal(out["traj"][:, :, 1], np.array([x["I_sim"] for x in tr]).astype(np.int32)) and
+          np.array_equal(out["traj"][:, :, 2], np.array([x["R_sim"] for x in tr]).astype(np.int32)) and
+          np.array_equal(out["theta"][acc, 0], np.array(ref["posterior"]["beta"])) and
+          np.array_equal(out["theta"][acc, 1], np.array(ref["posterior"]["gamma"])) and
+          np.array_equal(out["traj"][acc], ref["trajectories"][:, :, 1:].astype(np.int32)))
+    if not ok:
+        bad += 1
+        print("MISMATCH", tag, flush=True)
+
+
 for k in range(cases):
     fuzz_pf(k)
+for k in range(max(1, cases // 4)):
+    fuzz_abc(k)
 for k in range(cases):
     fuzz_ssa(k)
-print(f"{cases} filters + {cases} simulations against the unmodified reference: {bad} bad; {stats}")
+print(f"{cases} filters + {max(1, cases // 4)} ABC runs + {cases} simulations against the unmodified reference: {bad} bad; {stats}")
 sys.exit(1 if bad else 0)
