@@ -1,7 +1,7 @@
 """Randomised pin of the C oracle to the UNMODIFIED reference (CPU only; needs /root/reference, so it runs in the build
 container, not on the GPU box; not collected by pytest):
 
-    python tools/fuzz_oracle_vs_reference.py [cases] [seed]
+    python tools/fuzz_oracle_vs_reference.py [cases] [seed] [pf] [abc] [ssa]      (default: all three parts)
 
 Each case draws a random small particle-filter problem -- model, population (down to a handful), parameters, observation
 model and its parameter, number of particles and rows, data that may be impossible under the model -- runs the reference's
@@ -25,6 +25,7 @@ from oracle import c_oracle as co, ref_harness  # noqa: E402
 warnings.filterwarnings("ignore")
 cases = int(sys.argv[1]) if len(sys.argv) > 1 else 100
 rng = np.random.RandomState(int(sys.argv[2]) if len(sys.argv) > 2 else 1)
+parts = sys.argv[3:] or ["pf", "abc", "ssa"]
 co.build()
 bad = 0
 stats = dict(pf_full=0, pf_collapsed=0, pf_negative_init=0, pf_reference_raised_on_hidden_negative=0, pf_d2_linear_underflow=0, pf_sub2_hidden_negative=0, ssa=0, ssa_events=0, abc_cases=0, abc_trials=0, abc_accepted=0)
@@ -205,11 +206,12 @@ def fuzz_abc(k):
         print("MISMATCH", tag, flush=True)
 
 
-for k in range(cases):
+n_abc = max(1, cases // 4)
+for k in range(cases if "pf" in parts else 0):
     fuzz_pf(k)
-for k in range(max(1, cases // 4)):
+for k in range(n_abc if "abc" in parts else 0):
     fuzz_abc(k)
-for k in range(cases):
+for k in range(cases if "ssa" in parts else 0):
     fuzz_ssa(k)
-print(f"{cases} filters + {max(1, cases // 4)} ABC runs + {cases} simulations against the unmodified reference: {bad} bad; {stats}")
+print(f"{cases} filters + {n_abc} ABC runs + {cases} simulations ({' '.join(parts)}) against the unmodified reference: {bad} bad; {stats}")
 sys.exit(1 if bad else 0)
