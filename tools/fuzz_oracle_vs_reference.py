@@ -213,5 +213,5 @@ for k in range(n_abc if "abc" in parts else 0):
     fuzz_abc(k)
 for k in range(cases if "ssa" in parts else 0):
     fuzz_ssa(k)
-print(f"{cases} filters + {n_abc} ABC runs + {cases} simulations ({' '.join(parts)}) against the unmodified reference: {bad} bad; {stats}")
+print(f"{cases if 'pf' in parts else 0} filters + {n_abc if 'abc' in parts else 0} ABC runs + {cases if 'ssa' in parts else 0} simulations against the unmodified reference: {bad} bad; {stats}")
 sys.exit(1 if bad else 0)
