@@ -108,7 +108,11 @@ typedef struct sem_pf_config {
 typedef struct sem_pf_buffers {
     const double *Y;            /* device [T][n_obs_cols] */
     const double *theta;        /* device [n_filters][P]; P = 2 (SIR: beta,gamma), 3 (SEIR: beta,alpha,gamma),
-                                   G*G+1 (subgroups: betas row-major [infector][susceptible], gamma) */
+                                   G*G+1 (subgroups: betas row-major [infector][susceptible], gamma).
+                                   PRECONDITION: every rate constant >= 0 -- the reference rejects negative proposals before
+                                   it calls the filter (pmcmc.py:333-337) and its simulators raise on a negative propensity
+                                   (gillespie_algo.py:63); the event loops here do not end under one.  The Python layer checks
+                                   host inputs (engine.check_rates); a C caller holding theta on the device must do the same. */
     const int32_t *X0;          /* device [C][N] initial state shared by all filters, or NULL = draw
                                    I_0 ~ Poisson(mu) on the device */
     /* replay mode (all three NULL = Philox).  Uniforms in the reference's consumption order:        */
