@@ -1,7 +1,7 @@
 """Randomised pin of the C oracle to the UNMODIFIED reference (CPU only; needs /root/reference, so it runs in the build
 container, not on the GPU box; not collected by pytest):
 
-    python tools/fuzz_oracle_vs_reference.py [cases] [seed] [pf] [abc] [ssa]      (default: all three parts)
+    python tests/fuzz_oracle_vs_reference.py [cases] [seed] [pf] [abc] [ssa]      (default: all three parts)
 
 Each case draws a random small particle-filter problem -- model, population (down to a handful), parameters, observation
 model and its parameter, number of particles and rows, data that may be impossible under the model -- runs the reference's
@@ -18,7 +18,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))  # conftest helpers
 from conftest import mt_doubles  # noqa: E402
 from oracle import c_oracle as co, ref_harness  # noqa: E402
 

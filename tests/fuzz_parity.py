@@ -1,6 +1,6 @@
 """Randomised parity sweep (not collected by pytest): random configurations on the GPU against the C oracle, bit for bit.
 
-    python tools/fuzz_parity.py [cases] [seed] [mode ...]          modes: filter simulate abc peer dropin iteration   (default: all)
+    python tests/fuzz_parity.py [cases] [seed] [mode ...]          modes: filter simulate abc peer dropin iteration   (default: all)
 
 filter    particle filter: model, sizes, population, parameters, observation model, interval simulation, resampler, several
           filters per launch, CTA shape (balanced / sorted / helper layouts), kernel (offspring form, grid barrier, launch per

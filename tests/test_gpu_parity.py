@@ -939,7 +939,7 @@ def test_many_ctas_global_prefix_path(sem, c_oracle):
 
 
 @pytest.mark.parametrize("model,G,theta,npop,mu,arith,resampler", [
-    (3, 2, [2.665, 1.706, 1.764, 1.242, 0.934], [3, 4], [0, 1], 3, 1),    # the case tools/fuzz_parity.py found (Poisson(1) > 4)
+    (3, 2, [2.665, 1.706, 1.764, 1.242, 0.934], [3, 4], [0, 1], 3, 1),    # the case tests/fuzz_parity.py found (Poisson(1) > 4)
     (0, 1, [1.2, .4], [6], [4], 4, 1), (0, 1, [1.2, .4], [6], [4], 3, 0), (1, 1, [2.0, .5, .4], [5], [3], 3, 1)])
 def test_negative_initial_susceptibles_collapse_like_the_reference(sem, c_oracle, model, G, theta, npop, mu, arith, resampler):
     """pmcmc.py:156-169 sets S0 = n_population - Poisson(mu) without a clamp: with a tiny population some particles start
